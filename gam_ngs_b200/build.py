@@ -1,0 +1,40 @@
+"""Builds the native library IN-TREE (gam_ngs_b200/libgamx.so) for sm_100a.
+
+The built .so is git-ignored but travels with gpurun snapshots, so the GPU box never
+needs to compile.  nvcc cross-compiles without a GPU.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libgamx.so")
+SOURCES = [os.path.join(CSRC, "gamx.cu")]
+HEADERS = [os.path.join(CSRC, f) for f in
+           ("bsw_common.h", "bsw_warp.h", "bsw_generic.h", "bsw_traceback.h", "bsw_host.h")] + \
+          [os.path.join(os.path.dirname(HERE), "include", "gamx.h")]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,281 @@
+"""ctypes binding of the C ABI in include/gamx.h (libgamx.so).
+
+This is plumbing only: every alignment is computed by the CUDA kernels behind the C ABI.
+There is no CPU fallback; creating a Context without a usable CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+MODE_SCORE, MODE_ENDPOINTS, MODE_FULL = 0, 1, 2
+JOB_OK, JOB_EMPTY, JOB_OUT_OF_RANGE, JOB_UNDEFINED = 0, 1, 2, 3
+DEFAULT_BAND, DEFAULT_GAP = 150, -8
+U64_MAX = 2**64 - 1
+
+
+class GamxJob(C.Structure):
+    _fields_ = [
+        ("a_id", C.c_uint32), ("b_id", C.c_uint32),
+        ("a_rc", C.c_uint8), ("b_rc", C.c_uint8),
+        ("force_start", C.c_uint8), ("force_end", C.c_uint8),
+        ("mode", C.c_uint8), ("reserved_", C.c_uint8 * 3),
+        ("a_off", C.c_uint64), ("a_len", C.c_uint64),
+        ("b_off", C.c_uint64), ("b_len", C.c_uint64),
+        ("begin_a", C.c_uint64), ("end_a", C.c_uint64),
+        ("begin_b", C.c_uint64), ("end_b", C.c_uint64),
+        ("band", C.c_uint32), ("gap", C.c_int32),
+    ]
+
+
+class GamxResult(C.Structure):
+    _fields_ = [
+        ("status", C.c_int32), ("has_match", C.c_int32), ("score", C.c_int64),
+        ("begin_a", C.c_uint64), ("begin_b", C.c_uint64), ("a_size", C.c_uint64), ("b_size", C.c_uint64),
+        ("n_ops", C.c_uint64), ("n_match", C.c_uint64),
+        ("n_mismatch", C.c_uint64), ("n_gap_a", C.c_uint64), ("n_gap_b", C.c_uint64),
+        ("homology", C.c_double),
+        ("first_match_a", C.c_uint64), ("first_match_b", C.c_uint64),
+        ("last_match_a", C.c_uint64), ("last_match_b", C.c_uint64),
+        ("last_pos_a", C.c_uint64), ("last_pos_b", C.c_uint64),
+        ("gaps_a", C.c_uint64), ("gaps_b", C.c_uint64),
+        ("end_i", C.c_int64), ("end_j", C.c_int64),
+        ("x_size", C.c_uint64), ("ops_offset", C.c_uint64),
+    ]
+
+
+JOB_DTYPE = np.dtype([
+    ("a_id", "<u4"), ("b_id", "<u4"), ("a_rc", "u1"), ("b_rc", "u1"), ("force_start", "u1"),
+    ("force_end", "u1"), ("mode", "u1"), ("reserved_", "u1", (3,)),
+    ("a_off", "<u8"), ("a_len", "<u8"), ("b_off", "<u8"), ("b_len", "<u8"),
+    ("begin_a", "<u8"), ("end_a", "<u8"), ("begin_b", "<u8"), ("end_b", "<u8"),
+    ("band", "<u4"), ("gap", "<i4")], align=True)
+
+RESULT_DTYPE = np.dtype([
+    ("status", "<i4"), ("has_match", "<i4"), ("score", "<i8"),
+    ("begin_a", "<u8"), ("begin_b", "<u8"), ("a_size", "<u8"), ("b_size", "<u8"),
+    ("n_ops", "<u8"), ("n_match", "<u8"), ("n_mismatch", "<u8"), ("n_gap_a", "<u8"), ("n_gap_b", "<u8"),
+    ("homology", "<f8"),
+    ("first_match_a", "<u8"), ("first_match_b", "<u8"), ("last_match_a", "<u8"), ("last_match_b", "<u8"),
+    ("last_pos_a", "<u8"), ("last_pos_b", "<u8"), ("gaps_a", "<u8"), ("gaps_b", "<u8"),
+    ("end_i", "<i8"), ("end_j", "<i8"), ("x_size", "<u8"), ("ops_offset", "<u8")], align=True)
+
+assert JOB_DTYPE.itemsize == C.sizeof(GamxJob), (JOB_DTYPE.itemsize, C.sizeof(GamxJob))
+assert RESULT_DTYPE.itemsize == C.sizeof(GamxResult), (RESULT_DTYPE.itemsize, C.sizeof(GamxResult))
+
+EXPORTS = [
+    "gamx_abi_version", "gamx_create", "gamx_destroy", "gamx_device_count", "gamx_last_error",
+    "gamx_add_contig", "gamx_add_contig_ascii", "gamx_contig_length", "gamx_clear_contigs",
+    "gamx_ops_capacity", "gamx_align_batch", "gamx_unpack_ops", "gamx_cigar_rle",
+    "gamx_plan_create", "gamx_plan_run", "gamx_plan_sync", "gamx_plan_fetch", "gamx_plan_last_ms",
+    "gamx_plan_cells", "gamx_plan_kernel_launches", "gamx_plan_destroy", "gamx_measure_int_peak",
+]
+
+_lib = None
+
+
+class GamxError(RuntimeError):
+    pass
+
+
+def load_library(build_if_missing: bool = True):
+    """Loads gam_ngs_b200/libgamx.so (building it in-tree with nvcc when absent)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing and _build.needs_build():
+        _build.build()
+    if not os.path.exists(_build.LIB):
+        raise GamxError("libgamx.so is missing: run `python -m gam_ngs_b200.build`")
+    L = C.CDLL(_build.LIB)
+    vp, u64, u8p = C.c_void_p, C.c_uint64, C.POINTER(C.c_uint8)
+    L.gamx_abi_version.restype = C.c_int
+    L.gamx_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
+    L.gamx_create.restype = C.c_int
+    L.gamx_destroy.argtypes = [vp]
+    L.gamx_destroy.restype = None
+    L.gamx_device_count.argtypes = [vp]
+    L.gamx_device_count.restype = C.c_int
+    L.gamx_last_error.argtypes = [vp]
+    L.gamx_last_error.restype = C.c_char_p
+    L.gamx_add_contig.argtypes = [vp, u8p, u64]
+    L.gamx_add_contig.restype = C.c_int64
+    L.gamx_add_contig_ascii.argtypes = [vp, C.c_char_p, u64]
+    L.gamx_add_contig_ascii.restype = C.c_int64
+    L.gamx_contig_length.argtypes = [vp, C.c_uint32]
+    L.gamx_contig_length.restype = u64
+    L.gamx_clear_contigs.argtypes = [vp]
+    L.gamx_clear_contigs.restype = C.c_int
+    L.gamx_ops_capacity.argtypes = [vp, vp, u64]
+    L.gamx_ops_capacity.restype = u64
+    L.gamx_align_batch.argtypes = [vp, vp, u64, vp, vp, u64]
+    L.gamx_align_batch.restype = C.c_int
+    L.gamx_unpack_ops.argtypes = [vp, u64, u64, vp]
+    L.gamx_unpack_ops.restype = None
+    L.gamx_cigar_rle.argtypes = [vp, u64, u64, vp, u64]
+    L.gamx_cigar_rle.restype = u64
+    L.gamx_plan_create.argtypes = [vp, vp, u64, C.POINTER(vp)]
+    L.gamx_plan_create.restype = C.c_int
+    for f in ("gamx_plan_run", "gamx_plan_sync"):
+        getattr(L, f).argtypes = [vp]
+        getattr(L, f).restype = C.c_int
+    L.gamx_plan_fetch.argtypes = [vp, vp, vp, u64]
+    L.gamx_plan_fetch.restype = C.c_int
+    L.gamx_plan_last_ms.argtypes = [vp]
+    L.gamx_plan_last_ms.restype = C.c_float
+    L.gamx_plan_cells.argtypes = [vp]
+    L.gamx_plan_cells.restype = u64
+    L.gamx_plan_kernel_launches.argtypes = [vp]
+    L.gamx_plan_kernel_launches.restype = u64
+    L.gamx_plan_destroy.argtypes = [vp]
+    L.gamx_plan_destroy.restype = None
+    L.gamx_measure_int_peak.argtypes = [vp, C.c_int, C.c_int]
+    L.gamx_measure_int_peak.restype = C.c_double
+    _lib = L
+    return L
+
+
+def make_jobs(n: int) -> np.ndarray:
+    """Zeroed job array with the reference's defaults (band 150, gap -8, whole contigs)."""
+    jobs = np.zeros(n, dtype=JOB_DTYPE)
+    jobs["a_len"] = U64_MAX
+    jobs["b_len"] = U64_MAX
+    jobs["band"] = DEFAULT_BAND
+    jobs["gap"] = DEFAULT_GAP
+    jobs["mode"] = MODE_ENDPOINTS
+    return jobs
+
+
+class Plan:
+    """A validated, sharded batch whose descriptors are resident on the devices."""
+
+    def __init__(self, ctx: "Context", jobs: np.ndarray):
+        self.ctx = ctx
+        self.n = len(jobs)
+        self.jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+        self._h = C.c_void_p()
+        ctx._check(ctx.lib.gamx_plan_create(ctx._h, self.jobs.ctypes.data, self.n, C.byref(self._h)))
+        self.ops_capacity = int(ctx.lib.gamx_ops_capacity(ctx._h, self.jobs.ctypes.data, self.n))
+
+    def run(self):
+        self.ctx._check(self.ctx.lib.gamx_plan_run(self._h))
+
+    def sync(self):
+        self.ctx._check(self.ctx.lib.gamx_plan_sync(self._h))
+
+    def fetch(self):
+        results = np.zeros(self.n, dtype=RESULT_DTYPE)
+        ops = np.zeros((self.ops_capacity + 3) // 4 + 8, dtype=np.uint8)
+        self.ctx._check(self.ctx.lib.gamx_plan_fetch(self._h, results.ctypes.data, ops.ctypes.data,
+                                                     self.ops_capacity))
+        return results, ops
+
+    @property
+    def last_ms(self) -> float:
+        return float(self.ctx.lib.gamx_plan_last_ms(self._h))
+
+    @property
+    def cells(self) -> int:
+        return int(self.ctx.lib.gamx_plan_cells(self._h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.ctx.lib.gamx_plan_kernel_launches(self._h))
+
+    def close(self):
+        if self._h:
+            self.ctx.lib.gamx_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    def __init__(self, devices=None):
+        self.lib = load_library()
+        self._h = C.c_void_p()
+        if devices is None:
+            rc = self.lib.gamx_create(C.byref(self._h), None, 0)
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.lib.gamx_create(C.byref(self._h), arr, len(devices))
+        if rc != 0:
+            raise GamxError(f"gamx_create failed with {rc}: no usable CUDA device "
+                            "(this package has no CPU fallback)")
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise GamxError(f"gamx error {rc}: {self.lib.gamx_last_error(self._h).decode()}")
+
+    @property
+    def device_count(self) -> int:
+        return self.lib.gamx_device_count(self._h)
+
+    def add_contig(self, codes) -> int:
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        cid = self.lib.gamx_add_contig(self._h, codes.ctypes.data_as(C.POINTER(C.c_uint8)), len(codes))
+        if cid < 0:
+            self._check(int(cid))
+        return int(cid)
+
+    def add_contig_ascii(self, seq: str | bytes) -> int:
+        if isinstance(seq, str):
+            seq = seq.encode()
+        cid = self.lib.gamx_add_contig_ascii(self._h, seq, len(seq))
+        if cid < 0:
+            self._check(int(cid))
+        return int(cid)
+
+    def clear_contigs(self):
+        self._check(self.lib.gamx_clear_contigs(self._h))
+
+    def ops_capacity(self, jobs: np.ndarray) -> int:
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+        return int(self.lib.gamx_ops_capacity(self._h, jobs.ctypes.data, len(jobs)))
+
+    def align_batch(self, jobs: np.ndarray):
+        """Host buffers in, host buffers out (the end-to-end path): returns (results, ops)."""
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+        n = len(jobs)
+        cap = self.ops_capacity(jobs) if (jobs["mode"] == MODE_FULL).any() else 0
+        results = np.zeros(n, dtype=RESULT_DTYPE)
+        ops = np.zeros((cap + 3) // 4 + 8, dtype=np.uint8)
+        self._check(self.lib.gamx_align_batch(self._h, jobs.ctypes.data, n, results.ctypes.data,
+                                              ops.ctypes.data, cap))
+        return results, ops
+
+    def plan(self, jobs: np.ndarray) -> Plan:
+        return Plan(self, jobs)
+
+    def unpack_ops(self, ops: np.ndarray, offset: int, n_ops: int) -> np.ndarray:
+        out = np.zeros(n_ops, dtype=np.uint8)
+        self.lib.gamx_unpack_ops(ops.ctypes.data, offset, n_ops, out.ctypes.data)
+        return out
+
+    def cigar_rle(self, ops: np.ndarray, offset: int, n_ops: int):
+        runs = np.zeros(max(n_ops, 1), dtype=np.uint32)
+        n = self.lib.gamx_cigar_rle(ops.ctypes.data, offset, n_ops, runs.ctypes.data, len(runs))
+        runs = runs[:n]
+        return [(int(r & 3), int(r >> 2)) for r in runs]
+
+    def measure_int_peak(self, which: int = 0, dev_index: int = 0) -> float:
+        return float(self.lib.gamx_measure_int_peak(self._h, dev_index, which))
+
+    def close(self):
+        if self._h:
+            self.lib.gamx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,759 @@
+// libgamx.so - sm_100a kernels and the C-ABI host layer (include/gamx.h).
+//
+// Kernels
+//   k1_kernel<C, DIRS>   warp-per-pair banded DP (body: bsw_warp.h), persistent warps pulling
+//                        jobs from a device counter; DIRS adds the 2-bit direction store and
+//                        the on-device traceback / edit-string emission.
+//   generic_kernel       one thread per job, literal restatement of the reference for the
+//                        jobs outside K1's parameter range (body: bsw_generic.h).
+//   intpeak_kernel<W>    register-only issue-rate microbenchmarks for the roofline denominator.
+//
+// Host layer: contig store (2-bit + N mask, pinned staging, async upload), batch planning
+// (guards of banded_smith_waterman.cc:90-97, classification, cost-balanced sharding over the
+// context's devices), launch, gather.  No CPU compute path exists here: if CUDA is not usable
+// every entry point fails.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gamx.h"
+#include "bsw_common.h"
+#include "bsw_generic.h"
+#include "bsw_host.h"
+#include "bsw_traceback.h"
+#include "bsw_warp.h"
+
+using namespace gamx;
+
+// =============================================================================================
+// device code
+// =============================================================================================
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+
+struct DevWarp {
+  __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31); }
+  __device__ __forceinline__ int shfl_up(int v, int d) const { return __shfl_up_sync(0xffffffffu, v, d); }
+  __device__ __forceinline__ int shfl_down(int v, int d) const { return __shfl_down_sync(0xffffffffu, v, d); }
+  __device__ __forceinline__ int shfl_xor(int v, int m) const { return __shfl_xor_sync(0xffffffffu, v, m); }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
+
+template <int C, bool DIRS>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k1_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counter, SeqStore store,
+          uint32_t* __restrict__ dirs, uint64_t slot_stride, uint32_t* __restrict__ ops,
+          DevResult* __restrict__ results) {
+  __shared__ WarpSmem<C> sm[kWarpsPerBlock];
+  DevWarp w;
+  const int warp = (int)(threadIdx.x >> 5);
+  const uint64_t slot = (uint64_t)blockIdx.x * kWarpsPerBlock + warp;
+  uint32_t* my_dirs = DIRS ? dirs + slot * slot_stride : nullptr;
+  for (;;) {
+    int j = 0;
+    if (w.lane() == 0) j = atomicAdd(counter, 1);
+    j = __shfl_sync(0xffffffffu, j, 0);
+    if (j >= n_jobs) break;
+    const DevJob J = jobs[j];
+    warp_align<C, DIRS>(w, J, store, sm[warp], my_dirs, ops, &results[j]);
+  }
+}
+
+__global__ void __launch_bounds__(64)
+generic_kernel(const GenJob* __restrict__ jobs, int n_jobs, SeqStore store, int64_t* __restrict__ rows,
+               uint32_t* __restrict__ dirs, uint32_t* __restrict__ ops, DevResult* __restrict__ results) {
+  const int j = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (j >= n_jobs) return;
+  const GenJob J = jobs[j];
+  DevResult R;
+  generic_align(J, store, rows + J.rows_off, dirs + J.dirs_off, ops, R);
+  results[j] = R;
+}
+
+// ---- issue-rate microbenchmarks -------------------------------------------------------------
+template <int WHICH>
+__global__ void __launch_bounds__(256) intpeak_kernel(int* out, int iters, int seed) {
+  int a0 = seed + (int)threadIdx.x, a1 = a0 ^ 0x55, a2 = a0 + 7, a3 = a0 * 3;
+  int a4 = a0 + 11, a5 = a0 ^ 0x33, a6 = a0 - 5, a7 = a0 * 5;
+  const int b = seed | 1, c = seed ^ 0x1234;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      if (WHICH == 0) {
+        a0 = __viaddmax_s32(a0, b, c); a1 = __viaddmax_s32(a1, b, c); a2 = __viaddmax_s32(a2, b, c); a3 = __viaddmax_s32(a3, b, c);
+        a4 = __viaddmax_s32(a4, b, c); a5 = __viaddmax_s32(a5, b, c); a6 = __viaddmax_s32(a6, b, c); a7 = __viaddmax_s32(a7, b, c);
+      } else if (WHICH == 1) {
+        a0 = __vimax3_s32(a0, b, a1); a1 = __vimax3_s32(a1, c, a2); a2 = __vimax3_s32(a2, b, a3); a3 = __vimax3_s32(a3, c, a4);
+        a4 = __vimax3_s32(a4, b, a5); a5 = __vimax3_s32(a5, c, a6); a6 = __vimax3_s32(a6, b, a7); a7 = __vimax3_s32(a7, c, a0);
+      } else if (WHICH == 2) {
+        a0 = (int)__viaddmax_s16x2((unsigned)a0, (unsigned)b, (unsigned)c); a1 = (int)__viaddmax_s16x2((unsigned)a1, (unsigned)b, (unsigned)c);
+        a2 = (int)__viaddmax_s16x2((unsigned)a2, (unsigned)b, (unsigned)c); a3 = (int)__viaddmax_s16x2((unsigned)a3, (unsigned)b, (unsigned)c);
+        a4 = (int)__viaddmax_s16x2((unsigned)a4, (unsigned)b, (unsigned)c); a5 = (int)__viaddmax_s16x2((unsigned)a5, (unsigned)b, (unsigned)c);
+        a6 = (int)__viaddmax_s16x2((unsigned)a6, (unsigned)b, (unsigned)c); a7 = (int)__viaddmax_s16x2((unsigned)a7, (unsigned)b, (unsigned)c);
+      } else if (WHICH == 3) {
+        a0 = (a0 & b) ^ c; a1 = (a1 & b) ^ c; a2 = (a2 & b) ^ c; a3 = (a3 & b) ^ c;
+        a4 = (a4 & b) ^ c; a5 = (a5 & b) ^ c; a6 = (a6 & b) ^ c; a7 = (a7 & b) ^ c;
+      } else if (WHICH == 4) {
+        a0 = (int)__byte_perm((unsigned)a0, (unsigned)b, (unsigned)c); a1 = (int)__byte_perm((unsigned)a1, (unsigned)b, (unsigned)c);
+        a2 = (int)__byte_perm((unsigned)a2, (unsigned)b, (unsigned)c); a3 = (int)__byte_perm((unsigned)a3, (unsigned)b, (unsigned)c);
+        a4 = (int)__byte_perm((unsigned)a4, (unsigned)b, (unsigned)c); a5 = (int)__byte_perm((unsigned)a5, (unsigned)b, (unsigned)c);
+        a6 = (int)__byte_perm((unsigned)a6, (unsigned)b, (unsigned)c); a7 = (int)__byte_perm((unsigned)a7, (unsigned)b, (unsigned)c);
+      } else {
+        a0 = a0 * b + c; a1 = a1 * b + c; a2 = a2 * b + c; a3 = a3 * b + c;
+        a4 = a4 * b + c; a5 = a5 * b + c; a6 = a6 * b + c; a7 = a7 * b + c;
+      }
+    }
+  }
+  const int r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+  if (r == 0x7fffffff) out[0] = r;  // keeps the chain alive, practically never taken
+}
+
+}  // namespace
+
+// =============================================================================================
+// host code
+// =============================================================================================
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct Device {
+  int id = 0;
+  int sm_count = 0;
+  size_t total_mem = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DevBuf packed, nmask;           // contig store replica
+  uint64_t uploaded_words_p = 0;  // words of packed/nmask already on the device
+  uint64_t uploaded_words_n = 0;
+  DevBuf jobs, gjobs, results, dirs, ops, grows, gdirs, counters, peak;
+  PinBuf h_jobs, h_gjobs, h_results, h_ops, h_stage;
+};
+
+struct gamx_ctx {
+  std::vector<Device> devs;
+  HostStore store;
+  std::mutex mu;
+  std::string err;
+};
+
+namespace {
+
+#define CU(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      char buf_[512];                                                                    \
+      snprintf(buf_, sizeof(buf_), "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, \
+               cudaGetErrorString(e_));                                                  \
+      ctx->err = buf_;                                                                   \
+      return GAMX_ERR_CUDA;                                                              \
+    }                                                                                    \
+  } while (0)
+
+int ensure_dev(gamx_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return GAMX_OK;
+  if (b.p) CU(cudaFree(b.p));
+  b.p = nullptr; b.cap = 0;
+  size_t want = bytes + bytes / 4 + 256;
+  if (cudaMalloc(&b.p, want) != cudaSuccess) {
+    cudaGetLastError();
+    want = bytes;
+    CU(cudaMalloc(&b.p, want));
+  }
+  b.cap = want;
+  return GAMX_OK;
+}
+int ensure_pin(gamx_ctx* ctx, PinBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return GAMX_OK;
+  if (b.p) CU(cudaFreeHost(b.p));
+  b.p = nullptr; b.cap = 0;
+  const size_t want = bytes + bytes / 4 + 256;
+  CU(cudaHostAlloc(&b.p, want, cudaHostAllocPortable));
+  b.cap = want;
+  return GAMX_OK;
+}
+
+// uploads the not-yet-resident tail of the host store to one device through pinned staging
+int sync_store(gamx_ctx* ctx, Device& d) {
+  CU(cudaSetDevice(d.id));
+  const HostStore& hs = ctx->store;
+  const uint64_t wp = hs.packed.size(), wn = hs.nmask.size();
+  if (wp == 0) return GAMX_OK;
+  if (d.packed.cap < wp * 4 || d.nmask.cap < wn * 4) {
+    // grow: re-upload everything into fresh buffers
+    d.uploaded_words_p = d.uploaded_words_n = 0;
+    if (int rc = ensure_dev(ctx, d.packed, wp * 4 * 2)) return rc;
+    if (int rc = ensure_dev(ctx, d.nmask, wn * 4 * 2)) return rc;
+  }
+  // the last uploaded word may have been extended by a later contig's padding: re-send from one word back
+  uint64_t fp = d.uploaded_words_p > 2 ? d.uploaded_words_p - 2 : 0;
+  uint64_t fn = d.uploaded_words_n > 2 ? d.uploaded_words_n - 2 : 0;
+  if (fp >= wp && fn >= wn) return GAMX_OK;
+  const size_t chunk = 32u << 20;
+  if (int rc = ensure_pin(ctx, d.h_stage, chunk)) return rc;
+  auto send = [&](const uint32_t* src, uint64_t from, uint64_t to, void* dst) -> int {
+    while (from < to) {
+      const uint64_t n = std::min<uint64_t>(to - from, chunk / 4);
+      memcpy(d.h_stage.p, src + from, n * 4);
+      CU(cudaMemcpyAsync((uint32_t*)dst + from, d.h_stage.p, n * 4, cudaMemcpyHostToDevice, d.stream));
+      CU(cudaStreamSynchronize(d.stream));  // staging buffer is reused
+      from += n;
+    }
+    return GAMX_OK;
+  };
+  if (int rc = send(hs.packed.data(), fp, wp, d.packed.p)) return rc;
+  if (int rc = send(hs.nmask.data(), fn, wn, d.nmask.p)) return rc;
+  d.uploaded_words_p = wp;
+  d.uploaded_words_n = wn;
+  return GAMX_OK;
+}
+
+struct Group {
+  int c = 0;          // stripe width (0: generic)
+  bool dirs = false;  // K1 with direction store
+  std::vector<uint32_t> job_idx;  // indices into the batch
+  uint64_t max_dir_words = 0;
+  uint32_t res_off = 0;  // offset of this group's results in the device result array
+  uint32_t job_off = 0;  // offset into the device job array (DevJob or GenJob)
+  int grid = 0;
+};
+
+struct DevPlan {
+  int dev = 0;
+  std::vector<Group> groups;
+  uint32_t n_jobs = 0, n_dev_jobs = 0, n_gen_jobs = 0;
+  uint64_t ops_words = 0;  // device ops buffer size
+  uint64_t ops_base = 0;   // position (in ops) of this device's buffer in the caller's ops_buf
+  uint64_t dirs_words = 0, grows = 0, gdirs = 0;
+  float last_ms = 0.f;
+};
+
+}  // namespace
+
+struct gamx_plan {
+  gamx_ctx* ctx = nullptr;
+  uint64_t n = 0;
+  std::vector<Prepared> preps;
+  std::vector<uint8_t> modes;
+  std::vector<int> job_dev;       // device of each job (-1: early)
+  std::vector<uint32_t> job_res;  // index into that device's result array
+  std::vector<DevPlan> dps;
+  uint64_t cells = 0;
+  uint64_t launches = 0;
+  uint64_t ops_total = 0;  // ops capacity over all devices
+  bool ran = false;
+};
+
+namespace {
+
+template <int C, bool DIRS>
+int launch_k1_t(gamx_ctx* ctx, Device& d, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
+                uint64_t stride, uint32_t* ops, DevResult* results) {
+  SeqStore st{(const uint32_t*)d.packed.p, (const uint32_t*)d.nmask.p};
+  k1_kernel<C, DIRS><<<g.grid, kWarpsPerBlock * 32, 0, d.stream>>>(jobs, (int)g.job_idx.size(), counter, st, dirs,
+                                                                  stride, ops, results);
+  CU(cudaGetLastError());
+  return GAMX_OK;
+}
+
+template <int C, bool DIRS>
+int occupancy_k1_t(int* blocks_per_sm) {
+  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k1_kernel<C, DIRS>, kWarpsPerBlock * 32, 0);
+}
+
+#define GAMX_FOR_EACH_C(M) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11) M(12) M(13) M(14) M(15) M(16) M(17)
+
+int k1_blocks_per_sm(int c, bool dirs) {
+  int b = 0;
+  cudaError_t e = cudaErrorInvalidValue;
+  switch (c) {
+#define M(N) case N: e = (cudaError_t)(dirs ? occupancy_k1_t<N, true>(&b) : occupancy_k1_t<N, false>(&b)); break;
+    GAMX_FOR_EACH_C(M)
+#undef M
+    default: break;
+  }
+  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+  return b;
+}
+
+int launch_k1(gamx_ctx* ctx, Device& d, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
+              uint64_t stride, uint32_t* ops, DevResult* results) {
+  switch (g.c) {
+#define M(N) case N: return g.dirs ? launch_k1_t<N, true>(ctx, d, g, jobs, counter, dirs, stride, ops, results) \
+                                    : launch_k1_t<N, false>(ctx, d, g, jobs, counter, dirs, stride, ops, results);
+    GAMX_FOR_EACH_C(M)
+#undef M
+    default: ctx->err = "internal: bad stripe width"; return GAMX_ERR_INVALID;
+  }
+}
+
+bool resolve_views(const gamx_ctx* ctx, const gamx_job& j, SeqView* va, uint64_t* la, SeqView* vb, uint64_t* lb) {
+  const HostStore& hs = ctx->store;
+  if (j.a_id >= hs.start.size() || j.b_id >= hs.start.size()) return false;
+  const uint64_t ca = hs.length[j.a_id], cb = hs.length[j.b_id];
+  if (j.a_off > ca || j.b_off > cb) return false;
+  uint64_t al = j.a_len == UINT64_MAX ? ca - j.a_off : j.a_len;
+  uint64_t bl = j.b_len == UINT64_MAX ? cb - j.b_off : j.b_len;
+  if (al > ca - j.a_off || bl > cb - j.b_off) return false;
+  *va = make_view(hs.start[j.a_id], ca, j.a_rc != 0, j.a_off);
+  *vb = make_view(hs.start[j.b_id], cb, j.b_rc != 0, j.b_off);
+  *la = al; *lb = bl;
+  return true;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int gamx_abi_version(void) { return GAMX_ABI_VERSION; }
+
+int gamx_create(gamx_ctx** out, const int* device_ids, int n_devices) {
+  if (!out) return GAMX_ERR_INVALID;
+  *out = nullptr;
+  int visible = 0;
+  if (cudaGetDeviceCount(&visible) != cudaSuccess || visible <= 0) {
+    cudaGetLastError();
+    return GAMX_ERR_NO_DEVICE;
+  }
+  gamx_ctx* ctx = new gamx_ctx();
+  if (n_devices <= 0) n_devices = visible;
+  for (int i = 0; i < n_devices; i++) {
+    Device d;
+    d.id = device_ids ? device_ids[i] : i;
+    if (d.id < 0 || d.id >= visible) { delete ctx; return GAMX_ERR_INVALID; }
+    cudaDeviceProp prop;
+    if (cudaSetDevice(d.id) != cudaSuccess || cudaGetDeviceProperties(&prop, d.id) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&d.ev0) != cudaSuccess || cudaEventCreate(&d.ev1) != cudaSuccess) {
+      cudaGetLastError();
+      delete ctx;
+      return GAMX_ERR_CUDA;
+    }
+    d.sm_count = prop.multiProcessorCount;
+    d.total_mem = prop.totalGlobalMem;
+    ctx->devs.push_back(d);
+  }
+  *out = ctx;
+  return GAMX_OK;
+}
+
+void gamx_destroy(gamx_ctx* ctx) {
+  if (!ctx) return;
+  for (Device& d : ctx->devs) {
+    cudaSetDevice(d.id);
+    cudaStreamSynchronize(d.stream);
+    DevBuf* dbs[] = {&d.packed, &d.nmask, &d.jobs, &d.gjobs, &d.results, &d.dirs, &d.ops, &d.grows, &d.gdirs, &d.counters, &d.peak};
+    for (DevBuf* b : dbs) if (b->p) cudaFree(b->p);
+    PinBuf* pbs[] = {&d.h_jobs, &d.h_gjobs, &d.h_results, &d.h_ops, &d.h_stage};
+    for (PinBuf* b : pbs) if (b->p) cudaFreeHost(b->p);
+    cudaEventDestroy(d.ev0);
+    cudaEventDestroy(d.ev1);
+    cudaStreamDestroy(d.stream);
+  }
+  delete ctx;
+}
+
+int gamx_device_count(const gamx_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+const char* gamx_last_error(const gamx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int64_t gamx_add_contig(gamx_ctx* ctx, const uint8_t* codes, uint64_t len) {
+  if (!ctx || (!codes && len)) return GAMX_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (len >= (1ull << 31)) { ctx->err = "contig longer than 2^31 bases"; return GAMX_ERR_INVALID; }
+  return ctx->store.add(codes, len);
+}
+
+int64_t gamx_add_contig_ascii(gamx_ctx* ctx, const char* seq, uint64_t len) {
+  if (!ctx || (!seq && len)) return GAMX_ERR_INVALID;
+  std::vector<uint8_t> codes(len);
+  for (uint64_t i = 0; i < len; i++) codes[i] = ascii_to_code(seq[i]);
+  return gamx_add_contig(ctx, codes.data(), len);
+}
+
+uint64_t gamx_contig_length(const gamx_ctx* ctx, uint32_t id) {
+  return (ctx && id < ctx->store.length.size()) ? ctx->store.length[id] : 0;
+}
+
+int gamx_clear_contigs(gamx_ctx* ctx) {
+  if (!ctx) return GAMX_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->store.clear();
+  for (Device& d : ctx->devs) d.uploaded_words_p = d.uploaded_words_n = 0;
+  return GAMX_OK;
+}
+
+uint64_t gamx_ops_capacity(const gamx_ctx* ctx, const gamx_job* jobs, uint64_t n) {
+  if (!ctx || !jobs) return 0;
+  uint64_t total = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    if (jobs[i].mode != GAMX_MODE_FULL) continue;
+    SeqView va, vb;
+    uint64_t la, lb;
+    if (!resolve_views(ctx, jobs[i], &va, &la, &vb, &lb)) continue;
+    Prepared P = prepare_job(va, la, vb, lb, jobs[i].begin_a, jobs[i].end_a, jobs[i].begin_b, jobs[i].end_b,
+                             jobs[i].band, jobs[i].gap, jobs[i].force_start != 0, jobs[i].force_end != 0, jobs[i].mode);
+    total += P.ops_cap;
+  }
+  return total;
+}
+
+// ---- plans ------------------------------------------------------------------------------------
+
+static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan** out) {
+  gamx_plan* pl = new gamx_plan();
+  pl->ctx = ctx;
+  pl->n = n;
+  pl->preps.resize(n);
+  pl->modes.resize(n);
+  pl->job_dev.assign(n, -1);
+  pl->job_res.assign(n, 0);
+  const int nd = (int)ctx->devs.size();
+  pl->dps.resize(nd);
+  for (int d = 0; d < nd; d++) pl->dps[d].dev = d;
+
+  std::vector<uint32_t> order;
+  order.reserve(n);
+  for (uint64_t i = 0; i < n; i++) {
+    const gamx_job& j = jobs[i];
+    SeqView va, vb;
+    uint64_t la, lb;
+    if (j.mode > GAMX_MODE_FULL || !resolve_views(ctx, j, &va, &la, &vb, &lb)) {
+      ctx->err = "job " + std::to_string(i) + ": unknown contig id, view outside the contig, or bad mode";
+      delete pl;
+      return GAMX_ERR_INVALID;
+    }
+    pl->modes[i] = j.mode;
+    pl->preps[i] = prepare_job(va, la, vb, lb, j.begin_a, j.end_a, j.begin_b, j.end_b, j.band, j.gap,
+                               j.force_start != 0, j.force_end != 0, j.mode);
+    pl->cells += pl->preps[i].cells;
+    if (pl->preps[i].cls != kClassEarly) order.push_back((uint32_t)i);
+  }
+  // cost-balanced sharding (longest-processing-time greedy on DP cells); no collective is needed,
+  // every job is independent
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return pl->preps[x].cells > pl->preps[y].cells; });
+  std::vector<uint64_t> load(nd, 0);
+  std::vector<std::vector<uint32_t>> per_dev(nd);
+  for (uint32_t i : order) {
+    int best = 0;
+    for (int d = 1; d < nd; d++) if (load[d] < load[best]) best = d;
+    load[best] += pl->preps[i].cells + 1;
+    per_dev[best].push_back(i);
+    pl->job_dev[i] = best;
+  }
+  // per device: group by kernel family
+  uint64_t ops_base = 0;
+  for (int d = 0; d < nd; d++) {
+    DevPlan& dp = pl->dps[d];
+    dp.n_jobs = (uint32_t)per_dev[d].size();
+    std::vector<Group> groups;
+    auto find_group = [&](int c, bool dirs) -> Group& {
+      for (Group& g : groups) if (g.c == c && g.dirs == dirs) return g;
+      Group g; g.c = c; g.dirs = dirs;
+      groups.push_back(g);
+      return groups.back();
+    };
+    for (uint32_t i : per_dev[d]) {
+      Prepared& P = pl->preps[i];
+      if (P.cls == kClassWarp) {
+        Group& g = find_group(P.c, pl->modes[i] != GAMX_MODE_SCORE);
+        g.job_idx.push_back(i);
+        g.max_dir_words = std::max(g.max_dir_words, P.dir_words);
+      } else {
+        Group& g = find_group(0, true);
+        g.job_idx.push_back(i);
+      }
+    }
+    uint32_t res_off = 0, dj_off = 0, gj_off = 0;
+    uint64_t ops_words = 0;
+    for (Group& g : groups) {
+      g.res_off = res_off;
+      res_off += (uint32_t)g.job_idx.size();
+      if (g.c) { g.job_off = dj_off; dj_off += (uint32_t)g.job_idx.size(); }
+      else { g.job_off = gj_off; gj_off += (uint32_t)g.job_idx.size(); }
+      for (size_t k = 0; k < g.job_idx.size(); k++) {
+        const uint32_t i = g.job_idx[k];
+        Prepared& P = pl->preps[i];
+        pl->job_res[i] = g.res_off + (uint32_t)k;
+        if (g.c) { P.dj.ops_word = ops_words; }
+        else {
+          P.gj.ops_word = ops_words;
+          P.gj.rows_off = dp.grows; dp.grows += P.gen_rows;
+          P.gj.dirs_off = dp.gdirs; dp.gdirs += P.dir_words;
+        }
+        ops_words += P.ops_cap / 16;
+      }
+    }
+    dp.groups = groups;
+    dp.n_dev_jobs = dj_off;
+    dp.n_gen_jobs = gj_off;
+    dp.ops_words = ops_words;
+    dp.ops_base = ops_base;
+    ops_base += ops_words * 16;
+  }
+  pl->ops_total = ops_base;
+  *out = pl;
+  return GAMX_OK;
+}
+
+// uploads descriptors and sizes the scratch of every device
+static int plan_upload(gamx_plan* pl) {
+  gamx_ctx* ctx = pl->ctx;
+  for (DevPlan& dp : pl->dps) {
+    Device& d = ctx->devs[dp.dev];
+    if (dp.n_jobs == 0) continue;
+    CU(cudaSetDevice(d.id));
+    if (int rc = sync_store(ctx, d)) return rc;
+    if (int rc = ensure_pin(ctx, d.h_jobs, (size_t)dp.n_dev_jobs * sizeof(DevJob))) return rc;
+    if (int rc = ensure_pin(ctx, d.h_gjobs, (size_t)dp.n_gen_jobs * sizeof(GenJob))) return rc;
+    if (int rc = ensure_dev(ctx, d.jobs, (size_t)dp.n_dev_jobs * sizeof(DevJob))) return rc;
+    if (int rc = ensure_dev(ctx, d.gjobs, (size_t)dp.n_gen_jobs * sizeof(GenJob))) return rc;
+    if (int rc = ensure_dev(ctx, d.results, (size_t)dp.n_jobs * sizeof(DevResult))) return rc;
+    if (int rc = ensure_pin(ctx, d.h_results, (size_t)dp.n_jobs * sizeof(DevResult))) return rc;
+    if (int rc = ensure_dev(ctx, d.counters, sizeof(int) * (dp.groups.size() + 1))) return rc;
+    if (int rc = ensure_dev(ctx, d.ops, dp.ops_words * 4 + 64)) return rc;
+    if (int rc = ensure_dev(ctx, d.grows, dp.grows * 8 + 64)) return rc;
+    if (int rc = ensure_dev(ctx, d.gdirs, dp.gdirs * 4 + 64)) return rc;
+    // direction scratch: one region per resident warp ("slot"), reused from job to job
+    uint64_t dirs_words = 0;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t budget_words = (uint64_t)((free_b + d.dirs.cap) * 0.8) / 4;
+    for (Group& g : dp.groups) {
+      if (!g.c) { g.grid = (int)((g.job_idx.size() + 63) / 64); continue; }
+      int bps = k1_blocks_per_sm(g.c, g.dirs);
+      if (bps <= 0) { ctx->err = "k1 kernel does not fit on the device"; return GAMX_ERR_CUDA; }
+      uint64_t grid = (uint64_t)d.sm_count * bps;
+      const uint64_t need = (g.job_idx.size() + kWarpsPerBlock - 1) / kWarpsPerBlock;
+      if (need < grid) grid = need;
+      if (g.dirs && g.max_dir_words) {
+        const uint64_t per_block = g.max_dir_words * kWarpsPerBlock;
+        if (per_block > budget_words) { ctx->err = "direction scratch of one job exceeds device memory"; return GAMX_ERR_NOMEM; }
+        if (grid * per_block > budget_words) grid = budget_words / per_block;
+        dirs_words = std::max(dirs_words, grid * per_block);
+      }
+      g.grid = (int)std::max<uint64_t>(grid, 1);
+    }
+    dp.dirs_words = dirs_words;
+    if (int rc = ensure_dev(ctx, d.dirs, dirs_words * 4 + 64)) return rc;
+    DevJob* hj = (DevJob*)d.h_jobs.p;
+    GenJob* hg = (GenJob*)d.h_gjobs.p;
+    for (const Group& g : dp.groups)
+      for (size_t k = 0; k < g.job_idx.size(); k++) {
+        if (g.c) hj[g.job_off + k] = pl->preps[g.job_idx[k]].dj;
+        else hg[g.job_off + k] = pl->preps[g.job_idx[k]].gj;
+      }
+    if (dp.n_dev_jobs)
+      CU(cudaMemcpyAsync(d.jobs.p, hj, (size_t)dp.n_dev_jobs * sizeof(DevJob), cudaMemcpyHostToDevice, d.stream));
+    if (dp.n_gen_jobs)
+      CU(cudaMemcpyAsync(d.gjobs.p, hg, (size_t)dp.n_gen_jobs * sizeof(GenJob), cudaMemcpyHostToDevice, d.stream));
+  }
+  return GAMX_OK;
+}
+
+int gamx_plan_create(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan** out) {
+  if (!ctx || !out || (!jobs && n)) return GAMX_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  *out = nullptr;
+  gamx_plan* pl = nullptr;
+  if (int rc = plan_build(ctx, jobs, n, &pl)) return rc;
+  if (int rc = plan_upload(pl)) { delete pl; return rc; }
+  *out = pl;
+  return GAMX_OK;
+}
+
+static int plan_run_locked(gamx_plan* pl) {
+  gamx_ctx* ctx = pl->ctx;
+  pl->launches = 0;
+  for (DevPlan& dp : pl->dps) {
+    if (dp.n_jobs == 0) continue;
+    Device& d = ctx->devs[dp.dev];
+    CU(cudaSetDevice(d.id));
+    CU(cudaEventRecord(d.ev0, d.stream));
+    CU(cudaMemsetAsync(d.counters.p, 0, sizeof(int) * (dp.groups.size() + 1), d.stream));
+    for (size_t gi = 0; gi < dp.groups.size(); gi++) {
+      const Group& g = dp.groups[gi];
+      DevResult* res = (DevResult*)d.results.p + g.res_off;
+      if (g.c) {
+        if (int rc = launch_k1(ctx, d, g, (const DevJob*)d.jobs.p + g.job_off, (int*)d.counters.p + gi,
+                               (uint32_t*)d.dirs.p, g.max_dir_words, (uint32_t*)d.ops.p, res))
+          return rc;
+      } else {
+        SeqStore st{(const uint32_t*)d.packed.p, (const uint32_t*)d.nmask.p};
+        generic_kernel<<<g.grid, 64, 0, d.stream>>>((const GenJob*)d.gjobs.p + g.job_off, (int)g.job_idx.size(), st,
+                                                    (int64_t*)d.grows.p, (uint32_t*)d.gdirs.p, (uint32_t*)d.ops.p, res);
+        CU(cudaGetLastError());
+      }
+      pl->launches++;
+    }
+    CU(cudaEventRecord(d.ev1, d.stream));
+  }
+  pl->ran = true;
+  return GAMX_OK;
+}
+
+int gamx_plan_run(gamx_plan* pl) {
+  if (!pl) return GAMX_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(pl->ctx->mu);
+  return plan_run_locked(pl);
+}
+
+static int plan_sync_locked(gamx_plan* pl) {
+  gamx_ctx* ctx = pl->ctx;
+  for (DevPlan& dp : pl->dps) {
+    if (dp.n_jobs == 0) continue;
+    Device& d = ctx->devs[dp.dev];
+    CU(cudaSetDevice(d.id));
+    CU(cudaStreamSynchronize(d.stream));
+    if (pl->ran) CU(cudaEventElapsedTime(&dp.last_ms, d.ev0, d.ev1));
+  }
+  return GAMX_OK;
+}
+
+int gamx_plan_sync(gamx_plan* pl) {
+  if (!pl) return GAMX_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(pl->ctx->mu);
+  return plan_sync_locked(pl);
+}
+
+static int plan_fetch_locked(gamx_plan* pl, gamx_result* results, uint8_t* ops_buf, uint64_t ops_cap) {
+  gamx_ctx* ctx = pl->ctx;
+  if (!results && pl->n) return GAMX_ERR_INVALID;
+  if (pl->ops_total > 0 && (!ops_buf || ops_cap < pl->ops_total)) {
+    ctx->err = "ops buffer too small: need " + std::to_string(pl->ops_total) + " ops";
+    return GAMX_ERR_OPS_CAPACITY;
+  }
+  for (DevPlan& dp : pl->dps) {
+    if (dp.n_jobs == 0) continue;
+    Device& d = ctx->devs[dp.dev];
+    CU(cudaSetDevice(d.id));
+    CU(cudaMemcpyAsync(d.h_results.p, d.results.p, (size_t)dp.n_jobs * sizeof(DevResult), cudaMemcpyDeviceToHost, d.stream));
+    if (dp.ops_words) {
+      if (int rc = ensure_pin(ctx, d.h_ops, dp.ops_words * 4)) return rc;
+      CU(cudaMemcpyAsync(d.h_ops.p, d.ops.p, dp.ops_words * 4, cudaMemcpyDeviceToHost, d.stream));
+    }
+  }
+  for (DevPlan& dp : pl->dps) {
+    if (dp.n_jobs == 0) continue;
+    Device& d = ctx->devs[dp.dev];
+    CU(cudaSetDevice(d.id));
+    CU(cudaStreamSynchronize(d.stream));
+    if (dp.ops_words) memcpy(ops_buf + dp.ops_base / 4, d.h_ops.p, dp.ops_words * 4);
+  }
+  for (uint64_t i = 0; i < pl->n; i++) {
+    const Prepared& P = pl->preps[i];
+    const DevResult* dr = nullptr;
+    uint64_t base = 0;
+    if (pl->job_dev[i] >= 0) {
+      const DevPlan& dp = pl->dps[pl->job_dev[i]];
+      dr = (const DevResult*)ctx->devs[dp.dev].h_results.p + pl->job_res[i];
+      base = dp.ops_base;
+    }
+    finalize_result(P, dr, pl->modes[i], &results[i]);
+    results[i].ops_offset += base;
+  }
+  return GAMX_OK;
+}
+
+int gamx_plan_fetch(gamx_plan* pl, gamx_result* results, uint8_t* ops_buf, uint64_t ops_cap) {
+  if (!pl) return GAMX_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(pl->ctx->mu);
+  if (int rc = plan_sync_locked(pl)) return rc;
+  return plan_fetch_locked(pl, results, ops_buf, ops_cap);
+}
+
+float gamx_plan_last_ms(gamx_plan* pl) {
+  if (!pl) return 0.f;
+  float m = 0.f;
+  for (const DevPlan& dp : pl->dps) m = std::max(m, dp.last_ms);
+  return m;
+}
+uint64_t gamx_plan_cells(const gamx_plan* pl) { return pl ? pl->cells : 0; }
+uint64_t gamx_plan_kernel_launches(const gamx_plan* pl) { return pl ? pl->launches : 0; }
+void gamx_plan_destroy(gamx_plan* pl) { delete pl; }
+
+int gamx_align_batch(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_result* results, uint8_t* ops_buf,
+                     uint64_t ops_cap) {
+  if (!ctx || (!jobs && n) || (!results && n)) return GAMX_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  gamx_plan* pl = nullptr;
+  int rc = plan_build(ctx, jobs, n, &pl);
+  if (rc) return rc;
+  if (pl->ops_total > 0 && (!ops_buf || ops_cap < pl->ops_total)) {
+    ctx->err = "ops buffer too small: need " + std::to_string(pl->ops_total) + " ops";
+    delete pl;
+    return GAMX_ERR_OPS_CAPACITY;
+  }
+  rc = plan_upload(pl);
+  if (!rc) rc = plan_run_locked(pl);
+  if (!rc) rc = plan_sync_locked(pl);
+  if (!rc) rc = plan_fetch_locked(pl, results, ops_buf, ops_cap);
+  delete pl;
+  return rc;
+}
+
+void gamx_unpack_ops(const uint8_t* ops_buf, uint64_t ops_offset, uint64_t n_ops, uint8_t* out) {
+  for (uint64_t k = 0; k < n_ops; k++) {
+    const uint64_t g = ops_offset + k;
+    out[k] = (uint8_t)((ops_buf[g >> 2] >> (2 * (g & 3))) & 3u);
+  }
+}
+
+uint64_t gamx_cigar_rle(const uint8_t* ops_buf, uint64_t ops_offset, uint64_t n_ops, uint32_t* runs, uint64_t cap) {
+  uint64_t n_runs = 0;
+  uint32_t cur = 0, len = 0;
+  for (uint64_t k = 0; k < n_ops; k++) {
+    const uint64_t g = ops_offset + k;
+    const uint32_t op = (ops_buf[g >> 2] >> (2 * (g & 3))) & 3u;
+    if (len && op == cur && len < (1u << 30) - 1) { len++; continue; }
+    if (len) { if (n_runs < cap && runs) runs[n_runs] = (len << 2) | cur; n_runs++; }
+    cur = op; len = 1;
+  }
+  if (len) { if (n_runs < cap && runs) runs[n_runs] = (len << 2) | cur; n_runs++; }
+  return n_runs;
+}
+
+double gamx_measure_int_peak(gamx_ctx* ctx, int dev_index, int which) {
+  if (!ctx || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return 0.0;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  Device& d = ctx->devs[dev_index];
+  if (cudaSetDevice(d.id) != cudaSuccess) return 0.0;
+  if (ensure_dev(ctx, d.peak, 256)) return 0.0;
+  const int iters = 4096, threads = 256, blocks = d.sm_count * 8;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(d.ev0, d.stream);
+    switch (which) {
+      case 0: intpeak_kernel<0><<<blocks, threads, 0, d.stream>>>((int*)d.peak.p, iters, rep + 1); break;
+      case 1: intpeak_kernel<1><<<blocks, threads, 0, d.stream>>>((int*)d.peak.p, iters, rep + 1); break;
+      case 2: intpeak_kernel<2><<<blocks, threads, 0, d.stream>>>((int*)d.peak.p, iters, rep + 1); break;
+      case 3: intpeak_kernel<3><<<blocks, threads, 0, d.stream>>>((int*)d.peak.p, iters, rep + 1); break;
+      case 4: intpeak_kernel<4><<<blocks, threads, 0, d.stream>>>((int*)d.peak.p, iters, rep + 1); break;
+      default: intpeak_kernel<5><<<blocks, threads, 0, d.stream>>>((int*)d.peak.p, iters, rep + 1); break;
+    }
+    cudaEventRecord(d.ev1, d.stream);
+    if (cudaStreamSynchronize(d.stream) != cudaSuccess) { cudaGetLastError(); return 0.0; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, d.ev0, d.ev1);
+    const double ops = (double)blocks * threads * (double)iters * 64.0;  // 8 chains x 8 unrolled
+    if (rep > 0 && ms > 0) best = std::max(best, ops / (ms * 1e-3));
+  }
+  return best;
+}
+
+}  // extern "C"

@@ -1,0 +1,192 @@
+/*
+ * gamx.h - C ABI of the B200-native banded overlap aligner (the drop-in boundary).
+ *
+ * What it replaces in the reference (vice87/gam-ngs):
+ *   BandedSmithWaterman::find_alignment
+ *       lib/include/alignment/banded_smith_waterman.hpp:68-71   (declaration)
+ *       lib/src/alignment/banded_smith_waterman.cc:69-323       (definition)
+ *   and the MyAlignment reductions gam-merge reads from its result
+ *       first_match_pos / last_match_pos / last_pos / gaps_before_last_match
+ *       lib/src/alignment/my_alignment.cc:167-296
+ *   as called from PctgBuilder::alignBlocks / findBestAlignment
+ *       lib/src/pctg/PctgBuilder.cc:1544-1607, 1669, 1698.
+ *
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.  The C++
+ * drop-in classes (gam_ngs_b200/cpp/banded_smith_waterman.hpp) and the Python binding
+ * (gam_ngs_b200/capi.py) are thin layers over these entry points.  INTEGRATION.md shows
+ * the reference-side change a maintainer would make.
+ *
+ * There is no CPU fallback: every alignment is computed by the CUDA kernels in
+ * gam_ngs_b200/csrc/.  If no CUDA device is usable, gamx_create() fails.
+ *
+ * Thread safety: a gamx_ctx serialises its own entry points with an internal mutex, so the
+ * legacy one-call-per-pthread pattern (lib/src/pctg/ThreadedBuildPctg.cc:159-169) is safe;
+ * use one batch per call (or one ctx per thread) for throughput.
+ */
+#ifndef GAMX_H_
+#define GAMX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GAMX_ABI_VERSION 1
+
+/* Base codes = the reference's BaseType, lib/include/assembly/nucleotide.hpp:35-43 */
+enum { GAMX_BASE_A = 0, GAMX_BASE_T = 1, GAMX_BASE_C = 2, GAMX_BASE_G = 3, GAMX_BASE_N = 4 };
+
+/* Edit operations = the reference's AlignmentAlphabet, lib/include/alignment/my_alignment.hpp:57-62 */
+enum { GAMX_OP_GAP_A = 0, GAMX_OP_GAP_B = 1, GAMX_OP_MATCH = 2, GAMX_OP_MISMATCH = 3 };
+
+/* Reference defaults: banded_smith_waterman.hpp:37-39, my_alignment.hpp:46 */
+#define GAMX_DEFAULT_BAND 150
+#define GAMX_DEFAULT_GAP (-8)
+#define GAMX_FORCE_MAXGAP_LEN 10
+#define GAMX_MAX_ALIGNMENT 500000
+
+/* Per-job behavioural outcome, so a C++ shim can reproduce the reference exactly. */
+enum {
+  GAMX_JOB_OK = 0,           /* an alignment was produced                                        */
+  GAMX_JOB_EMPTY = 1,        /* reference returns a default MyAlignment() (.cc:90, .cc:215)       */
+  GAMX_JOB_OUT_OF_RANGE = 2, /* reference throws std::out_of_range from Contig::at (.cc:231,:265) */
+  GAMX_JOB_UNDEFINED = 3     /* reference behaviour is undefined (x_size == 0, .cc:102-122)       */
+};
+
+/* What to compute for a job. */
+enum {
+  GAMX_MODE_SCORE = 0,     /* score + end cell only (no traceback; begin/stat fields are zero)   */
+  GAMX_MODE_ENDPOINTS = 1, /* + begin_a/begin_b, n_ops, n_match, first/last match (device traceback,
+                              no edit string copied back) - everything gam-merge reads            */
+  GAMX_MODE_FULL = 2       /* + the full edit string (2 bits per op) and run-length CIGAR         */
+};
+
+/* Infrastructure errors (negative return values). */
+enum {
+  GAMX_OK = 0,
+  GAMX_ERR_CUDA = -1,
+  GAMX_ERR_INVALID = -2,
+  GAMX_ERR_NOMEM = -3,
+  GAMX_ERR_OPS_CAPACITY = -4, /* ops buffer too small; gamx_ops_capacity() tells how much */
+  GAMX_ERR_NO_DEVICE = -5
+};
+
+typedef struct gamx_ctx gamx_ctx;
+
+/*
+ * One alignment = one find_alignment call (banded_smith_waterman.hpp:68-71).
+ * `a` and `b` are views into contigs of the context's store:
+ *   view = (rc ? reverse_complement(contig) : contig)[off, off+len)
+ * which covers reverse_complement (PctgBuilder.cc:1443) and chop_begin tails
+ * (PctgBuilder.cc:1577,1595) without re-uploading sequence.  len == UINT64_MAX means
+ * "to the end of the contig".  begin/end are in view coordinates, exactly the
+ * arguments the reference call would receive; a.size() is the view length.
+ */
+typedef struct {
+  uint32_t a_id, b_id;
+  uint8_t a_rc, b_rc;
+  uint8_t force_start, force_end;
+  uint8_t mode; /* GAMX_MODE_* */
+  uint8_t reserved_[3];
+  uint64_t a_off, a_len;
+  uint64_t b_off, b_len;
+  uint64_t begin_a, end_a, begin_b, end_b;
+  uint32_t band; /* _band_size (ctor argument, banded_smith_waterman.cc:61-67) */
+  int32_t gap;   /* _gap_score; GAMX_DEFAULT_GAP unless the 5-argument ctor is used (.cc:48-59) */
+} gamx_job;
+
+/*
+ * Result of one job.  Fields mirror MyAlignment (my_alignment.hpp:65-126) plus the
+ * reductions of my_alignment.cc:167-296 computed on the device.
+ *   homology = n_ops ? (double)(n_match*100)/(double)n_ops : 0   (banded_smith_waterman.cc:319)
+ */
+typedef struct {
+  int32_t status; /* GAMX_JOB_* */
+  int32_t has_match;
+  int64_t score;
+  uint64_t begin_a, begin_b, a_size, b_size;
+  uint64_t n_ops, n_match; /* length() and number of MATCH ops */
+  uint64_t n_mismatch, n_gap_a, n_gap_b;
+  double homology;
+  uint64_t first_match_a, first_match_b; /* first_match_pos(); valid output even if !has_match */
+  uint64_t last_match_a, last_match_b;   /* last_match_pos()                                  */
+  uint64_t last_pos_a, last_pos_b;       /* last_pos()                                        */
+  uint64_t gaps_a, gaps_b;               /* gaps_before_last_match()                          */
+  int64_t end_i, end_j;                  /* selected end cell (row, band column), .cc:174-212  */
+  uint64_t x_size;                       /* DP rows, .cc:93-95; cells = x_size*(2*band+1)      */
+  uint64_t ops_offset;                   /* FULL mode: index (in ops) of op 0 inside ops_buf   */
+} gamx_result;
+
+/* ---- lifecycle ------------------------------------------------------------------- */
+
+/* Creates a context driving the given CUDA devices (device_ids == NULL: devices 0..n-1;
+ * n_devices == 0: all visible devices).  Jobs of a batch are sharded over the devices by
+ * DP cost; results are gathered on the host; no collectives are involved. */
+int gamx_create(gamx_ctx** out, const int* device_ids, int n_devices);
+void gamx_destroy(gamx_ctx* ctx);
+int gamx_device_count(const gamx_ctx* ctx);
+const char* gamx_last_error(const gamx_ctx* ctx);
+int gamx_abi_version(void);
+
+/* ---- contig store (replaces the vector<Nucleotide> copies of PctgBuilder.cc:747-748) -- */
+
+/* Adds a contig given as base codes 0..4 (values > 4 are treated as N, like
+ * nucleotide.code.hpp:47-75 does for unknown characters).  The contig is packed to 2 bits
+ * per base plus an N bitmask and staged to every device with pinned async copies at the
+ * next batch.  Returns the contig id (>= 0) or a negative error. */
+int64_t gamx_add_contig(gamx_ctx* ctx, const uint8_t* codes, uint64_t len);
+/* Same, from FASTA characters (ACGTacgt, everything else -> N). */
+int64_t gamx_add_contig_ascii(gamx_ctx* ctx, const char* seq, uint64_t len);
+uint64_t gamx_contig_length(const gamx_ctx* ctx, uint32_t id);
+int gamx_clear_contigs(gamx_ctx* ctx);
+
+/* ---- alignment ---------------------------------------------------------------------- */
+
+/* Upper bound on the number of ops the batch can emit in FULL mode (0 for other modes). */
+uint64_t gamx_ops_capacity(const gamx_ctx* ctx, const gamx_job* jobs, uint64_t n);
+
+/* Aligns a batch.  results[n] is always filled.  ops_buf (may be NULL when no job is in FULL
+ * mode) receives the edit strings packed 2 bits per op, op k of a job at bits
+ * [2*((ops_offset+k)%4), +2) of byte (ops_offset+k)/4; ops_cap is its capacity in ops. */
+int gamx_align_batch(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_result* results,
+                     uint8_t* ops_buf, uint64_t ops_cap);
+
+/* Expands n_ops packed ops starting at ops_offset to one byte per op (GAMX_OP_*), the layout
+ * of the reference's std::vector<AlignmentAlphabet>. */
+void gamx_unpack_ops(const uint8_t* ops_buf, uint64_t ops_offset, uint64_t n_ops, uint8_t* out);
+
+/* Run-length CIGAR of a packed edit string: writes up to cap (op,len) pairs
+ * (op in the low 2 bits, length in the upper 30 of each uint32), returns the number of runs. */
+uint64_t gamx_cigar_rle(const uint8_t* ops_buf, uint64_t ops_offset, uint64_t n_ops,
+                        uint32_t* runs, uint64_t cap);
+
+/* ---- device-resident (pre-staged) batches: the kernel-only timing path -------------- */
+
+typedef struct gamx_plan gamx_plan;
+/* Validates, sorts, shards and uploads a batch once; gamx_plan_run() then only launches the
+ * kernels (inputs already resident in HBM) and gamx_plan_fetch() copies the results back. */
+int gamx_plan_create(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan** out);
+int gamx_plan_run(gamx_plan* plan);    /* asynchronous; enqueues on each device's stream */
+int gamx_plan_sync(gamx_plan* plan);   /* waits for all devices */
+int gamx_plan_fetch(gamx_plan* plan, gamx_result* results, uint8_t* ops_buf, uint64_t ops_cap);
+/* Device time of the last run in milliseconds (CUDA events on the launching streams, max
+ * over devices); kernel_ms[i] receives per-kernel-family times when not NULL (see
+ * gamx_plan_kernel_names). */
+float gamx_plan_last_ms(gamx_plan* plan);
+uint64_t gamx_plan_cells(const gamx_plan* plan);        /* sum of x_size*(2*band+1)           */
+uint64_t gamx_plan_kernel_launches(const gamx_plan* plan); /* kernels launched per run        */
+void gamx_plan_destroy(gamx_plan* plan);
+
+/* ---- microbenchmarks used for the roofline denominators (bench.py) ------------------ */
+
+/* Measures the integer/DPX issue peak of device `dev_index` of the context with a
+ * register-only kernel: which = 0 VIADDMNMX(s32), 1 VIMNMX3(s32), 2 VIADDMNMX(s16x2),
+ * 3 LOP3, 4 PRMT, 5 IMAD.  Returns lane-ops per second (1 op = 1 instruction lane). */
+double gamx_measure_int_peak(gamx_ctx* ctx, int dev_index, int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAMX_H_ */

@@ -1,0 +1,197 @@
+// TEST INFRASTRUCTURE ONLY: CPU lane simulator for the kernel bodies.
+//
+// There is no GPU in the development container, so the warp-level kernel body
+// (gam_ngs_b200/csrc/bsw_warp.h) is written against a small warp policy and executed here by
+// 32 cooperative fibers (ucontext) in SPMD fashion: every collective (shuffle / warp sync) is
+// a rendezvous of all 32 lanes, exactly like the *_sync intrinsics.  Lanes run either in
+// ascending or descending order between rendezvous points, so a missing warp sync between a
+// shared-memory write and a cross-lane read shows up as a mismatch in one of the two orders.
+//
+// The simulator shares the host-side preparation, packing and finalisation code with the
+// product (bsw_host.h), so those are exercised on the CPU too.  Nothing here is used by the
+// product path; the -m gpu tests exercise the real kernels through the C ABI.
+#include <stdint.h>
+#include <string.h>
+#include <ucontext.h>
+
+#include <vector>
+
+#include "../../gam_ngs_b200/csrc/bsw_generic.h"
+#include "../../gam_ngs_b200/csrc/bsw_host.h"
+#include "../../gam_ngs_b200/csrc/bsw_warp.h"
+
+using namespace gamx;
+
+namespace {
+
+struct Sched;
+struct SimWarp {
+  Sched* s;
+  int lane_;
+  int lane() const { return lane_; }
+  int exchange(int v, int src);
+  int shfl_up(int v, int d) { return exchange(v, lane_ - d >= 0 ? lane_ - d : lane_); }
+  int shfl_down(int v, int d) { return exchange(v, lane_ + d < 32 ? lane_ + d : lane_); }
+  int shfl_xor(int v, int m) { return exchange(v, lane_ ^ m); }
+  void sync() { exchange(0, lane_); }
+};
+
+struct Sched {
+  ucontext_t main_ctx;
+  ucontext_t ctx[32];
+  std::vector<char> stacks[32];
+  bool done[32];
+  int slot[32];
+  int arrived = 0;
+  unsigned gen = 0;
+  int cur = 0;
+  bool descending = false;
+  void (*body)(SimWarp&, void*) = nullptr;
+  void* arg = nullptr;
+  SimWarp warps[32];
+
+  void yield(int lane) { swapcontext(&ctx[lane], &main_ctx); }
+  // two-phase rendezvous: everybody publishes, then everybody reads
+  void barrier(int lane) {
+    const unsigned g = gen;
+    if (++arrived == 32) { arrived = 0; gen++; }
+    while (gen == g) yield(lane);
+  }
+  static void tramp(int lane_lo, int sp_lo, int sp_hi) {
+    Sched* s = (Sched*)(((uintptr_t)(uint32_t)sp_hi << 32) | (uint32_t)sp_lo);
+    s->body(s->warps[lane_lo], s->arg);
+    s->done[lane_lo] = true;
+    swapcontext(&s->ctx[lane_lo], &s->main_ctx);
+  }
+  void run(void (*b)(SimWarp&, void*), void* a, bool desc) {
+    body = b; arg = a; descending = desc; arrived = 0; gen = 0;
+    for (int l = 0; l < 32; l++) {
+      warps[l].s = this; warps[l].lane_ = l; done[l] = false;
+      stacks[l].assign(1 << 18, 0);
+      getcontext(&ctx[l]);
+      ctx[l].uc_stack.ss_sp = stacks[l].data();
+      ctx[l].uc_stack.ss_size = stacks[l].size();
+      ctx[l].uc_link = &main_ctx;
+      const uintptr_t p = (uintptr_t)this;
+      makecontext(&ctx[l], (void (*)())tramp, 3, l, (int)(uint32_t)p, (int)(uint32_t)(p >> 32));
+    }
+    for (;;) {
+      bool any = false;
+      for (int n = 0; n < 32; n++) {
+        const int l = descending ? 31 - n : n;
+        if (done[l]) continue;
+        any = true;
+        swapcontext(&main_ctx, &ctx[l]);
+      }
+      if (!any) break;
+    }
+  }
+};
+
+int SimWarp::exchange(int v, int src) {
+  s->slot[lane_] = v;
+  s->barrier(lane_);
+  const int r = s->slot[src];
+  s->barrier(lane_);
+  return r;
+}
+
+struct WarpArgs {
+  const DevJob* job;
+  SeqStore store;
+  void* smem;
+  uint32_t* dirs;
+  uint32_t* ops;
+  DevResult* out;
+  int c;
+  bool dirs_on;
+};
+
+template <int C>
+void body_c(SimWarp& w, void* p) {
+  WarpArgs* a = (WarpArgs*)p;
+  WarpSmem<C>& sm = *(WarpSmem<C>*)a->smem;
+  if (a->dirs_on) warp_align<C, true>(w, *a->job, a->store, sm, a->dirs, a->ops, a->out);
+  else warp_align<C, false>(w, *a->job, a->store, sm, a->dirs, a->ops, a->out);
+}
+
+template <int C>
+void dispatch(WarpArgs& a, bool desc) {
+  std::vector<uint64_t> smem((sizeof(WarpSmem<C>) + 7) / 8);
+  a.smem = smem.data();
+  Sched* s = new Sched();
+  s->run(body_c<C>, &a, desc);
+  delete s;
+}
+
+void run_warp(WarpArgs& a, bool desc) {
+  switch (a.c) {
+#define CASE(N) case N: dispatch<N>(a, desc); break;
+    CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12)
+    CASE(13) CASE(14) CASE(15) CASE(16) CASE(17)
+#undef CASE
+    default: break;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// One job through packing -> prepare_job -> kernel body (simulated warp or generic thread)
+// -> finalize_result.  a/b are the CONTIGS (codes 0..4); the job's views are taken from them.
+// force_class: 0 = as classified, 2 = force the generic body.  lane_order: 0 ascending, 1 descending.
+// ops_out receives one byte per op (FULL mode).  Returns the class that ran.
+int sim_align(const uint8_t* a, uint64_t a_clen, int a_rc, uint64_t a_off, uint64_t a_len,
+              const uint8_t* b, uint64_t b_clen, int b_rc, uint64_t b_off, uint64_t b_len,
+              uint64_t begin_a, uint64_t end_a, uint64_t begin_b, uint64_t end_b, uint64_t band,
+              int64_t gap, int fs, int fe, int mode, int force_class, int lane_order,
+              gamx_result* result, uint8_t* ops_out, uint64_t ops_out_cap) {
+  HostStore hs;
+  const int64_t ia = hs.add(a, a_clen), ib = hs.add(b, b_clen);
+  if (a_len == UINT64_MAX) a_len = a_clen - a_off;
+  if (b_len == UINT64_MAX) b_len = b_clen - b_off;
+  const SeqView va = make_view(hs.start[ia], a_clen, a_rc != 0, a_off);
+  const SeqView vb = make_view(hs.start[ib], b_clen, b_rc != 0, b_off);
+  Prepared P = prepare_job(va, a_len, vb, b_len, begin_a, end_a, begin_b, end_b, band, gap, fs != 0,
+                           fe != 0, mode);
+  if (force_class == kClassGeneric && P.cls == kClassWarp) {
+    // re-prepare as generic
+    Prepared Q = P;
+    Q.cls = kClassGeneric;
+    GenJob& g = Q.gj;
+    memset(&g, 0, sizeof(g));
+    g.a = va; g.b = vb; g.la = a_len; g.lb = b_len;
+    g.begin_a = begin_a; g.end_a = end_a; g.begin_b = begin_b; g.end_b = end_b;
+    g.band = band; g.gap = gap; g.force_start = fs; g.force_end = fe; g.mode = mode;
+    g.ops_cap = P.ops_cap; g.x_size = P.x_size;
+    Q.dir_words = (P.x_size * (2 * band + 1) + 15) / 16;
+    Q.gen_rows = 2 * (2 * band + 1);
+    P = Q;
+  }
+  SeqStore st{hs.packed.data(), hs.nmask.data()};
+  DevResult dr;
+  memset(&dr, 0, sizeof(dr));
+  std::vector<uint32_t> ops(P.ops_cap / 16 + 1, 0u);
+  if (P.cls == kClassWarp) {
+    std::vector<uint32_t> dirs(P.dir_words + 1, 0xdeadbeefu);
+    P.dj.ops_word = 0;
+    WarpArgs wa{&P.dj, st, nullptr, dirs.data(), ops.data(), &dr, P.c, mode != kModeScore};
+    run_warp(wa, lane_order != 0);
+  } else if (P.cls == kClassGeneric) {
+    std::vector<int64_t> rows(P.gen_rows + 1, 0x5a5a5a5a5a5a5a5aLL);
+    std::vector<uint32_t> dirs(P.dir_words + 1, 0xdeadbeefu);
+    P.gj.ops_word = 0;
+    generic_align(P.gj, st, rows.data(), dirs.data(), ops.data(), dr);
+  }
+  finalize_result(P, &dr, mode, result);
+  if (result->status == GAMX_JOB_OK && mode == kModeFull && ops_out) {
+    for (uint64_t k = 0; k < result->n_ops && k < ops_out_cap; k++) {
+      const uint64_t g = result->ops_offset + k;
+      ops_out[k] = (uint8_t)((ops[g >> 4] >> (2 * (g & 15))) & 3u);
+    }
+  }
+  return P.cls;
+}
+
+}  // extern "C"

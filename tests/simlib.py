@@ -1,0 +1,98 @@
+"""ctypes wrapper of the CPU lane simulator (tests/sim/warp_sim.cc) - test infrastructure."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+class GamxResult(C.Structure):
+    """include/gamx.h: gamx_result"""
+    _fields_ = [
+        ("status", C.c_int32), ("has_match", C.c_int32), ("score", C.c_int64),
+        ("begin_a", C.c_uint64), ("begin_b", C.c_uint64), ("a_size", C.c_uint64), ("b_size", C.c_uint64),
+        ("n_ops", C.c_uint64), ("n_match", C.c_uint64),
+        ("n_mismatch", C.c_uint64), ("n_gap_a", C.c_uint64), ("n_gap_b", C.c_uint64),
+        ("homology", C.c_double),
+        ("first_match_a", C.c_uint64), ("first_match_b", C.c_uint64),
+        ("last_match_a", C.c_uint64), ("last_match_b", C.c_uint64),
+        ("last_pos_a", C.c_uint64), ("last_pos_b", C.c_uint64),
+        ("gaps_a", C.c_uint64), ("gaps_b", C.c_uint64),
+        ("end_i", C.c_int64), ("end_j", C.c_int64),
+        ("x_size", C.c_uint64), ("ops_offset", C.c_uint64),
+    ]
+
+
+def result_to_expect(r, ops=None, mode=2):
+    """Normalise a gamx_result like util.oracle_expect does for the oracle."""
+    if r.status != 0:
+        return {"status": r.status}
+    d = {"status": 0, "score": r.score}
+    if mode == 0:
+        return d
+    d.update(begin_a=r.begin_a, begin_b=r.begin_b, a_size=r.a_size, b_size=r.b_size, n_ops=r.n_ops,
+             homology=r.homology,
+             has_first_match=int(r.has_match), first_match_a=r.first_match_a, first_match_b=r.first_match_b,
+             has_last_match=int(r.has_match), last_match_a=r.last_match_a, last_match_b=r.last_match_b,
+             has_last_pos=int(r.has_match), last_pos_a=r.last_pos_a, last_pos_b=r.last_pos_b,
+             has_gaps=int(r.has_match), gaps_a=r.gaps_a, gaps_b=r.gaps_b)
+    if ops is not None:
+        d["ops"] = bytes(ops[: r.n_ops])
+    return d
+
+
+def project(exp, mode):
+    """Reduce an oracle expectation to what a mode reports."""
+    if exp["status"] != 0:
+        return dict(exp)
+    if mode == 0:
+        return {"status": 0, "score": exp["score"]}
+    d = dict(exp)
+    if mode == 1:
+        d.pop("ops", None)
+    return d
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        out = os.path.join(HERE, "_build", "libwarpsim.so")
+        src = os.path.join(HERE, "sim", "warp_sim.cc")
+        deps = [src] + [os.path.join(ROOT, "gam_ngs_b200", "csrc", f) for f in
+                        ("bsw_common.h", "bsw_warp.h", "bsw_generic.h", "bsw_traceback.h", "bsw_host.h")]
+        if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            subprocess.run(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", "-shared", "-fPIC",
+                            "-o", out, src], check=True)
+        _lib = C.CDLL(out)
+        u8p, u64 = C.POINTER(C.c_uint8), C.c_uint64
+        _lib.sim_align.argtypes = [u8p, u64, C.c_int, u64, u64, u8p, u64, C.c_int, u64, u64,
+                                   u64, u64, u64, u64, u64, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.POINTER(GamxResult), u8p, u64]
+        _lib.sim_align.restype = C.c_int
+    return _lib
+
+
+U64_MAX = 2**64 - 1
+
+
+def sim_align(job, mode=2, force_class=0, lane_order=0, a_rc=0, a_off=0, a_len=U64_MAX, b_rc=0,
+              b_off=0, b_len=U64_MAX):
+    a = np.ascontiguousarray(job["a"], dtype=np.uint8)
+    b = np.ascontiguousarray(job["b"], dtype=np.uint8)
+    r = GamxResult()
+    cap = len(a) + len(b) + 2 * job["band"] + 64
+    ops = np.zeros(cap, dtype=np.uint8)
+    u8p = C.POINTER(C.c_uint8)
+    cls = lib().sim_align(a.ctypes.data_as(u8p), len(a), a_rc, a_off, a_len,
+                          b.ctypes.data_as(u8p), len(b), b_rc, b_off, b_len,
+                          job["begin_a"], job["end_a"], job["begin_b"], job["end_b"], job["band"],
+                          job["gap"], int(job["force_start"]), int(job["force_end"]), mode,
+                          force_class, lane_order, C.byref(r), ops.ctypes.data_as(u8p), cap)
+    return cls, r, ops

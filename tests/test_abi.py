@@ -1,0 +1,64 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds, loads and exports every symbol
+include/gamx.h declares; without a CUDA device the product path fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gam_ngs_b200
+from gam_ngs_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gamx.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gamx_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load_library()
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/gamx.h but not exported"
+    assert sorted(capi.EXPORTS) == declared
+    assert lib.gamx_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(capi.GamxJob) == capi.JOB_DTYPE.itemsize == 88
+    assert C.sizeof(capi.GamxResult) == capi.RESULT_DTYPE.itemsize == 192
+    for name, _ in capi.GamxJob._fields_:
+        if name != "reserved_":
+            assert getattr(capi.GamxJob, name).offset == capi.JOB_DTYPE.fields[name][1]
+    for name, _ in capi.GamxResult._fields_:
+        assert getattr(capi.GamxResult, name).offset == capi.RESULT_DTYPE.fields[name][1]
+
+
+def test_host_side_helpers_without_gpu():
+    """unpack / CIGAR helpers are pure host code in the C ABI."""
+    lib = capi.load_library()
+    ops = np.array([2, 2, 3, 0, 0, 1, 2, 2, 2], dtype=np.uint8)
+    packed = np.zeros(8, dtype=np.uint8)
+    off = 5
+    for k, op in enumerate(ops):
+        g = off + k
+        packed[g >> 2] |= op << (2 * (g & 3))
+    out = np.zeros(len(ops), dtype=np.uint8)
+    lib.gamx_unpack_ops(packed.ctypes.data, off, len(ops), out.ctypes.data)
+    assert (out == ops).all()
+    runs = np.zeros(16, dtype=np.uint32)
+    n = lib.gamx_cigar_rle(packed.ctypes.data, off, len(ops), runs.ctypes.data, 16)
+    assert [(int(r & 3), int(r >> 2)) for r in runs[:n]] == [(2, 2), (3, 1), (0, 2), (1, 1), (2, 3)]
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(gam_ngs_b200.GamxError):
+        gam_ngs_b200.Context()

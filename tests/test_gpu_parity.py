@@ -1,0 +1,232 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI
+(include/gamx.h via gam_ngs_b200.capi), against the oracle on the same seeded inputs -
+bit-exact scores, coordinates, statuses and every edit op.  Nothing here reads /root/reference:
+the checker is the C restatement (oracle/bsw_oracle.c) plus the committed golden vectors."""
+import numpy as np
+import pytest
+
+import gen
+import gam_ngs_b200 as g
+from gam_ngs_b200 import capi
+from util import load_golden, oracle_expect, x_size_of
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = g.Context(devices=[0])
+    yield c
+    c.close()
+
+
+def result_to_expect(ctx, r, ops, mode):
+    if r["status"] != 0:
+        return {"status": int(r["status"])}
+    d = {"status": 0, "score": int(r["score"])}
+    if mode == capi.MODE_SCORE:
+        return d
+    hm = int(r["has_match"])
+    d.update(begin_a=int(r["begin_a"]), begin_b=int(r["begin_b"]), a_size=int(r["a_size"]),
+             b_size=int(r["b_size"]), n_ops=int(r["n_ops"]), homology=float(r["homology"]),
+             has_first_match=hm, first_match_a=int(r["first_match_a"]), first_match_b=int(r["first_match_b"]),
+             has_last_match=hm, last_match_a=int(r["last_match_a"]), last_match_b=int(r["last_match_b"]),
+             has_last_pos=hm, last_pos_a=int(r["last_pos_a"]), last_pos_b=int(r["last_pos_b"]),
+             has_gaps=hm, gaps_a=int(r["gaps_a"]), gaps_b=int(r["gaps_b"]))
+    if mode == capi.MODE_FULL:
+        d["ops"] = bytes(ctx.unpack_ops(ops, int(r["ops_offset"]), int(r["n_ops"])))
+    return d
+
+
+def project(exp, mode):
+    if exp["status"] != 0:
+        return dict(exp)
+    if mode == capi.MODE_SCORE:
+        return {"status": 0, "score": exp["score"]}
+    d = dict(exp)
+    if mode != capi.MODE_FULL:
+        d.pop("ops", None)
+    return d
+
+
+def run_batch(ctx, cases, mode, views=None):
+    """cases: list of job dicts with raw sequences; returns normalised results."""
+    ctx.clear_contigs()
+    jobs = g.make_jobs(len(cases))
+    for k, c in enumerate(cases):
+        jobs[k]["a_id"] = ctx.add_contig(c["a"])
+        jobs[k]["b_id"] = ctx.add_contig(c["b"])
+        for f in ("begin_a", "end_a", "begin_b", "end_b", "band", "gap"):
+            jobs[k][f] = c[f]
+        jobs[k]["force_start"], jobs[k]["force_end"] = int(c["force_start"]), int(c["force_end"])
+        jobs[k]["mode"] = mode
+        if views is not None:
+            for f, v in views[k].items():
+                jobs[k][f] = v
+    res, ops = ctx.align_batch(jobs)
+    return [result_to_expect(ctx, res[k], ops, mode) for k in range(len(cases))]
+
+
+def test_golden_vectors(ctx):
+    cases = load_golden()
+    jobs = [j for j, _ in cases]
+    for mode in (capi.MODE_FULL, capi.MODE_ENDPOINTS, capi.MODE_SCORE):
+        got = run_batch(ctx, jobs, mode)
+        for k, (job, exp) in enumerate(cases):
+            if x_size_of(job) == 0:
+                exp = {"status": 3}
+            assert got[k] == project(exp, mode), (k, mode, {a: b for a, b in job.items() if a not in "ab"})
+
+
+@pytest.mark.parametrize("seed", [21, 22, 23])
+def test_fuzz_every_clamp(ctx, seed):
+    rng = np.random.default_rng(seed)
+    cases, exps = [], []
+    while len(cases) < 1500:
+        job = gen.fuzz_case(rng)
+        x = x_size_of(job)
+        if x is not None and x > 3000:
+            continue
+        cases.append(job)
+        exps.append(oracle_expect(job) if x != 0 else {"status": 3})
+    for mode in (capi.MODE_FULL, capi.MODE_SCORE):
+        got = run_batch(ctx, cases, mode)
+        for k in range(len(cases)):
+            assert got[k] == project(exps[k], mode), (k, mode, {a: b for a, b in cases[k].items() if a not in "ab"})
+
+
+@pytest.mark.parametrize("band", [0, 1, 16, 47, 64, 100, 150, 256, 271])
+def test_warp_kernel_all_stripe_widths(ctx, band):
+    rng = np.random.default_rng(2000 + band)
+    cases = []
+    for length in (70, 333, 700, 1500):
+        for _ in range(6):
+            a, b = gen.make_pair(rng, length, div=float(rng.choice([0.0, 0.02, 0.1])), p_n=0.003)
+            b = b[int(rng.integers(0, min(band // 2, length // 4) + 1)):]
+            la, lb = len(a), len(b)
+            shape = int(rng.integers(0, 3))
+            if shape == 0:
+                w = dict(begin_a=0, end_a=la - 1, begin_b=0, end_b=lb - 1, force_start=False, force_end=False)
+            elif shape == 1:
+                w = dict(begin_a=int(rng.integers(0, la // 2)), end_a=la - 1, begin_b=0, end_b=lb - 1,
+                         force_start=False, force_end=True)
+            else:
+                w = dict(begin_a=3, end_a=la + 40, begin_b=int(rng.integers(0, lb // 2)), end_b=lb + 5,
+                         force_start=True, force_end=False)
+            cases.append(dict(a=a, b=b, band=band, gap=int(rng.choice([-8, -8, -5, -29])), **w))
+    exps = [oracle_expect(c) for c in cases]
+    for mode in (capi.MODE_FULL, capi.MODE_ENDPOINTS, capi.MODE_SCORE):
+        got = run_batch(ctx, cases, mode)
+        for k in range(len(cases)):
+            assert got[k] == project(exps[k], mode), (k, mode)
+
+
+def test_config2_shape_1kb_band64(ctx):
+    """BASELINE.json configs[1] shape: 1 kb pairs, band 64, ~2% divergence (+ an N variant)."""
+    rng = np.random.default_rng(2)
+    cases = []
+    for n in range(400):
+        a, b = gen.make_pair(rng, 1000, div=0.02, p_n=0.001 if n % 4 == 0 else 0.0)
+        cases.append(dict(a=a, b=b, begin_a=0, end_a=len(a) - 1, begin_b=0, end_b=len(b) - 1, band=64,
+                          gap=-8, force_start=False, force_end=False))
+    exps = [oracle_expect(c) for c in cases]
+    for mode in (capi.MODE_ENDPOINTS, capi.MODE_FULL, capi.MODE_SCORE):
+        got = run_batch(ctx, cases, mode)
+        for k in range(len(cases)):
+            assert got[k] == project(exps[k], mode), (k, mode)
+
+
+def test_config3_shape_long_band256(ctx):
+    """BASELINE.json configs[2] shape at a size the CPU oracle finishes in seconds."""
+    rng = np.random.default_rng(3)
+    cases = []
+    for length in (10000, 17000, 25000):
+        a, b = gen.make_pair(rng, length, div=0.02, offset=int(rng.integers(0, 128)))
+        cases.append(dict(a=a, b=b, begin_a=0, end_a=len(a) - 1, begin_b=0, end_b=len(b) - 1, band=256,
+                          gap=-8, force_start=False, force_end=False))
+    exps = [oracle_expect(c) for c in cases]
+    got = run_batch(ctx, cases, capi.MODE_FULL)
+    for k in range(len(cases)):
+        assert got[k] == exps[k], k
+        assert exps[k]["n_ops"] > 9000
+
+
+def test_views_reverse_complement_and_offsets(ctx):
+    rng = np.random.default_rng(5)
+    cases, views, exps = [], [], []
+    for _ in range(40):
+        a, b = gen.make_pair(rng, int(rng.integers(150, 900)), div=0.03, p_n=0.01)
+        band = int(rng.choice([20, 64, 150]))
+        a_off, b_off = int(rng.integers(0, 40)), int(rng.integers(0, 40))
+        a_len = len(a) - a_off - int(rng.integers(0, 20))
+        b_len = len(b) - b_off - int(rng.integers(0, 20))
+        va, vb = a[a_off:a_off + a_len], b[b_off:b_off + b_len]
+        mat = dict(a=va, b=vb, begin_a=0, end_a=len(va) - 1, begin_b=0, end_b=len(vb) - 1, band=band, gap=-8,
+                   force_start=False, force_end=False)
+        exps.append(oracle_expect(mat))
+        cases.append(dict(mat, a=gen.revcomp(a), b=gen.revcomp(b)))  # store holds the reverse complement
+        views.append(dict(a_rc=1, b_rc=1, a_off=a_off, a_len=a_len, b_off=b_off, b_len=b_len))
+    got = run_batch(ctx, cases, capi.MODE_FULL, views)
+    for k in range(len(cases)):
+        assert got[k] == exps[k], k
+
+
+def test_traceback_round_trip_properties_at_scale(ctx):
+    """Size-independent properties on a larger batch than the oracle is asked to check:
+    the edit string must consume exactly the aligned spans and re-score to the DP score."""
+    rng = np.random.default_rng(9)
+    ctx.clear_contigs()
+    n = 3000
+    jobs = g.make_jobs(n)
+    seqs = []
+    for k in range(n):
+        a, b = gen.make_pair(rng, 1000, div=0.02)
+        seqs.append((a, b))
+        jobs[k]["a_id"], jobs[k]["b_id"] = ctx.add_contig(a), ctx.add_contig(b)
+        jobs[k]["end_a"], jobs[k]["end_b"] = len(a) - 1, len(b) - 1
+        jobs[k]["band"], jobs[k]["mode"] = 64, capi.MODE_FULL
+    res, ops = ctx.align_batch(jobs)
+    S = np.array([[5, -4, -4, -4, 0], [-4, 5, -4, -4, 0], [-4, -4, 5, -4, 0], [-4, -4, -4, 5, 0], [0, 0, 0, 0, 5]])
+    assert (res["status"] == 0).all()
+    for k in range(0, n, 7):
+        r = res[k]
+        o = ctx.unpack_ops(ops, int(r["ops_offset"]), int(r["n_ops"]))
+        a, b = seqs[k]
+        n_diag = int(((o == 2) | (o == 3)).sum())
+        n_ga, n_gb = int((o == 0).sum()), int((o == 1).sum())
+        assert n_ga == r["n_gap_a"] and n_gb == r["n_gap_b"] and int((o == 2).sum()) == r["n_match"]
+        # spans: a advances on diag+GAP_B, b on diag+GAP_A; the path ends at the selected end cell
+        end_a_pos = int(r["end_i"]) + int(r["end_j"]) - 64
+        assert int(r["begin_a"]) + n_diag + n_gb == end_a_pos + 1
+        assert int(r["begin_b"]) + n_diag + n_ga == int(r["end_i"]) + 1
+        # re-score (interior path: every op costs its face value when the path starts at row 0 / pos 0 with a diag)
+        pa, pb, sc = int(r["begin_a"]), int(r["begin_b"]), 0
+        for op in o:
+            if op >= 2:
+                sc += S[a[pa], b[pb]]; pa += 1; pb += 1
+            elif op == 0:
+                sc -= 8; pb += 1
+            else:
+                sc -= 8; pa += 1
+        if o[0] >= 2:
+            assert sc == r["score"], k
+
+
+def test_python_mirror_interface(ctx):
+    """The Python mirror keeps the reference's call shape and error behaviour."""
+    rng = np.random.default_rng(4)
+    a, b = gen.make_pair(rng, 400, div=0.02)
+    A, B = g.Contig(a), g.Contig(b)
+    sw = g.BandedSmithWaterman(ctx=ctx)  # band 150
+    al = sw.find_alignment(A, 0, A.size() - 1, B, 0, B.size() - 1)
+    exp = oracle_expect(dict(a=a, b=b, begin_a=0, end_a=len(a) - 1, begin_b=0, end_b=len(b) - 1, band=150,
+                             gap=-8, force_start=False, force_end=False))
+    assert (al.begin_a(), al.begin_b(), al.score(), al.length()) == (exp["begin_a"], exp["begin_b"], exp["score"], exp["n_ops"])
+    assert bytes(al.sequence()) == exp["ops"] and al.homology() == exp["homology"]
+    # default MyAlignment for an inverted b window (.cc:90)
+    e = sw.find_alignment(A, 0, 10, B, 5, 4)
+    assert (e.begin_a(), e.a_size(), e.length(), e.score()) == (0, 0, 0, 0)
+    # std::out_of_range when the chosen end cell lies beyond |a|
+    all_a, all_c = g.Contig("A" * 50), g.Contig("C" * 50)
+    with pytest.raises(IndexError):
+        g.BandedSmithWaterman(10, ctx=ctx).find_alignment(all_a, 0, 60, all_c, 0, 49)

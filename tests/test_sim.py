@@ -1,0 +1,90 @@
+"""CPU tests of the kernel bodies through the lane simulator (tests/sim/warp_sim.cc): the same
+bsw_warp.h / bsw_generic.h / bsw_host.h code the CUDA library compiles, executed by 32
+cooperative fibers, compared with the oracle.  The -m gpu tests repeat this on the device."""
+import numpy as np
+import pytest
+
+import gen
+import simlib
+from util import load_golden, oracle_expect, x_size_of
+
+
+def _check(job, exp, modes=(2, 1, 0), lane_order=0, force_class=0, **view):
+    for mode in modes:
+        cls, r, ops = simlib.sim_align(job, mode=mode, lane_order=lane_order, force_class=force_class, **view)
+        got = simlib.result_to_expect(r, ops if mode == 2 else None, mode)
+        assert got == simlib.project(exp, mode), (mode, cls, {k: v for k, v in job.items() if k not in "ab"})
+    return cls
+
+
+def test_sim_matches_golden():
+    classes = set()
+    for n, (job, exp) in enumerate(load_golden()):
+        if x_size_of(job) == 0:
+            exp = {"status": 3}
+        classes.add(_check(job, exp, lane_order=n & 1))
+    assert classes == {0, 1, 2}  # early-out, warp kernel and generic kernel all exercised
+
+
+def test_generic_body_matches_golden():
+    for job, exp in load_golden():
+        if x_size_of(job) == 0:
+            continue
+        _check(job, exp, modes=(2,), force_class=2)
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_sim_fuzz_small(seed):
+    rng = np.random.default_rng(seed)
+    n = 0
+    while n < 400:
+        job = gen.fuzz_case(rng)
+        x = x_size_of(job)
+        if x is not None and x > 3000:
+            continue
+        n += 1
+        exp = oracle_expect(job) if x != 0 else {"status": 3}
+        _check(job, exp, modes=(2, 0), lane_order=n & 1)
+
+
+@pytest.mark.parametrize("band", [0, 1, 16, 47, 64, 100, 150, 256, 271])
+def test_sim_warp_kernel_bands(band):
+    """Every lane-stripe width C = 2..17, fast path, tile refills (rows > 256), force flags."""
+    rng = np.random.default_rng(1000 + band)
+    for length in (70, 333, 700):
+        a, b = gen.make_pair(rng, length, div=0.05, p_n=0.004)
+        b = b[int(rng.integers(0, min(band // 2, length // 4) + 1)):]
+        la, lb = len(a), len(b)
+        for shape in range(3):
+            if shape == 0:
+                w = dict(begin_a=0, end_a=la - 1, begin_b=0, end_b=lb - 1, force_start=False, force_end=False)
+            elif shape == 1:
+                w = dict(begin_a=int(rng.integers(0, la // 2)), end_a=la - 1, begin_b=0, end_b=lb - 1,
+                         force_start=False, force_end=True)
+            else:
+                w = dict(begin_a=3, end_a=la + 40, begin_b=int(rng.integers(0, lb // 2)), end_b=lb + 5,
+                         force_start=True, force_end=False)
+            job = dict(a=a, b=b, band=band, gap=-8, **w)
+            cls = _check(job, oracle_expect(job), modes=(2, 0), lane_order=shape & 1)
+            assert cls == 1
+
+
+def test_sim_views_reverse_complement_and_offsets():
+    """Jobs address views (rc, offset, length) of stored contigs: must equal aligning the
+    materialised reverse-complement / chopped contig (PctgBuilder.cc:1443, :1577)."""
+    rng = np.random.default_rng(5)
+    for _ in range(12):
+        a, b = gen.make_pair(rng, int(rng.integers(150, 500)), div=0.03, p_n=0.01)
+        band = int(rng.choice([20, 64, 150]))
+        a_off = int(rng.integers(0, 40)); b_off = int(rng.integers(0, 40))
+        a_len = len(a) - a_off - int(rng.integers(0, 20)); b_len = len(b) - b_off - int(rng.integers(0, 20))
+        # the stored contigs hold the reverse complement of what the job must see
+        a_store, b_store = gen.revcomp(a), gen.revcomp(b)
+        va, vb = a[a_off:a_off + a_len], b[b_off:b_off + b_len]
+        job_mat = dict(a=va, b=vb, begin_a=0, end_a=len(va) - 1, begin_b=0, end_b=len(vb) - 1, band=band,
+                       gap=-8, force_start=False, force_end=False)
+        exp = oracle_expect(job_mat)
+        job_view = dict(job_mat, a=a_store, b=b_store)
+        _check(job_view, exp, modes=(2,), a_rc=1, a_off=a_off, a_len=a_len, b_rc=1, b_off=b_off, b_len=b_len)
+        _check(dict(job_mat, a=a, b=b_store), exp, modes=(2,), a_rc=0, a_off=a_off, a_len=a_len,
+               b_rc=1, b_off=b_off, b_len=b_len, force_class=2)
