@@ -84,11 +84,14 @@ GAMX_HD void warp_align(W& w, const DevJob& J, const SeqStore& S, WarpSmem<C>& s
   const uint32_t cdP = ((uint32_t)alpha << SH) | tagX;  // padding: score 0
 
   int H[C];
-  uint32_t A[C], acc[C];
+  // Direction words are accumulated as the difference of two multiply-add chains (both on the
+  // FMA pipe, leaving the ALU pipe to the DP): accV = 4*accV + v, accH = 4*accH + (v & ~3);
+  // accV - accH (mod 2^32) = the last 16 tags, oldest in the top bit pair.
+  uint32_t A[C], accV[C], accH[C];
   int U[C];
 #pragma unroll
   for (int k = 0; k < C; k++) {
-    H[k] = 0; A[k] = 0x7775u; acc[k] = 0;
+    H[k] = 0; A[k] = 0x7775u; accV[k] = 0; accH[k] = 0;
     U[k] = (lane == ld && k == kd) ? kBlock : (DIRS ? 1 : 0);
   }
 
@@ -156,7 +159,8 @@ GAMX_HD void warp_align(W& w, const DevJob& J, const SeqStore& S, WarpSmem<C>& s
             const int v = viaddmax(H[k], cd, m);
             if (DIRS) {
               const int hc = v & ~3;
-              acc[k] = acc[k] * 4u + (uint32_t)(v - hc);
+              accV[k] = accV[k] * 4u + (uint32_t)v;
+              accH[k] = accH[k] * 4u + (uint32_t)hc;
               H[k] = hc;
             } else {
               H[k] = v;
@@ -166,7 +170,7 @@ GAMX_HD void warp_align(W& w, const DevJob& J, const SeqStore& S, WarpSmem<C>& s
           }
           if (DIRS && (tt & 15) == 15) {
 #pragma unroll
-            for (int k = 0; k < C; k++) dirs[((size_t)(tt >> 4) * C + k) * 32 + lane] = acc[k];
+            for (int k = 0; k < C; k++) dirs[((uint32_t)(tt >> 4) * C + k) * 32 + lane] = accV[k] - accH[k];
           }
         }
         t += C;
@@ -200,7 +204,7 @@ GAMX_HD void warp_align(W& w, const DevJob& J, const SeqStore& S, WarpSmem<C>& s
               v = ((h + beta * j) << SH) | ((DIRS && h == s) ? (cd & 3) : 0);
               lt = h;
             }
-            if (DIRS) { acc[k] = acc[k] * 4u + (uint32_t)(v & 3); H[k] = v & ~3; }
+            if (DIRS) { accV[k] = accV[k] * 4u + (uint32_t)v; accH[k] = accH[k] * 4u + (uint32_t)(v & ~3); H[k] = v & ~3; }
             else H[k] = v;
           }
         } else {
@@ -208,7 +212,7 @@ GAMX_HD void warp_align(W& w, const DevJob& J, const SeqStore& S, WarpSmem<C>& s
           const int m = viaddmax(H[1 % C], U[0], left);
           const int v = viaddmax(H[0], cd, m);
           const int hc = DIRS ? (v & ~3) : v;
-          if (DIRS) acc[0] = acc[0] * 4u + (uint32_t)(v - hc);
+          if (DIRS) { accV[0] = accV[0] * 4u + (uint32_t)v; accH[0] = accH[0] * 4u + (uint32_t)hc; }
           if (act) H[0] = hc;
         }
         const int right = w.shfl_down(H[0], 1);
@@ -220,7 +224,7 @@ GAMX_HD void warp_align(W& w, const DevJob& J, const SeqStore& S, WarpSmem<C>& s
             const int m = viaddmax(up, U[k], H[k - 1]);
             const int v = viaddmax(H[k], cd, m);
             const int hc = DIRS ? (v & ~3) : v;
-            if (DIRS) acc[k] = acc[k] * 4u + (uint32_t)(v - hc);
+            if (DIRS) { accV[k] = accV[k] * 4u + (uint32_t)v; accH[k] = accH[k] * 4u + (uint32_t)hc; }
             if (act) H[k] = hc;
           }
         }
@@ -240,7 +244,7 @@ GAMX_HD void warp_align(W& w, const DevJob& J, const SeqStore& S, WarpSmem<C>& s
         if (DIRS && ((t & 15) == 15 || t == T_total - 1)) {
           const int sh = 2 * (15 - (t & 15));
 #pragma unroll
-          for (int k = 0; k < C; k++) dirs[((size_t)(t >> 4) * C + k) * 32 + lane] = acc[k] << sh;
+          for (int k = 0; k < C; k++) dirs[((uint32_t)(t >> 4) * C + k) * 32 + lane] = (accV[k] - accH[k]) << sh;
         }
         t++;
       }
@@ -280,8 +284,7 @@ GAMX_HD void warp_align(W& w, const DevJob& J, const SeqStore& S, WarpSmem<C>& s
       if (p0 + ei + ej >= la) {
         R.status = kStatusOutOfRange;  // first traceback step reads a.at(pos), .cc:231/:265
       } else if (DIRS) {
-        K1DirAt<C> da{dirs};
-        traceback_walk(da, ei, ej, (int64_t)p0, J.mode == kModeFull, ops_buf + J.ops_word, J.ops_cap, R);
+        k1_traceback<C>(dirs, ei, ej, p0, J.mode == kModeFull, ops_buf + J.ops_word, J.ops_cap, R);
         R.ops_start = J.ops_word * 16 + J.ops_cap - R.n_ops;
       }
     }

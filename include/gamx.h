@@ -35,6 +35,12 @@ extern "C" {
 
 #define GAMX_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define GAMX_API __attribute__((visibility("default")))
+#else
+#define GAMX_API
+#endif
+
 /* Base codes = the reference's BaseType, lib/include/assembly/nucleotide.hpp:35-43 */
 enum { GAMX_BASE_A = 0, GAMX_BASE_T = 1, GAMX_BASE_C = 2, GAMX_BASE_G = 3, GAMX_BASE_N = 4 };
 
@@ -124,11 +130,11 @@ typedef struct {
 /* Creates a context driving the given CUDA devices (device_ids == NULL: devices 0..n-1;
  * n_devices == 0: all visible devices).  Jobs of a batch are sharded over the devices by
  * DP cost; results are gathered on the host; no collectives are involved. */
-int gamx_create(gamx_ctx** out, const int* device_ids, int n_devices);
-void gamx_destroy(gamx_ctx* ctx);
-int gamx_device_count(const gamx_ctx* ctx);
-const char* gamx_last_error(const gamx_ctx* ctx);
-int gamx_abi_version(void);
+GAMX_API int gamx_create(gamx_ctx** out, const int* device_ids, int n_devices);
+GAMX_API void gamx_destroy(gamx_ctx* ctx);
+GAMX_API int gamx_device_count(const gamx_ctx* ctx);
+GAMX_API const char* gamx_last_error(const gamx_ctx* ctx);
+GAMX_API int gamx_abi_version(void);
 
 /* ---- contig store (replaces the vector<Nucleotide> copies of PctgBuilder.cc:747-748) -- */
 
@@ -136,30 +142,30 @@ int gamx_abi_version(void);
  * nucleotide.code.hpp:47-75 does for unknown characters).  The contig is packed to 2 bits
  * per base plus an N bitmask and staged to every device with pinned async copies at the
  * next batch.  Returns the contig id (>= 0) or a negative error. */
-int64_t gamx_add_contig(gamx_ctx* ctx, const uint8_t* codes, uint64_t len);
+GAMX_API int64_t gamx_add_contig(gamx_ctx* ctx, const uint8_t* codes, uint64_t len);
 /* Same, from FASTA characters (ACGTacgt, everything else -> N). */
-int64_t gamx_add_contig_ascii(gamx_ctx* ctx, const char* seq, uint64_t len);
-uint64_t gamx_contig_length(const gamx_ctx* ctx, uint32_t id);
-int gamx_clear_contigs(gamx_ctx* ctx);
+GAMX_API int64_t gamx_add_contig_ascii(gamx_ctx* ctx, const char* seq, uint64_t len);
+GAMX_API uint64_t gamx_contig_length(const gamx_ctx* ctx, uint32_t id);
+GAMX_API int gamx_clear_contigs(gamx_ctx* ctx);
 
 /* ---- alignment ---------------------------------------------------------------------- */
 
 /* Upper bound on the number of ops the batch can emit in FULL mode (0 for other modes). */
-uint64_t gamx_ops_capacity(const gamx_ctx* ctx, const gamx_job* jobs, uint64_t n);
+GAMX_API uint64_t gamx_ops_capacity(const gamx_ctx* ctx, const gamx_job* jobs, uint64_t n);
 
 /* Aligns a batch.  results[n] is always filled.  ops_buf (may be NULL when no job is in FULL
  * mode) receives the edit strings packed 2 bits per op, op k of a job at bits
  * [2*((ops_offset+k)%4), +2) of byte (ops_offset+k)/4; ops_cap is its capacity in ops. */
-int gamx_align_batch(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_result* results,
+GAMX_API int gamx_align_batch(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_result* results,
                      uint8_t* ops_buf, uint64_t ops_cap);
 
 /* Expands n_ops packed ops starting at ops_offset to one byte per op (GAMX_OP_*), the layout
  * of the reference's std::vector<AlignmentAlphabet>. */
-void gamx_unpack_ops(const uint8_t* ops_buf, uint64_t ops_offset, uint64_t n_ops, uint8_t* out);
+GAMX_API void gamx_unpack_ops(const uint8_t* ops_buf, uint64_t ops_offset, uint64_t n_ops, uint8_t* out);
 
 /* Run-length CIGAR of a packed edit string: writes up to cap (op,len) pairs
  * (op in the low 2 bits, length in the upper 30 of each uint32), returns the number of runs. */
-uint64_t gamx_cigar_rle(const uint8_t* ops_buf, uint64_t ops_offset, uint64_t n_ops,
+GAMX_API uint64_t gamx_cigar_rle(const uint8_t* ops_buf, uint64_t ops_offset, uint64_t n_ops,
                         uint32_t* runs, uint64_t cap);
 
 /* ---- device-resident (pre-staged) batches: the kernel-only timing path -------------- */
@@ -167,24 +173,24 @@ uint64_t gamx_cigar_rle(const uint8_t* ops_buf, uint64_t ops_offset, uint64_t n_
 typedef struct gamx_plan gamx_plan;
 /* Validates, sorts, shards and uploads a batch once; gamx_plan_run() then only launches the
  * kernels (inputs already resident in HBM) and gamx_plan_fetch() copies the results back. */
-int gamx_plan_create(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan** out);
-int gamx_plan_run(gamx_plan* plan);    /* asynchronous; enqueues on each device's stream */
-int gamx_plan_sync(gamx_plan* plan);   /* waits for all devices */
-int gamx_plan_fetch(gamx_plan* plan, gamx_result* results, uint8_t* ops_buf, uint64_t ops_cap);
+GAMX_API int gamx_plan_create(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan** out);
+GAMX_API int gamx_plan_run(gamx_plan* plan);    /* asynchronous; enqueues on each device's stream */
+GAMX_API int gamx_plan_sync(gamx_plan* plan);   /* waits for all devices */
+GAMX_API int gamx_plan_fetch(gamx_plan* plan, gamx_result* results, uint8_t* ops_buf, uint64_t ops_cap);
 /* Device time of the last run in milliseconds (CUDA events on the launching streams, max
  * over devices); kernel_ms[i] receives per-kernel-family times when not NULL (see
  * gamx_plan_kernel_names). */
-float gamx_plan_last_ms(gamx_plan* plan);
-uint64_t gamx_plan_cells(const gamx_plan* plan);        /* sum of x_size*(2*band+1)           */
-uint64_t gamx_plan_kernel_launches(const gamx_plan* plan); /* kernels launched per run        */
-void gamx_plan_destroy(gamx_plan* plan);
+GAMX_API float gamx_plan_last_ms(gamx_plan* plan);
+GAMX_API uint64_t gamx_plan_cells(const gamx_plan* plan);        /* sum of x_size*(2*band+1)           */
+GAMX_API uint64_t gamx_plan_kernel_launches(const gamx_plan* plan); /* kernels launched per run        */
+GAMX_API void gamx_plan_destroy(gamx_plan* plan);
 
 /* ---- microbenchmarks used for the roofline denominators (bench.py) ------------------ */
 
 /* Measures the integer/DPX issue peak of device `dev_index` of the context with a
  * register-only kernel: which = 0 VIADDMNMX(s32), 1 VIMNMX3(s32), 2 VIADDMNMX(s16x2),
  * 3 LOP3, 4 PRMT, 5 IMAD.  Returns lane-ops per second (1 op = 1 instruction lane). */
-double gamx_measure_int_peak(gamx_ctx* ctx, int dev_index, int which);
+GAMX_API double gamx_measure_int_peak(gamx_ctx* ctx, int dev_index, int which);
 
 #ifdef __cplusplus
 }
