@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py - alignment GCUPS of the contig-pair alignment hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, 1 rank/GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], the config the metric is quoted on): per GPU 1,000,000
+synthetic 1 kb contig-end pairs, band 64, ~2 % divergence, score + endpoints (the warp-per-pair
+kernel).  A "step" is one pass of the hot path over that batch.  Metric: GCUPS, cells =
+x_size * (2*band+1) per job (banded_smith_waterman.cc:93-97,135-137).
+
+  value   whole-job GCUPS with inputs (packed contigs + job descriptors) resident in HBM,
+          device time by CUDA events on the launching stream, max over ranks.
+  e2e     the same metric through the C-ABI call a user makes, host buffers in and out:
+          every step re-uploads the raw sequences from pinned host memory (gamx_add_contigs:
+          H2D + pack kernel), the job descriptors, runs the kernels and reads the results back.
+  roofline  score+endpoints is integer-ALU/DPX bound, not HBM bound: achieved =
+          cells/s * 4 lane-ops against the VIADDMNMX issue peak measured live by a
+          register-only microbenchmark; the HBM view of the same kernel is reported beside it.
+  cpu_baseline  the reference's own aligner (oracle/_ref, compiled from the unmodified sources)
+          on all host cores, on a bounded seeded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (pairs per GPU, length spec, band, divergence, mode)
+    "cfg2_1M_1kb_band64_endpoints": dict(pairs=1_000_000, length=1000, band=64, div=0.02, mode=1),
+    "cfg2_1M_1kb_band64_score": dict(pairs=1_000_000, length=1000, band=64, div=0.02, mode=0),
+    "cfg3_long_band256_full": dict(pairs=4000, len_lo=10000, len_hi=50000, band=256, div=0.02, mode=2),
+}
+DEFAULT_WORKLOAD = "cfg2_1M_1kb_band64_endpoints"
+ALGO_LANE_OPS_PER_CELL = 4      # select + add + max + fused add-max in 32-bit
+DIR_BYTES_PER_CELL = 0.25       # 2 direction bits per cell
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, smax = [], set(), None
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); smax = float(f[2])
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            busy = [x for x in sm if x > 0.5 * max(sm)] or sm
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def make_workload(spec, seed):
+    import gen
+    rng = np.random.default_rng(seed)
+    if "length" in spec:
+        a, al, b, bl = gen.bulk_pairs(rng, spec["pairs"], spec["length"], div=spec["div"])
+    else:
+        a, al, b, bl = gen.bulk_pairs(rng, spec["pairs"], 0, div=spec["div"], len_lo=spec["len_lo"], len_hi=spec["len_hi"])
+    return a, al, b, bl
+
+
+def cpu_baseline(spec, a, al, b, bl, seconds_target=12.0, threads=None):
+    """Times the reference aligner (oracle/_ref) on a bounded sample of the workload."""
+    import oracle
+    cores = threads or os.cpu_count() or 1
+    band = spec["band"]
+    cells_per_pair = float(np.mean(np.minimum(bl[:1000], al[:1000] + band))) * (2 * band + 1)
+    # ~0.07 GCUPS per thread (BASELINE.md probe); keep it bounded
+    n = int(max(cores, min(len(al), seconds_target * 0.07e9 * cores / cells_per_pair)))
+    ao = np.concatenate([[0], np.cumsum(al[:n])]).astype(np.int64)
+    bo = np.concatenate([[0], np.cumsum(bl[:n])]).astype(np.int64)
+    A = [a[ao[k]:ao[k + 1]] for k in range(n)]
+    B = [b[bo[k]:bo[k + 1]] for k in range(n)]
+    if oracle.reference_available():
+        ref = oracle.reference()
+        sec, cells, ssum = ref.bench(A, B, band, cores)
+        kind = "reference"
+    else:  # the C restatement, single thread
+        rst = oracle.restatement()
+        n = max(1, n // cores)
+        t0 = time.perf_counter()
+        cells = ssum = 0
+        for k in range(n):
+            r, _ = rst.align(A[k], 0, len(A[k]) - 1, B[k], 0, len(B[k]) - 1, band, want_ops=False)
+            cells += int(r.x_size) * (2 * band + 1)
+            ssum += int(r.score)
+        sec = time.perf_counter() - t0
+        kind, cores = "port", 1
+    return {"value": cells / sec / 1e9, "unit": "GCUPS", "cores": cores, "kind": kind,
+            "sample": f"first {n} pairs of the workload, full-window find_alignment, band {band}",
+            "seconds": sec, "score_sum": int(ssum)}
+
+
+def run_reference(args, spec, rank, world):
+    """--impl reference: the reference's own CPU implementation on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    sub = dict(spec)
+    sub["pairs"] = min(spec["pairs"], 200_000)
+    a, al, b, bl = make_workload(sub, 1000)
+    vals = []
+    for _ in range(args.warmup):
+        cpu_baseline(spec, a, al, b, bl, seconds_target=1.0)
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(args.steps):
+        last = cpu_baseline(spec, a, al, b, bl, seconds_target=8.0)
+        vals.append(last["value"])
+    wall = time.perf_counter() - t0
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": "alignment_gcups", "value": v, "unit": "GCUPS", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / max(1, args.steps) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": args.workload, "band": spec["band"], "note": "bounded sample per step"},
+            "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=0, help="override pairs per GPU (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    spec = dict(WORKLOADS[args.workload])
+    if args.pairs:
+        spec["pairs"] = args.pairs
+    if args.impl == "reference":
+        run_reference(args, spec, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import gam_ngs_b200 as g
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- synthetic workload (independent pairs per rank: the batch shards with no collective) ---
+    t_gen = time.perf_counter()
+    a, al, b, bl = make_workload(spec, 1000 + rank)
+    n = len(al)
+    total_bases = len(a) + len(b)
+    host = torch.empty(total_bases, dtype=torch.uint8, pin_memory=True)  # pinned host copy of the inputs
+    hv = host.numpy()
+    hv[: len(a)] = a
+    hv[len(a):] = b
+    lengths = np.concatenate([al, bl]).astype(np.uint64)
+    jobs = g.make_jobs(n)
+    jobs["a_id"] = np.arange(n, dtype=np.uint32)
+    jobs["b_id"] = np.arange(n, 2 * n, dtype=np.uint32)
+    jobs["end_a"] = al - 1
+    jobs["end_b"] = bl - 1
+    jobs["band"] = spec["band"]
+    jobs["mode"] = spec["mode"]
+    t_gen = time.perf_counter() - t_gen
+
+    ctx = g.Context(devices=[local_rank])
+    int_peak = ctx.measure_int_peak(0)  # VIADDMNMX lane-ops/s, measured live
+
+    # ---- kernel-only: inputs resident in HBM ---------------------------------------------------
+    ctx.add_contigs(host.data_ptr(), lengths)
+    plan = ctx.plan(jobs)
+    cells = plan.cells
+    for _ in range(args.warmup):
+        plan.run(); plan.sync()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        plan.run(); plan.sync()
+        dev_ms += plan.last_ms  # CUDA events on the launching stream (this device)
+    torch.cuda.synchronize()
+    wall_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop()
+    launches = plan.kernel_launches * args.steps
+    res, ops = plan.fetch()
+    dev_s = max_over_ranks(dev_ms * 1e-3)
+    wall_s = max_over_ranks(wall_s)
+    total_cells = sum_over_ranks(float(cells))
+    value = total_cells * args.steps / dev_s / 1e9
+    ok = int((res["status"] == 0).sum())
+    plan.close()
+
+    # ---- parity spot check against the oracle (outside the timed regions) ----------------------
+    checked = 0
+    if rank == 0:
+        import oracle
+        rst = oracle.restatement()
+        ao = np.concatenate([[0], np.cumsum(al[:64])]).astype(np.int64)
+        bo = np.concatenate([[0], np.cumsum(bl[:64])]).astype(np.int64)
+        for k in range(0, 64, 4):
+            A, B = a[ao[k]:ao[k + 1]], b[bo[k]:bo[k + 1]]
+            r, _ = rst.align(A, 0, len(A) - 1, B, 0, len(B) - 1, spec["band"], want_ops=False)
+            got = res[k]
+            same = r.status == got["status"] and r.score == got["score"]
+            if spec["mode"] >= 1:
+                same = same and (r.begin_a, r.begin_b, r.n_ops, r.n_match) == (
+                    got["begin_a"], got["begin_b"], got["n_ops"], got["n_match"])
+            if not same:
+                raise SystemExit(f"PARITY FAILURE on pair {k}: bench numbers would be meaningless")
+            checked += 1
+
+    # ---- end to end through the C ABI with host buffers ----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            ctx.clear_contigs()
+            ctx.add_contigs(host.data_ptr(), lengths)   # H2D of the raw sequences + pack kernel
+            return ctx.align_batch(jobs)                # H2D descriptors, kernels, D2H results
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            r2, _ = e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        h2d = total_bases + lengths.nbytes * 3 + n * 96  # raw codes + pack metadata + DevJob descriptors (96 B each)
+        d2h = n * 104                                     # DevResult records
+        e2e = {"value": total_cells * args.steps / e2e_s / 1e9, "unit": "GCUPS",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": e2e_s / args.steps * 1e3,
+               "includes": "raw sequence H2D from pinned memory + device 2-bit pack, job descriptor H2D, kernels, result D2H"}
+        launches_e2e = 2  # pack kernel + k1 per step
+    # ---- roofline --------------------------------------------------------------------------------
+    peaks, peak_src = load_peaks()
+    kernel_s = dev_s / args.steps
+    cells_rank = float(cells)
+    ach_int = cells_rank / (dev_ms * 1e-3 / args.steps) * ALGO_LANE_OPS_PER_CELL / 1e12
+    roofline = {"bound": "int_alu", "achieved": ach_int, "peak": int_peak / 1e12, "unit": "Tlaneop/s",
+                "frac": ach_int / (int_peak / 1e12) if int_peak else None, "traffic": None,
+                "kernel": "k1_kernel<5,true>" if spec["mode"] else "k1_kernel<5,false>",
+                "algorithmic": f"{ALGO_LANE_OPS_PER_CELL} int32 lane-ops per cell (SURVEY 8d) x {int(cells_rank)} cells per launch",
+                "peak_source": "VIADDMNMX issue rate measured live by gamx_measure_int_peak (register-only kernel)"}
+    seq_bytes = total_bases * 3 / 8
+    algo_bytes = (cells_rank * DIR_BYTES_PER_CELL if spec["mode"] else 0.0) + seq_bytes + n * (96 + 104)
+    ach_hbm = algo_bytes / (dev_ms * 1e-3 / args.steps) / 1e9
+    roofline_hbm = {"bound": "hbm", "achieved": ach_hbm, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach_hbm / peaks["hbm_gbs"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
+                    "note": "direction bits (0.25 B/cell) live in a per-warp scratch that stays in L2; not the binding resource"}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(spec, a, al, b, bl)
+
+    if rank == 0:
+        line = {"metric": "alignment_gcups", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": kernel_s * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+                "config": {"workload": args.workload, "pairs_per_gpu": n, "band": spec["band"],
+                           "divergence": spec["div"], "mode": ["score", "endpoints", "full"][spec["mode"]],
+                           "l2": "inputs_larger_than_l2 (packed contigs + job/result records > 126 MB per step)",
+                           "timing": "CUDA events on the launching stream per step, max over ranks"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
+                "wall_ms_per_step": wall_s / args.steps * 1e3, "jobs_ok": ok, "parity_checked": checked,
+                "gen_seconds": t_gen}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

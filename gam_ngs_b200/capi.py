@@ -69,7 +69,7 @@ assert RESULT_DTYPE.itemsize == C.sizeof(GamxResult), (RESULT_DTYPE.itemsize, C.
 
 EXPORTS = [
     "gamx_abi_version", "gamx_create", "gamx_destroy", "gamx_device_count", "gamx_last_error",
-    "gamx_add_contig", "gamx_add_contig_ascii", "gamx_contig_length", "gamx_clear_contigs",
+    "gamx_add_contig", "gamx_add_contig_ascii", "gamx_add_contigs", "gamx_contig_length", "gamx_clear_contigs",
     "gamx_ops_capacity", "gamx_align_batch", "gamx_unpack_ops", "gamx_cigar_rle",
     "gamx_plan_create", "gamx_plan_run", "gamx_plan_sync", "gamx_plan_fetch", "gamx_plan_last_ms",
     "gamx_plan_cells", "gamx_plan_kernel_launches", "gamx_plan_destroy", "gamx_measure_int_peak",
@@ -106,6 +106,8 @@ def load_library(build_if_missing: bool = True):
     L.gamx_add_contig.restype = C.c_int64
     L.gamx_add_contig_ascii.argtypes = [vp, C.c_char_p, u64]
     L.gamx_add_contig_ascii.restype = C.c_int64
+    L.gamx_add_contigs.argtypes = [vp, vp, vp, u64]
+    L.gamx_add_contigs.restype = C.c_int64
     L.gamx_contig_length.argtypes = [vp, C.c_uint32]
     L.gamx_contig_length.restype = u64
     L.gamx_clear_contigs.argtypes = [vp]
@@ -233,6 +235,16 @@ class Context:
         if cid < 0:
             self._check(int(cid))
         return int(cid)
+
+    def add_contigs(self, codes, lengths) -> int:
+        """Bulk upload: `codes` = concatenated base codes (numpy uint8 array or a raw pointer to
+        pinned host memory), `lengths` = bases per contig.  Returns the first contig id."""
+        lengths = np.ascontiguousarray(lengths, dtype=np.uint64)
+        ptr = codes if isinstance(codes, int) else np.ascontiguousarray(codes, dtype=np.uint8).ctypes.data
+        first = self.lib.gamx_add_contigs(self._h, ptr, lengths.ctypes.data, len(lengths))
+        if first < 0:
+            self._check(int(first))
+        return int(first)
 
     def clear_contigs(self):
         self._check(self.lib.gamx_clear_contigs(self._h))

@@ -77,6 +77,38 @@ generic_kernel(const GenJob* __restrict__ jobs, int n_jobs, SeqStore store, int6
   results[j] = R;
 }
 
+// K0: packs raw base codes (1 byte per base, values > 4 -> N) into the store format (2 bits per
+// base + N bitmask).  One thread produces one group of 32 bases = 2 packed words + 1 mask word.
+// Contig c of the upload occupies store groups [sgroup[c], sgroup[c+1]) (relative to group0) and
+// raw bytes [roff[c], roff[c] + len[c]).
+__global__ void __launch_bounds__(256)
+pack_kernel(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ roff, const uint64_t* __restrict__ len,
+            const uint64_t* __restrict__ sgroup, int n_contigs, uint64_t group0, uint64_t n_groups,
+            uint32_t* __restrict__ packed, uint32_t* __restrict__ nmask) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  int lo = 0, hi = n_contigs;  // last c with sgroup[c] <= g
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (sgroup[mid] <= g) lo = mid; else hi = mid;
+  }
+  const uint64_t local = (g - sgroup[lo]) * 32;
+  const uint64_t remain = len[lo] - local;
+  const int n = remain < 32 ? (int)remain : 32;
+  const uint8_t* src = raw + roff[lo] + local;
+  uint32_t w0 = 0, w1 = 0, m = 0;
+  for (int i = 0; i < n; i++) {
+    const uint32_t c = src[i];
+    if (c >= 4u) m |= 1u << i;
+    else if (i < 16) w0 |= c << (2 * i);
+    else w1 |= c << (2 * (i - 16));
+  }
+  const uint64_t G = group0 + g;
+  packed[2 * G] = w0;
+  packed[2 * G + 1] = w1;
+  nmask[G] = m;
+}
+
 // ---- issue-rate microbenchmarks -------------------------------------------------------------
 template <int WHICH>
 __global__ void __launch_bounds__(256) intpeak_kernel(int* out, int iters, int seed) {
@@ -135,16 +167,27 @@ struct Device {
   size_t total_mem = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  DevBuf packed, nmask;           // contig store replica
-  uint64_t uploaded_words_p = 0;  // words of packed/nmask already on the device
-  uint64_t uploaded_words_n = 0;
+  DevBuf packed, nmask;           // contig store replica (2 bits per base + N mask)
+  uint64_t store_groups = 0;      // 32-base groups already packed on this device
+  DevBuf raw, meta;               // staging for K0: raw base codes + per-contig offsets
   DevBuf jobs, gjobs, results, dirs, ops, grows, gdirs, counters, peak;
-  PinBuf h_jobs, h_gjobs, h_results, h_ops, h_stage;
+  PinBuf h_jobs, h_gjobs, h_results, h_ops, h_stage, h_stage2, h_meta;
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+};
+
+// Index of the contig store.  Sequence data itself lives only on the devices; contigs added one
+// at a time wait as raw bytes in `pending` until the next upload.
+struct StoreIndex {
+  std::vector<uint64_t> start;   // first base index (multiple of 32)
+  std::vector<uint64_t> length;
+  uint64_t n_bases = 0;
 };
 
 struct gamx_ctx {
   std::vector<Device> devs;
-  HostStore store;
+  StoreIndex store;
+  std::vector<uint8_t> pending;   // raw codes of contigs [pending_first, store.start.size())
+  size_t pending_first = 0;
   std::mutex mu;
   std::string err;
 };
@@ -186,39 +229,110 @@ int ensure_pin(gamx_ctx* ctx, PinBuf& b, size_t bytes) {
   return GAMX_OK;
 }
 
-// uploads the not-yet-resident tail of the host store to one device through pinned staging
-int sync_store(gamx_ctx* ctx, Device& d) {
-  CU(cudaSetDevice(d.id));
-  const HostStore& hs = ctx->store;
-  const uint64_t wp = hs.packed.size(), wn = hs.nmask.size();
-  if (wp == 0) return GAMX_OK;
-  if (d.packed.cap < wp * 4 || d.nmask.cap < wn * 4) {
-    // grow: re-upload everything into fresh buffers
-    d.uploaded_words_p = d.uploaded_words_n = 0;
-    if (int rc = ensure_dev(ctx, d.packed, wp * 4 * 2)) return rc;
-    if (int rc = ensure_dev(ctx, d.nmask, wn * 4 * 2)) return rc;
-  }
-  // the last uploaded word may have been extended by a later contig's padding: re-send from one word back
-  uint64_t fp = d.uploaded_words_p > 2 ? d.uploaded_words_p - 2 : 0;
-  uint64_t fn = d.uploaded_words_n > 2 ? d.uploaded_words_n - 2 : 0;
-  if (fp >= wp && fn >= wn) return GAMX_OK;
-  const size_t chunk = 32u << 20;
-  if (int rc = ensure_pin(ctx, d.h_stage, chunk)) return rc;
-  auto send = [&](const uint32_t* src, uint64_t from, uint64_t to, void* dst) -> int {
-    while (from < to) {
-      const uint64_t n = std::min<uint64_t>(to - from, chunk / 4);
-      memcpy(d.h_stage.p, src + from, n * 4);
-      CU(cudaMemcpyAsync((uint32_t*)dst + from, d.h_stage.p, n * 4, cudaMemcpyHostToDevice, d.stream));
-      CU(cudaStreamSynchronize(d.stream));  // staging buffer is reused
-      from += n;
-    }
-    return GAMX_OK;
-  };
-  if (int rc = send(hs.packed.data(), fp, wp, d.packed.p)) return rc;
-  if (int rc = send(hs.nmask.data(), fn, wn, d.nmask.p)) return rc;
-  d.uploaded_words_p = wp;
-  d.uploaded_words_n = wn;
+// grows a store array, keeping its contents
+int grow_keep(gamx_ctx* ctx, Device& d, DevBuf& b, size_t bytes, size_t used) {
+  if (bytes <= b.cap) return GAMX_OK;
+  void* np = nullptr;
+  const size_t want = bytes + bytes / 2 + 4096;
+  CU(cudaMalloc(&np, want));
+  if (b.p && used) CU(cudaMemcpyAsync(np, b.p, used, cudaMemcpyDeviceToDevice, d.stream));
+  CU(cudaStreamSynchronize(d.stream));
+  if (b.p) CU(cudaFree(b.p));
+  b.p = np; b.cap = want;
   return GAMX_OK;
+}
+
+// host -> device copy of `bytes` raw codes: direct when the source is pinned, else through two
+// pinned staging buffers so the host memcpy of chunk n+1 overlaps the DMA of chunk n
+int h2d_raw(gamx_ctx* ctx, Device& d, void* dst, const uint8_t* src, size_t bytes) {
+  if (!bytes) return GAMX_OK;
+  cudaPointerAttributes at;
+  const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  if (!pinned) cudaGetLastError();
+  if (pinned) {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d.stream));
+    return GAMX_OK;
+  }
+  const size_t chunk = 16u << 20;
+  if (int rc = ensure_pin(ctx, d.h_stage, chunk)) return rc;
+  if (int rc = ensure_pin(ctx, d.h_stage2, chunk)) return rc;
+  void* st[2] = {d.h_stage.p, d.h_stage2.p};
+  bool used[2] = {false, false};
+  size_t off = 0;
+  for (int i = 0; off < bytes; i ^= 1) {
+    const size_t n = std::min(chunk, bytes - off);
+    if (used[i]) CU(cudaEventSynchronize(d.ev_stage[i]));
+    memcpy(st[i], src + off, n);
+    CU(cudaMemcpyAsync((uint8_t*)dst + off, st[i], n, cudaMemcpyHostToDevice, d.stream));
+    CU(cudaEventRecord(d.ev_stage[i], d.stream));
+    used[i] = true;
+    off += n;
+  }
+  return GAMX_OK;
+}
+
+// Stages contigs [first, first+n) - raw codes concatenated in `raw`, lengths in the index - to
+// every device: pinned async H2D of the raw bytes, then K0 packs them into the store on the device.
+int store_upload(gamx_ctx* ctx, const uint8_t* raw, size_t first, size_t n) {
+  if (n == 0) return GAMX_OK;
+  const StoreIndex& si = ctx->store;
+  const uint64_t group0 = si.start[first] / 32;
+  const uint64_t groups_end = si.n_bases / 32;
+  const uint64_t n_groups = groups_end - group0;
+  uint64_t raw_bytes = 0;
+  for (size_t c = first; c < first + n; c++) raw_bytes += si.length[c];
+  for (Device& d : ctx->devs) {
+    CU(cudaSetDevice(d.id));
+    if (int rc = grow_keep(ctx, d, d.packed, groups_end * 8 + 64, d.store_groups * 8)) return rc;
+    if (int rc = grow_keep(ctx, d, d.nmask, groups_end * 4 + 64, d.store_groups * 4)) return rc;
+    if (n_groups == 0) { d.store_groups = groups_end; continue; }
+    // per-contig metadata: roff[n], len[n], sgroup[n+1]
+    const size_t meta_bytes = (3 * n + 1) * sizeof(uint64_t);
+    if (int rc = ensure_pin(ctx, d.h_meta, meta_bytes)) return rc;
+    if (int rc = ensure_dev(ctx, d.meta, meta_bytes)) return rc;
+    if (int rc = ensure_dev(ctx, d.raw, raw_bytes + 64)) return rc;
+    uint64_t* roff = (uint64_t*)d.h_meta.p;
+    uint64_t* len = roff + n;
+    uint64_t* sg = len + n;
+    uint64_t off = 0;
+    for (size_t c = 0; c < n; c++) {
+      roff[c] = off; len[c] = si.length[first + c]; sg[c] = si.start[first + c] / 32 - group0;
+      off += len[c];
+    }
+    sg[n] = n_groups;
+    CU(cudaMemcpyAsync(d.meta.p, d.h_meta.p, meta_bytes, cudaMemcpyHostToDevice, d.stream));
+    if (int rc = h2d_raw(ctx, d, d.raw.p, raw, raw_bytes)) return rc;
+    const uint64_t* dm = (const uint64_t*)d.meta.p;
+    const unsigned blocks = (unsigned)((n_groups + 255) / 256);
+    pack_kernel<<<blocks, 256, 0, d.stream>>>((const uint8_t*)d.raw.p, dm, dm + n, dm + 2 * n, (int)n, group0, n_groups,
+                                             (uint32_t*)d.packed.p, (uint32_t*)d.nmask.p);
+    CU(cudaGetLastError());
+    d.store_groups = groups_end;
+  }
+  // the caller's raw buffer (and our pinned metadata) may be reused once the copies are done
+  for (Device& d : ctx->devs) {
+    CU(cudaSetDevice(d.id));
+    CU(cudaStreamSynchronize(d.stream));
+  }
+  return GAMX_OK;
+}
+
+int flush_pending(gamx_ctx* ctx) {
+  const size_t n_all = ctx->store.start.size();
+  if (ctx->pending_first >= n_all) return GAMX_OK;
+  if (int rc = store_upload(ctx, ctx->pending.data(), ctx->pending_first, n_all - ctx->pending_first)) return rc;
+  ctx->pending.clear();
+  ctx->pending_first = n_all;
+  return GAMX_OK;
+}
+
+// registers a contig in the index (store positions are multiples of 32 bases)
+int64_t index_add(gamx_ctx* ctx, uint64_t len) {
+  StoreIndex& si = ctx->store;
+  si.start.push_back(si.n_bases);
+  si.length.push_back(len);
+  si.n_bases += (len + 31) & ~uint64_t(31);
+  return (int64_t)si.start.size() - 1;
 }
 
 struct Group {
@@ -301,7 +415,7 @@ int launch_k1(gamx_ctx* ctx, Device& d, const Group& g, const DevJob* jobs, int*
 }
 
 bool resolve_views(const gamx_ctx* ctx, const gamx_job& j, SeqView* va, uint64_t* la, SeqView* vb, uint64_t* lb) {
-  const HostStore& hs = ctx->store;
+  const StoreIndex& hs = ctx->store;
   if (j.a_id >= hs.start.size() || j.b_id >= hs.start.size()) return false;
   const uint64_t ca = hs.length[j.a_id], cb = hs.length[j.b_id];
   if (j.a_off > ca || j.b_off > cb) return false;
@@ -340,7 +454,9 @@ int gamx_create(gamx_ctx** out, const int* device_ids, int n_devices) {
     cudaDeviceProp prop;
     if (cudaSetDevice(d.id) != cudaSuccess || cudaGetDeviceProperties(&prop, d.id) != cudaSuccess ||
         cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&d.ev0) != cudaSuccess || cudaEventCreate(&d.ev1) != cudaSuccess) {
+        cudaEventCreate(&d.ev0) != cudaSuccess || cudaEventCreate(&d.ev1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&d.ev_stage[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&d.ev_stage[1], cudaEventDisableTiming) != cudaSuccess) {
       cudaGetLastError();
       delete ctx;
       return GAMX_ERR_CUDA;
@@ -358,12 +474,14 @@ void gamx_destroy(gamx_ctx* ctx) {
   for (Device& d : ctx->devs) {
     cudaSetDevice(d.id);
     cudaStreamSynchronize(d.stream);
-    DevBuf* dbs[] = {&d.packed, &d.nmask, &d.jobs, &d.gjobs, &d.results, &d.dirs, &d.ops, &d.grows, &d.gdirs, &d.counters, &d.peak};
+    DevBuf* dbs[] = {&d.packed, &d.nmask, &d.raw, &d.meta, &d.jobs, &d.gjobs, &d.results, &d.dirs, &d.ops, &d.grows, &d.gdirs, &d.counters, &d.peak};
     for (DevBuf* b : dbs) if (b->p) cudaFree(b->p);
-    PinBuf* pbs[] = {&d.h_jobs, &d.h_gjobs, &d.h_results, &d.h_ops, &d.h_stage};
+    PinBuf* pbs[] = {&d.h_jobs, &d.h_gjobs, &d.h_results, &d.h_ops, &d.h_stage, &d.h_stage2, &d.h_meta};
     for (PinBuf* b : pbs) if (b->p) cudaFreeHost(b->p);
     cudaEventDestroy(d.ev0);
     cudaEventDestroy(d.ev1);
+    cudaEventDestroy(d.ev_stage[0]);
+    cudaEventDestroy(d.ev_stage[1]);
     cudaStreamDestroy(d.stream);
   }
   delete ctx;
@@ -376,7 +494,8 @@ int64_t gamx_add_contig(gamx_ctx* ctx, const uint8_t* codes, uint64_t len) {
   if (!ctx || (!codes && len)) return GAMX_ERR_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (len >= (1ull << 31)) { ctx->err = "contig longer than 2^31 bases"; return GAMX_ERR_INVALID; }
-  return ctx->store.add(codes, len);
+  ctx->pending.insert(ctx->pending.end(), codes, codes + len);
+  return index_add(ctx, len);
 }
 
 int64_t gamx_add_contig_ascii(gamx_ctx* ctx, const char* seq, uint64_t len) {
@@ -386,6 +505,20 @@ int64_t gamx_add_contig_ascii(gamx_ctx* ctx, const char* seq, uint64_t len) {
   return gamx_add_contig(ctx, codes.data(), len);
 }
 
+int64_t gamx_add_contigs(gamx_ctx* ctx, const uint8_t* codes, const uint64_t* lengths, uint64_t n) {
+  if (!ctx || !lengths || n == 0) return GAMX_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (int rc = flush_pending(ctx)) return rc;
+  const size_t first = ctx->store.start.size();
+  for (uint64_t c = 0; c < n; c++) {
+    if (lengths[c] >= (1ull << 31)) { ctx->err = "contig longer than 2^31 bases"; return GAMX_ERR_INVALID; }
+    index_add(ctx, lengths[c]);
+  }
+  ctx->pending_first = ctx->store.start.size();
+  if (int rc = store_upload(ctx, codes, first, n)) return rc;
+  return (int64_t)first;
+}
+
 uint64_t gamx_contig_length(const gamx_ctx* ctx, uint32_t id) {
   return (ctx && id < ctx->store.length.size()) ? ctx->store.length[id] : 0;
 }
@@ -393,8 +526,10 @@ uint64_t gamx_contig_length(const gamx_ctx* ctx, uint32_t id) {
 int gamx_clear_contigs(gamx_ctx* ctx) {
   if (!ctx) return GAMX_ERR_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
-  ctx->store.clear();
-  for (Device& d : ctx->devs) d.uploaded_words_p = d.uploaded_words_n = 0;
+  ctx->store = StoreIndex();
+  ctx->pending.clear();
+  ctx->pending_first = 0;
+  for (Device& d : ctx->devs) d.store_groups = 0;
   return GAMX_OK;
 }
 
@@ -514,11 +649,11 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
 // uploads descriptors and sizes the scratch of every device
 static int plan_upload(gamx_plan* pl) {
   gamx_ctx* ctx = pl->ctx;
+  if (int rc = flush_pending(ctx)) return rc;
   for (DevPlan& dp : pl->dps) {
     Device& d = ctx->devs[dp.dev];
     if (dp.n_jobs == 0) continue;
     CU(cudaSetDevice(d.id));
-    if (int rc = sync_store(ctx, d)) return rc;
     if (int rc = ensure_pin(ctx, d.h_jobs, (size_t)dp.n_dev_jobs * sizeof(DevJob))) return rc;
     if (int rc = ensure_pin(ctx, d.h_gjobs, (size_t)dp.n_gen_jobs * sizeof(GenJob))) return rc;
     if (int rc = ensure_dev(ctx, d.jobs, (size_t)dp.n_dev_jobs * sizeof(DevJob))) return rc;

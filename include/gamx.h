@@ -139,12 +139,17 @@ GAMX_API int gamx_abi_version(void);
 /* ---- contig store (replaces the vector<Nucleotide> copies of PctgBuilder.cc:747-748) -- */
 
 /* Adds a contig given as base codes 0..4 (values > 4 are treated as N, like
- * nucleotide.code.hpp:47-75 does for unknown characters).  The contig is packed to 2 bits
- * per base plus an N bitmask and staged to every device with pinned async copies at the
- * next batch.  Returns the contig id (>= 0) or a negative error. */
+ * nucleotide.code.hpp:47-75 does for unknown characters).  At the next batch the raw codes are
+ * staged to every device with pinned async copies and packed there (kernel K0) to 2 bits per
+ * base plus an N bitmask.  Returns the contig id (>= 0) or a negative error. */
 GAMX_API int64_t gamx_add_contig(gamx_ctx* ctx, const uint8_t* codes, uint64_t len);
 /* Same, from FASTA characters (ACGTacgt, everything else -> N). */
 GAMX_API int64_t gamx_add_contig_ascii(gamx_ctx* ctx, const char* seq, uint64_t len);
+/* Bulk form: n contigs whose codes are concatenated in `codes` (lengths[n] bases each).  The raw
+ * bytes are copied to every device (directly when `codes` is pinned host memory, through pinned
+ * staging otherwise) and packed there by a kernel; the call returns when `codes` may be reused.
+ * Returns the id of the first contig (ids are consecutive) or a negative error. */
+GAMX_API int64_t gamx_add_contigs(gamx_ctx* ctx, const uint8_t* codes, const uint64_t* lengths, uint64_t n);
 GAMX_API uint64_t gamx_contig_length(const gamx_ctx* ctx, uint32_t id);
 GAMX_API int gamx_clear_contigs(gamx_ctx* ctx);
 

@@ -96,3 +96,47 @@ def fuzz_case(rng, max_len=80, max_band=40):
     gap = int(rng.choice([-8, -8, -8, -8, -5, -12, -3, -1, 0, 2, -29, -30]))
     return dict(a=a, b=b, begin_a=ba, end_a=ea, begin_b=bb, end_b=eb, band=band, gap=gap,
                 force_start=fs, force_end=fe)
+
+
+def bulk_pairs(rng, n, length, div=0.02, indel_share=0.5, len_lo=None, len_hi=None, chunk=32768):
+    """Vectorised generator for large batches: n pairs (a_k, b_k), b_k = mutate(a_k).
+    Lengths: fixed `length`, or uniform in [len_lo, len_hi].  Returns
+    (a_codes, a_lens, b_codes, b_lens): concatenated uint8 codes and per-pair lengths."""
+    a_parts, b_parts, a_lens_all, b_lens_all = [], [], [], []
+    if len_lo is not None:
+        per_chunk = max(1, int(chunk * 1000 // max(1, (len_lo + len_hi) // 2)))
+    else:
+        per_chunk = max(1, int(chunk * 1000 // max(1, length)))
+    done = 0
+    while done < n:
+        m = min(per_chunk, n - done)
+        if len_lo is None:
+            la = np.full(m, length, dtype=np.int64)
+        else:
+            la = rng.integers(len_lo, len_hi + 1, size=m, dtype=np.int64)
+        total = int(la.sum())
+        a = rng.integers(0, 4, size=total, dtype=np.uint8)
+        starts = np.zeros(m + 1, dtype=np.int64)
+        np.cumsum(la, out=starts[1:])
+        n_edit = rng.binomial(total, div) if div > 0 else 0
+        pos = np.unique(rng.integers(0, total, size=n_edit)) if n_edit else np.zeros(0, dtype=np.int64)
+        kind = rng.random(len(pos))
+        p_sub = 1.0 - indel_share
+        sub_pos = pos[kind < p_sub]
+        ins_pos = pos[(kind >= p_sub) & (kind < p_sub + indel_share / 2)]
+        del_pos = pos[kind >= p_sub + indel_share / 2]
+        src = a.copy()
+        src[sub_pos] = (src[sub_pos] + rng.integers(1, 4, size=len(sub_pos), dtype=np.uint8)) % 4
+        reps = np.ones(total, dtype=np.int8)
+        reps[del_pos] = 0
+        reps[ins_pos] = 2
+        b = np.repeat(src, reps)
+        # output index of the extra copy after each insertion position
+        shift = np.searchsorted(ins_pos, ins_pos, side="left") - np.searchsorted(del_pos, ins_pos, side="left")
+        b[ins_pos + shift + 1] = rng.integers(0, 4, size=len(ins_pos), dtype=np.uint8)
+        pair_of = lambda p: np.searchsorted(starts, p, side="right") - 1  # noqa: E731
+        lb = la + np.bincount(pair_of(ins_pos), minlength=m) - np.bincount(pair_of(del_pos), minlength=m)
+        a_parts.append(a); b_parts.append(b); a_lens_all.append(la); b_lens_all.append(lb)
+        done += m
+    return (np.concatenate(a_parts), np.concatenate(a_lens_all).astype(np.uint64),
+            np.concatenate(b_parts), np.concatenate(b_lens_all).astype(np.uint64))
