@@ -62,3 +62,23 @@ def test_no_cpu_fallback():
         pytest.skip("CUDA device present")
     with pytest.raises(gam_ngs_b200.GamxError):
         gam_ngs_b200.Context()
+
+
+def _build_dropin(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "test_dropin")
+    libdir = os.path.join(ROOT, "gam_ngs_b200")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_dropin.cc"),
+                    "-L" + libdir, "-lgamx", "-Wl,-rpath," + libdir], check=True)
+    return exe
+
+
+def test_cpp_dropin_compiles_links_and_fails_loudly_without_gpu(tmp_path):
+    """The C++ drop-in (same signatures as banded_smith_waterman.hpp:41-72) builds against
+    libgamx.so; without a CUDA device it reports so (exit 77), it never computes on the CPU."""
+    import subprocess
+    import torch
+    capi.load_library()
+    exe = _build_dropin(tmp_path)
+    rc = subprocess.run([exe], capture_output=True).returncode
+    assert rc == (0 if torch.cuda.is_available() else 77)

@@ -232,3 +232,13 @@ def test_python_mirror_interface(ctx):
     all_a, all_c = g.Contig("A" * 50), g.Contig("C" * 50)
     with pytest.raises(IndexError):
         g.BandedSmithWaterman(10, ctx=ctx).find_alignment(all_a, 0, 60, all_c, 0, 49)
+
+
+def test_cpp_dropin_runs_on_gpu(tmp_path):
+    """The C++ drop-in class (gam_ngs_b200/cpp/gamx_dropin.hpp) called like PctgBuilder.cc:1669
+    returns the oracle's answer (checked inside tests/cpp/test_dropin.cc)."""
+    import subprocess
+    from test_abi import _build_dropin
+    exe = _build_dropin(tmp_path)
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
