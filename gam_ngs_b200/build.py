@@ -16,7 +16,7 @@ HEADERS = [os.path.join(CSRC, f) for f in
            ("bsw_common.h", "bsw_warp.h", "bsw_generic.h", "bsw_traceback.h", "bsw_host.h")] + \
           [os.path.join(os.path.dirname(HERE), "include", "gamx.h")]
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+NVCC_FLAGS = ["-split-compile", "0", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
 

@@ -4,6 +4,7 @@
 // device result into the fields of MyAlignment + its reductions (my_alignment.cc:167-296).
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -67,6 +68,7 @@ struct Prepared {
   int cls;             // kClass*
   int early_status;    // for kClassEarly
   int c;               // lane stripe width for kClassWarp
+  int lg;              // lanes per pair for kClassWarp (32, 16 or 8)
   uint64_t x_size;
   uint64_t cells;      // x_size * (2*band+1), the unit of the GCUPS metric
   uint64_t la, lb;
@@ -78,10 +80,27 @@ struct Prepared {
   uint32_t ops_cap;    // ops (multiple of 16), FULL mode only
 };
 
-inline int stripe_for_band(uint64_t band) {
+// Lanes per pair and stripe width for a band: the combination with the fewest idle cell slots
+// (LG*C >= 2*band+1), preferring fewer lanes per pair (more pairs per warp, longer stripes, fewer
+// shuffles per cell) on ties.  LG < 32 only from C >= 5 (short stripes do not amortise a step).
+// GAMX_FORCE_LG=8|16|32 (environment, tuning/experiments only) restricts the choice when feasible.
+inline void geometry_for_band(uint64_t band, int* c_out, int* lg_out) {
+  static const int forced = [] { const char* e = getenv("GAMX_FORCE_LG"); return e ? atoi(e) : 0; }();
   const uint64_t y = 2 * band + 1;
-  int c = (int)((y + 31) / 32);
-  return c < 2 ? 2 : c;
+  int best_c = 0, best_lg = 0;
+  uint64_t best_slots = ~0ull;
+  const int lgs[3] = {8, 16, 32};
+  for (int n = 0; n < 3; n++) {
+    const int lg = lgs[n];
+    int c = (int)((y + lg - 1) / lg);
+    if (c < 2) c = 2;
+    if (c > kMaxC) continue;
+    if (forced && lg != forced && (y + forced - 1) / forced <= (uint64_t)kMaxC) continue;
+    if (!forced && lg < 32 && c < 5) continue;
+    const uint64_t slots = (uint64_t)lg * c;
+    if (slots < best_slots) { best_slots = slots; best_c = c; best_lg = lg; }
+  }
+  *c_out = best_c; *lg_out = best_lg;
 }
 
 // a_view / b_view: views of position 0 of a and b; la / lb: view lengths (a.size(), b.size()).
@@ -125,7 +144,7 @@ inline Prepared prepare_job(const SeqView& a_view, uint64_t la, const SeqView& b
   }
 
   P.cls = kClassWarp;
-  P.c = stripe_for_band(band);
+  geometry_for_band(band, &P.c, &P.lg);
   DevJob& d = P.dj;
   d.a = a_view;
   d.b = b_view;
@@ -163,7 +182,7 @@ inline Prepared prepare_job(const SeqView& a_view, uint64_t la, const SeqView& b
   d.gap = (int32_t)gap;
   d.mode = mode;
   d.ops_cap = P.ops_cap;
-  P.dir_words = (mode == kModeScore) ? 0 : k1_dir_words((int)x, (int)band, P.c);
+  P.dir_words = (mode == kModeScore) ? 0 : k1_dir_words((int)x, (int)band, P.c, P.lg);
   return P;
 }
 

@@ -126,9 +126,9 @@ GAMX_HD void traceback_walk(const DirAt& dir_at, int end_i, int end_j, int64_t p
   s.store(R, pos, x);
 }
 
-// K1 layout: word ((t>>4)*C + k)*32 + l holds the tags of band column j = l*C+k for the 16
+// K1 layout: word ((t>>4)*C + k)*LG + l holds the tags of band column j = l*C+k for the 16
 // steps t = x + l of one step block, the tag of step offset o = t&15 at bits [2*(15-o), +2).
-template <int C>
+template <int C, int LG>
 GAMX_HD void k1_traceback(const uint32_t* dirs, int end_i, int end_j, int p0, bool want_ops,
                           uint32_t* ops_words, uint32_t ops_cap, DevResult& R) {
   OpsWriter ow;
@@ -139,7 +139,7 @@ GAMX_HD void k1_traceback(const uint32_t* dirs, int end_i, int end_j, int p0, bo
   int l = y / C, k = y - l * C;
   while (x >= 0 && y >= 0 && pos >= 0) {
     const int t = x + l, o = t & 15;
-    const uint32_t w = dirs[((uint32_t)(t >> 4) * C + k) * 32 + l];
+    const uint32_t w = dirs[((uint32_t)(t >> 4) * C + k) * LG + l];
     const uint32_t ws = w >> (2 * (15 - o));  // pair p = tag of row x-p (p <= o)
     const uint32_t tag = ws & 3u;
     if (tag >= (uint32_t)kTagDiagMis) {

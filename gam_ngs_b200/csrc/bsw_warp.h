@@ -1,59 +1,62 @@
-// K1 - warp-per-pair banded overlap DP (inter-task parallelism: every warp owns one pair).
+// K1 - warp-level banded overlap DP with inter-task parallelism: every group of LG lanes
+// (LG = 32, 16 or 8; 1, 2 or 4 pairs per warp) owns one pair.
 //
 // Computes what BandedSmithWaterman::find_alignment computes
 // (/root/reference/lib/src/alignment/banded_smith_waterman.cc:69-323) for the jobs the host
-// classifies as "regular" (DESIGN.md 4.1): -29 <= gap <= -5, 2*band+1 <= 32*C, windows that
+// classifies as "regular" (DESIGN.md 4): -29 <= gap <= -5, 2*band+1 <= LG*C, windows that
 // start inside both contigs.  Everything else goes to the generic kernel (bsw_generic.h).
 //
-// Layout.  Band coordinates (i, j): row i <-> b[begin_b+i], column j <->
-// a[pos], pos = begin_a - band + i + j.  Lane l owns the C consecutive band columns
-// j = l*C .. l*C+C-1 ("slots"); at step t it processes row i = t - l, so the three
+// Layout.  Band coordinates (i, j): row i <-> b[begin_b+i], column j <-> a[pos],
+// pos = begin_a - band + i + j.  Lane gl of a group owns the C consecutive band columns
+// j = gl*C .. gl*C+C-1 ("slots"); at step t it processes row i = t - gl, so the three
 // dependencies of a cell
 //      diag (i-1, j)    -> the lane's own register of the previous step
-//      up   (i-1, j+1)  -> own register, or lane l+1's slot 0 of THIS step   (1 shuffle)
-//      left (i,   j-1)  -> own register, or lane l-1's last slot of the PREVIOUS step (1 shuffle)
+//      up   (i-1, j+1)  -> own register, or lane gl+1's slot 0 of THIS step      (1 shuffle)
+//      left (i,   j-1)  -> own register, or lane gl-1's last slot of the PREVIOUS step (1 shuffle)
 // cost two shuffles per C cells.  H lives in registers only; nothing but the 2-bit
 // directions ever goes to memory.
 //
-// Cell update.  Stored value V = ((H + alpha*i + beta*j) << 2) | tag with
-// beta = -gap, alpha = -2*gap, which makes both gap moves free:
+// Cell update.  Stored value V = ((H + alpha*i + beta*j) << 2) | tag with beta = -gap,
+// alpha = -2*gap, which makes both gap moves free:
 //      V = max( diag + Cd , up + 1 , left )        Cd = ((S + alpha) << 2) | (2 + is_match)
 // The low two bits of the max are the direction with exactly the reference's priority
 // diag > up > left on ties (.cc:272-307), and tag^1 is the edit op.  Per cell: one PRMT (Cd
 // from an 8-byte per-row table indexed by the a-base), two VIADDMNMX, one LOP3 (strip the
-// tag) on the ALU pipe, plus two IMAD-class ops that append the tag to the lane's direction
-// word.  The score-only variant (DIRS=false) drops the tag handling: 3 ALU ops per cell.
+// tag) on the ALU pipe, plus two IMADs on the FMA pipe that append the tag to the lane's
+// direction word.  The score-only variant (DIRS=false) drops the tag handling: 3 ALU ops/cell.
+//
+// Step variants.  Steps run in unrolled groups of C (register renaming for the sliding a-window):
+//   <CAPTURE=false, MASKED=false>  steady state
+//   <CAPTURE=true,  *>             additionally latches the "last column" cells (pos == end_a,
+//                                  .cc:197-212) of the anti-diagonals that contain them
+//   <*, MASKED=true>               pipeline drain: lanes past their last row keep their registers
+// and a general single step handles the pipeline fill (first row, .cc:112-132).
 #pragma once
 #include "bsw_common.h"
 #include "bsw_traceback.h"
 
 namespace gamx {
 
-constexpr int kTileSteps = 256;  // steps per shared-memory sequence tile
+constexpr int kTileSteps = 128;  // steps per shared-memory sequence tile
 constexpr int kMaxC = 17;        // widest lane stripe: band <= (32*17-1)/2 = 271
 
-template <int C>
-struct WarpSmem {
+template <int C, int LG>
+struct GroupSmem {
   // a-bases of the tile as PRMT selectors (0x7770 | code), b-rows as 8-byte Cd tables
-  uint64_t btab[kTileSteps + 32];
-  uint16_t asel[kTileSteps + 32 * C];
+  uint64_t btab[kTileSteps + LG];
+  uint16_t asel[kTileSteps + LG * C + 2];
+};
+template <int C, int LG>
+struct WarpSmem {
+  GroupSmem<C, LG> g[32 / LG];
 };
 
-template <int C>
-struct K1DirAt {
-  const uint32_t* dirs;
-  GAMX_HD int operator()(int x, int y) const {
-    const int l = y / C, k = y - l * C, t = x + l;
-    const uint32_t w = dirs[((size_t)(t >> 4) * C + k) * 32 + l];
-    return (int)((w >> (2 * (15 - (t & 15)))) & 3u);
-  }
-};
-
-// number of direction words one job needs in the K1 layout
-GAMX_HD uint64_t k1_dir_words(int x, int band, int c) {
-  const int ld = (2 * band) / c;
-  const uint64_t steps = (uint64_t)x + ld;
-  return ((steps + 15) / 16) * (uint64_t)c * 32;
+// number of direction words one job needs in the K1 layout (a few extra step blocks because the
+// groups of a warp share one step loop: the host sizes the scratch for the largest job of a launch)
+GAMX_HD uint64_t k1_dir_words(int x, int band, int c, int lg) {
+  (void)band;
+  const uint64_t steps = (uint64_t)x + lg + 16;
+  return ((steps + 15) / 16) * (uint64_t)c * lg;
 }
 
 struct EndBest {
@@ -63,18 +66,45 @@ struct EndBest {
   }
 };
 
-template <int C, bool DIRS, class W>
-GAMX_HD void warp_align(W& w, const DevJob& J, const SeqStore& S, WarpSmem<C>& sm, uint32_t* dirs,
-                        uint32_t* ops_buf, DevResult* out) {
+// One warp: 32/LG jobs.  Jp / out are per-lane arguments, uniform within a group of LG lanes:
+// the group's job (null: idle group) and its result slot.  dirs: the warp's direction scratch,
+// group g uses dirs + g*group_stride.
+template <int C, int LG, bool DIRS, class W>
+GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& S, WarpSmem<C, LG>& wsm, uint32_t* dirs,
+                        uint64_t group_stride, uint32_t* ops_buf, DevResult* out) {
   static_assert(C >= 2 && C <= kMaxC, "lane stripe width");
+  static_assert(LG == 8 || LG == 16 || LG == 32, "lanes per pair");
   constexpr int SH = DIRS ? 2 : 0;
   const int lane = w.lane();
-  const int X = J.x, B = J.band, Y = 2 * B + 1;
+  const int grp = lane / LG, gl = lane % LG;
+  const bool live = Jp != nullptr;
+  GroupSmem<C, LG>& sm = wsm.g[grp];
+  uint32_t* gdirs = DIRS ? dirs + (uint64_t)grp * group_stride : nullptr;
+
+  const int X = live ? Jp->x : 0, B = live ? Jp->band : 0, Y = 2 * B + 1;
   const int ld = (Y - 1) / C, kd = (Y - 1) - ld * C;  // lane/slot of band column 2B
-  const int alpha = -2 * J.gap, beta = -J.gap;
-  const int la = J.la, p0 = J.p0;
-  const int T_total = X + ld;
-  const int j0 = lane * C;
+  const int gap = live ? Jp->gap : -8;
+  const int alpha = -2 * gap, beta = -gap;
+  const int la = live ? Jp->la : 0, p0 = live ? Jp->p0 : 0;
+  const int kc = live ? Jp->kc : -1;
+  const int j0 = gl * C;
+  SeqView va, vb;
+  va.origin = vb.origin = 0; va.dir = vb.dir = 1; va.comp = vb.comp = 0;
+  if (live) { va = Jp->a; vb = Jp->b; }
+
+  // warp-uniform extents
+  int t_end = live ? X + ld : 0;     // this group's last step + 1
+  int x_min = live ? X : 0x7fffffff;
+  int win_lo = (live && kc >= 0) ? kc - (ld + 1) * (C - 1) : 0x7fffffff;
+  int win_hi = (live && kc >= 0) ? kc : -1;
+#pragma unroll
+  for (int d = LG; d < 32; d <<= 1) {
+    t_end = imax(t_end, w.shfl_xor(t_end, d, 32));
+    x_min = imin(x_min, w.shfl_xor(x_min, d, 32));
+    win_lo = imin(win_lo, w.shfl_xor(win_lo, d, 32));
+    win_hi = imax(win_hi, w.shfl_xor(win_hi, d, 32));
+  }
+  const int T_total = t_end;
 
   // Cd bytes (see header comment)
   const uint32_t tagM = DIRS ? (uint32_t)kTagDiagMatch : 0u, tagX = DIRS ? (uint32_t)kTagDiagMis : 0u;
@@ -83,24 +113,18 @@ GAMX_HD void warp_align(W& w, const DevJob& J, const SeqStore& S, WarpSmem<C>& s
   const uint32_t cdZ = ((uint32_t)alpha << SH) | tagM;  // N against anything: score 0, MATCH op
   const uint32_t cdP = ((uint32_t)alpha << SH) | tagX;  // padding: score 0
 
-  int H[C];
   // Direction words are accumulated as the difference of two multiply-add chains (both on the
   // FMA pipe, leaving the ALU pipe to the DP): accV = 4*accV + v, accH = 4*accH + (v & ~3);
   // accV - accH (mod 2^32) = the last 16 tags, oldest in the top bit pair.
+  int H[C], capv[C];
   uint32_t A[C], accV[C], accH[C];
   int U[C];
 #pragma unroll
   for (int k = 0; k < C; k++) {
-    H[k] = 0; A[k] = 0x7775u; accV[k] = 0; accH[k] = 0;
-    U[k] = (lane == ld && k == kd) ? kBlock : (DIRS ? 1 : 0);
+    H[k] = 0; capv[k] = 0; A[k] = 0x7775u; accV[k] = 0; accH[k] = 0;
+    U[k] = (gl == ld && k == kd) ? kBlock : (DIRS ? 1 : 0);
   }
-
-  EndBest best;
-  best.found = 0; best.val = 0; best.ord = 0;
-
-  // "last column" cells (pos == end_a) are met in steps [win_lo, win_hi]
-  const int kc = J.kc;
-  const int win_lo = kc >= 0 ? kc - (ld + 1) * (C - 1) : 1, win_hi = kc >= 0 ? kc : 0;
+  const int tcap0 = kc - gl * (C - 1);  // step at which slot 0 holds a "last column" cell (slot k: tcap0 - k)
 
   int t = 0;
   while (t < T_total) {
@@ -108,17 +132,17 @@ GAMX_HD void warp_align(W& w, const DevJob& J, const SeqStore& S, WarpSmem<C>& s
     const int t0 = t;
     w.sync();
     {
-      const int na = kTileSteps + 32 * C - 31;
+      const int na = kTileSteps + LG * C - (LG - 1);
       const int pa0 = p0 + t0;
-      for (int idx = lane; idx < na; idx += 32) {
+      for (int idx = gl; idx < na; idx += LG) {
         const int pos = pa0 + idx;
-        const uint32_t code = (pos >= 0 && pos < la) ? load_code(S, J.a, pos) : (uint32_t)kCodePad;
+        const uint32_t code = (live && pos >= 0 && pos < la) ? load_code(S, va, pos) : (uint32_t)kCodePad;
         sm.asel[idx] = (uint16_t)(0x7770u | code);
       }
-      const int nb = kTileSteps + 31;
-      for (int idx = lane; idx < nb; idx += 32) {
-        const int i = t0 - 31 + idx;
-        const uint32_t bc = (i >= 0 && i < X) ? load_code(S, J.b, i) : (uint32_t)kCodePad;
+      const int nb = kTileSteps + LG - 1;
+      for (int idx = gl; idx < nb; idx += LG) {
+        const int i = t0 - (LG - 1) + idx;
+        const uint32_t bc = (live && i >= 0 && i < X) ? load_code(S, vb, i) : (uint32_t)kCodePad;
         uint32_t lo, hi;
         if (bc < 4u) { lo = (cdX * 0x01010101u) ^ ((cdX ^ cdM) << (8 * bc)); hi = cdZ | (cdP << 8); }
         else if (bc == (uint32_t)kCodeN) { lo = cdZ * 0x01010101u; hi = cdM | (cdP << 8); }
@@ -127,65 +151,74 @@ GAMX_HD void warp_align(W& w, const DevJob& J, const SeqStore& S, WarpSmem<C>& s
       }
     }
     w.sync();
-    const uint16_t* pa = sm.asel + (lane * (C - 1) + (C - 1) - t0);  // pa[t]: slot C-1's base at step t
-    const uint64_t* pb = sm.btab + (31 - lane - t0);                 // pb[t]: table of row t - lane
+    const uint16_t* pa = sm.asel + (gl * (C - 1) + (C - 1) - t0);  // pa[t]: slot C-1's base at step t
+    const uint64_t* pb = sm.btab + ((LG - 1) - gl - t0);           // pb[t]: table of row t - gl
     if (t0 == 0) {
       // slots 0..C-2 of step 0
 #pragma unroll
-      for (int k = 0; k < C - 1; k++) A[k] = sm.asel[lane * (C - 1) + k];
+      for (int k = 0; k < C - 1; k++) A[k] = sm.asel[gl * (C - 1) + k];
     }
     const int tile_end = imin(t0 + kTileSteps, T_total);
 
+    // C unrolled steps starting at step t (every lane's row >= 1).
+    // CAPTURE: latch "last column" cells; MASKED: lanes whose row is past X-1 keep their registers.
+#define GAMX_STEP_GROUP(CAPTURE, MASKED)                                                              \
+  {                                                                                                   \
+    const int dcap = tcap0 - t;                                                                       \
+    _Pragma("unroll") for (int u = 0; u < C; u++) {                                                   \
+      const int tt = t + u;                                                                           \
+      A[(u + C - 1) % C] = pa[tt];                                                                    \
+      const uint64_t tb = pb[tt];                                                                     \
+      const uint32_t tlo = (uint32_t)tb, thi = (uint32_t)(tb >> 32);                                  \
+      int left = w.shfl_up(H[C - 1], 1, LG);                                                          \
+      if (gl == 0) left = kNegInf;                                                                    \
+      const bool act = !(MASKED) || (tt - gl < X);                                                    \
+      int right = 0;                                                                                  \
+      _Pragma("unroll") for (int k = 0; k < C; k++) {                                                 \
+        const int up = (k == C - 1) ? right : H[(k + 1) % C];                                         \
+        const int cd = (int)prmt(tlo, thi, A[(u + k) % C]);                                           \
+        const int m = viaddmax(up, U[k], left);                                                       \
+        const int v = viaddmax(H[k], cd, m);                                                          \
+        int hc = v;                                                                                   \
+        if (DIRS) {                                                                                   \
+          hc = v & ~3;                                                                                \
+          accV[k] = accV[k] * 4u + (uint32_t)v;                                                       \
+          accH[k] = accH[k] * 4u + (uint32_t)hc;                                                      \
+        }                                                                                             \
+        if (MASKED) { if (act) H[k] = hc; } else H[k] = hc;                                           \
+        if (CAPTURE) { if (dcap == u + k) capv[k] = H[k]; }                                           \
+        left = H[k];                                                                                  \
+        if (k == 0) right = w.shfl_down(H[0], 1, LG);                                                 \
+      }                                                                                               \
+      if (DIRS && (tt & 15) == 15) {                                                                  \
+        _Pragma("unroll") for (int k = 0; k < C; k++)                                                 \
+            gdirs[((uint32_t)(tt >> 4) * C + k) * LG + gl] = accV[k] - accH[k];                        \
+      }                                                                                               \
+    }                                                                                                 \
+    t += C;                                                                                           \
+  }
+
     while (t < tile_end) {
-      // the final step always takes the general path (it flushes the partial direction words)
-      const bool fast = (t >= 32) && (t + C - 1 <= X - 1) && (t + C - 1 <= T_total - 2) &&
-                        (t + C <= tile_end) && (t + C - 1 < win_lo || t > win_hi);
-      if (fast) {
-        // ---- C steps, every lane on a row in [1, X-1], no candidate capture ----------------
-#pragma unroll
-        for (int u = 0; u < C; u++) {
-          const int tt = t + u;
-          A[(u + C - 1) % C] = pa[tt];
-          const uint64_t tb = pb[tt];
-          const uint32_t tlo = (uint32_t)tb, thi = (uint32_t)(tb >> 32);
-          int left = w.shfl_up(H[C - 1], 1);
-          if (lane == 0) left = kNegInf;
-          int right = 0;
-#pragma unroll
-          for (int k = 0; k < C; k++) {
-            const int up = (k == C - 1) ? right : H[(k + 1) % C];
-            const int cd = (int)prmt(tlo, thi, A[(u + k) % C]);
-            const int m = viaddmax(up, U[k], left);
-            const int v = viaddmax(H[k], cd, m);
-            if (DIRS) {
-              const int hc = v & ~3;
-              accV[k] = accV[k] * 4u + (uint32_t)v;
-              accH[k] = accH[k] * 4u + (uint32_t)hc;
-              H[k] = hc;
-            } else {
-              H[k] = v;
-            }
-            left = H[k];
-            if (k == 0) right = w.shfl_down(H[0], 1);
-          }
-          if (DIRS && (tt & 15) == 15) {
-#pragma unroll
-            for (int k = 0; k < C; k++) dirs[((uint32_t)(tt >> 4) * C + k) * 32 + lane] = accV[k] - accH[k];
-          }
-        }
-        t += C;
+      // the warp's final step always takes the general path (it flushes the partial direction words)
+      const bool grouped = (t >= LG) && (t + C <= tile_end) && (t + C - 1 <= T_total - 2);
+      if (grouped) {
+        const bool masked = t + C - 1 > x_min - 1;
+        const bool capture = !(t + C - 1 < win_lo || t > win_hi);
+        if (!masked && !capture) GAMX_STEP_GROUP(false, false)
+        else if (!masked) GAMX_STEP_GROUP(true, false)
+        else GAMX_STEP_GROUP(true, true)
         continue;
       }
 
-      // ---- one general step: pipeline fill/drain, first row, candidate capture -------------
+      // ---- one general step: pipeline fill (first row), tile/tail remainders ---------------
       {
-        const int i = t - lane;
-        const bool act = (i >= 0) && (i < X);
+        const int i = t - gl;
+        const bool act = live && (i >= 0) && (i < X);
         A[C - 1] = pa[t];
         const uint64_t tb = pb[t];
         const uint32_t tlo = (uint32_t)tb, thi = (uint32_t)(tb >> 32);
-        int left = w.shfl_up(H[C - 1], 1);
-        if (lane == 0) left = kNegInf;
+        int left = w.shfl_up(H[C - 1], 1, LG);
+        if (gl == 0) left = kNegInf;
         const bool row0 = act && i == 0;
         if (row0) {
           // first row, banded_smith_waterman.cc:112-132 (gap < every substitution score, so the
@@ -215,7 +248,7 @@ GAMX_HD void warp_align(W& w, const DevJob& J, const SeqStore& S, WarpSmem<C>& s
           if (DIRS) { accV[0] = accV[0] * 4u + (uint32_t)v; accH[0] = accH[0] * 4u + (uint32_t)hc; }
           if (act) H[0] = hc;
         }
-        const int right = w.shfl_down(H[0], 1);
+        const int right = w.shfl_down(H[0], 1, LG);
         if (!row0) {
 #pragma unroll
           for (int k = 1; k < C; k++) {
@@ -228,46 +261,55 @@ GAMX_HD void warp_align(W& w, const DevJob& J, const SeqStore& S, WarpSmem<C>& s
             if (act) H[k] = hc;
           }
         }
-        // "last column" candidates, .cc:197-212: the cell of this row with i + j == kc
-        if (act && kc >= 0 && i >= J.col_imin) {
+        // latch "last column" cells, .cc:197-212: slot k at step tcap0 - k
+        const int dc = tcap0 - t;
 #pragma unroll
-          for (int k = 0; k < C; k++) {
-            const int j = j0 + k;
-            if (i + j == kc && j <= 2 * B) {
-              const int val = J.col_zero ? 0 : ((H[k] >> SH) - alpha * i - beta * j);
-              best.consider(val, Y + i);
-            }
-          }
-        }
+        for (int k = 0; k < C; k++)
+          if (dc == k) capv[k] = H[k];
 #pragma unroll
         for (int k = 0; k < C - 1; k++) A[k] = A[k + 1];
         if (DIRS && ((t & 15) == 15 || t == T_total - 1)) {
           const int sh = 2 * (15 - (t & 15));
 #pragma unroll
-          for (int k = 0; k < C; k++) dirs[((uint32_t)(t >> 4) * C + k) * 32 + lane] = (accV[k] - accH[k]) << sh;
+          for (int k = 0; k < C; k++) gdirs[((uint32_t)(t >> 4) * C + k) * LG + gl] = (accV[k] - accH[k]) << sh;
         }
         t++;
       }
     }
+#undef GAMX_STEP_GROUP
   }
 
   // ---- end-cell selection, .cc:174-212: last row (columns ascending) before last column ----
+  EndBest best;
+  best.found = 0; best.val = 0; best.ord = 0;
+  if (live) {
 #pragma unroll
-  for (int k = 0; k < C; k++) {
-    const int j = j0 + k;
-    if (j >= J.jlo && j <= J.jhi) {
-      const int val = (j < J.jfill) ? ((H[k] >> SH) - alpha * (X - 1) - beta * j) : 0;
-      best.consider(val, j);
+    for (int k = 0; k < C; k++) {
+      const int j = j0 + k;
+      if (j >= Jp->jlo && j <= Jp->jhi) {
+        const int val = (j < Jp->jfill) ? ((H[k] >> SH) - alpha * (X - 1) - beta * j) : 0;
+        best.consider(val, j);
+      }
+    }
+    if (kc >= 0) {
+#pragma unroll
+      for (int k = 0; k < C; k++) {
+        const int j = j0 + k, i = tcap0 - k - gl;  // the row this slot was on when it met pos == end_a
+        if (i >= 0 && i < X && j <= 2 * B && i >= Jp->col_imin) {
+          const int val = Jp->col_zero ? 0 : ((capv[k] >> SH) - alpha * i - beta * j);
+          best.consider(val, Y + i);
+        }
+      }
     }
   }
 #pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) {
-    const int of = w.shfl_xor(best.found, d), ov = w.shfl_xor(best.val, d), oo = w.shfl_xor(best.ord, d);
+  for (int d = LG / 2; d >= 1; d >>= 1) {
+    const int of = w.shfl_xor(best.found, d, 32), ov = w.shfl_xor(best.val, d, 32), oo = w.shfl_xor(best.ord, d, 32);
     if (of) best.consider(ov, oo);
   }
-  w.sync();  // direction words of all lanes are visible to lane 0
+  w.sync();  // direction words of all lanes are visible to the group leaders
 
-  if (lane == 0) {
+  if (live && gl == 0) {
     DevResult R;
     R.status = kStatusOk; R.score = 0; R.end_i = 0; R.end_j = 0; R.has_match = 0;
     R.n_ops = R.n_match = R.n_mismatch = R.n_gap_a = R.n_gap_b = 0;
@@ -284,8 +326,8 @@ GAMX_HD void warp_align(W& w, const DevJob& J, const SeqStore& S, WarpSmem<C>& s
       if (p0 + ei + ej >= la) {
         R.status = kStatusOutOfRange;  // first traceback step reads a.at(pos), .cc:231/:265
       } else if (DIRS) {
-        k1_traceback<C>(dirs, ei, ej, p0, J.mode == kModeFull, ops_buf + J.ops_word, J.ops_cap, R);
-        R.ops_start = J.ops_word * 16 + J.ops_cap - R.n_ops;
+        k1_traceback<C, LG>(gdirs, ei, ej, p0, Jp->mode == kModeFull, ops_buf + Jp->ops_word, Jp->ops_cap, R);
+        R.ops_start = Jp->ops_word * 16 + Jp->ops_cap - R.n_ops;
       }
     }
     *out = R;

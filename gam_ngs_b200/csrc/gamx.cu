@@ -40,29 +40,32 @@ constexpr int kWarpsPerBlock = 4;
 
 struct DevWarp {
   __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31); }
-  __device__ __forceinline__ int shfl_up(int v, int d) const { return __shfl_up_sync(0xffffffffu, v, d); }
-  __device__ __forceinline__ int shfl_down(int v, int d) const { return __shfl_down_sync(0xffffffffu, v, d); }
-  __device__ __forceinline__ int shfl_xor(int v, int m) const { return __shfl_xor_sync(0xffffffffu, v, m); }
+  __device__ __forceinline__ int shfl_up(int v, int d, int width) const { return __shfl_up_sync(0xffffffffu, v, d, width); }
+  __device__ __forceinline__ int shfl_down(int v, int d, int width) const { return __shfl_down_sync(0xffffffffu, v, d, width); }
+  __device__ __forceinline__ int shfl_xor(int v, int m, int width) const { return __shfl_xor_sync(0xffffffffu, v, m, width); }
   __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
 
-template <int C, bool DIRS>
+template <int C, int LG, bool DIRS>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 k1_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counter, SeqStore store,
-          uint32_t* __restrict__ dirs, uint64_t slot_stride, uint32_t* __restrict__ ops,
+          uint32_t* __restrict__ dirs, uint64_t group_stride, uint32_t* __restrict__ ops,
           DevResult* __restrict__ results) {
-  __shared__ WarpSmem<C> sm[kWarpsPerBlock];
+  constexpr int G = 32 / LG;  // pairs per warp
+  __shared__ WarpSmem<C, LG> sm[kWarpsPerBlock];
   DevWarp w;
   const int warp = (int)(threadIdx.x >> 5);
   const uint64_t slot = (uint64_t)blockIdx.x * kWarpsPerBlock + warp;
-  uint32_t* my_dirs = DIRS ? dirs + slot * slot_stride : nullptr;
+  uint32_t* my_dirs = DIRS ? dirs + slot * (group_stride * G) : nullptr;
+  const int grp = w.lane() / LG;
   for (;;) {
     int j = 0;
-    if (w.lane() == 0) j = atomicAdd(counter, 1);
+    if (w.lane() == 0) j = atomicAdd(counter, G);
     j = __shfl_sync(0xffffffffu, j, 0);
     if (j >= n_jobs) break;
-    const DevJob J = jobs[j];
-    warp_align<C, DIRS>(w, J, store, sm[warp], my_dirs, ops, &results[j]);
+    const int mine = j + grp;  // jobs are sorted by cost: the groups of a warp get similar work
+    const DevJob* Jp = mine < n_jobs ? jobs + mine : nullptr;
+    warp_align<C, LG, DIRS>(w, Jp, store, sm[warp], my_dirs, group_stride, ops, results + (mine < n_jobs ? mine : 0));
   }
 }
 
@@ -337,6 +340,7 @@ int64_t index_add(gamx_ctx* ctx, uint64_t len) {
 
 struct Group {
   int c = 0;          // stripe width (0: generic)
+  int lg = 32;        // lanes per pair
   bool dirs = false;  // K1 with direction store
   std::vector<uint32_t> job_idx;  // indices into the batch
   uint64_t max_dir_words = 0;
@@ -373,45 +377,57 @@ struct gamx_plan {
 
 namespace {
 
-template <int C, bool DIRS>
+template <int C, int LG, bool DIRS>
 int launch_k1_t(gamx_ctx* ctx, Device& d, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
                 uint64_t stride, uint32_t* ops, DevResult* results) {
   SeqStore st{(const uint32_t*)d.packed.p, (const uint32_t*)d.nmask.p};
-  k1_kernel<C, DIRS><<<g.grid, kWarpsPerBlock * 32, 0, d.stream>>>(jobs, (int)g.job_idx.size(), counter, st, dirs,
-                                                                  stride, ops, results);
+  k1_kernel<C, LG, DIRS><<<g.grid, kWarpsPerBlock * 32, 0, d.stream>>>(jobs, (int)g.job_idx.size(), counter, st, dirs,
+                                                                      stride, ops, results);
   CU(cudaGetLastError());
   return GAMX_OK;
 }
 
-template <int C, bool DIRS>
+template <int C, int LG, bool DIRS>
 int occupancy_k1_t(int* blocks_per_sm) {
-  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k1_kernel<C, DIRS>, kWarpsPerBlock * 32, 0);
+  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k1_kernel<C, LG, DIRS>, kWarpsPerBlock * 32, 0);
 }
 
-#define GAMX_FOR_EACH_C(M) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11) M(12) M(13) M(14) M(15) M(16) M(17)
+#define GAMX_FOR_EACH_C(M, LG) M(2, LG) M(3, LG) M(4, LG) M(5, LG) M(6, LG) M(7, LG) M(8, LG) M(9, LG) M(10, LG) \
+  M(11, LG) M(12, LG) M(13, LG) M(14, LG) M(15, LG) M(16, LG) M(17, LG)
 
-int k1_blocks_per_sm(int c, bool dirs) {
+template <int LG>
+int k1_blocks_per_sm_lg(int c, bool dirs) {
   int b = 0;
   cudaError_t e = cudaErrorInvalidValue;
   switch (c) {
-#define M(N) case N: e = (cudaError_t)(dirs ? occupancy_k1_t<N, true>(&b) : occupancy_k1_t<N, false>(&b)); break;
-    GAMX_FOR_EACH_C(M)
+#define M(N, L) case N: e = (cudaError_t)(dirs ? occupancy_k1_t<N, L, true>(&b) : occupancy_k1_t<N, L, false>(&b)); break;
+    GAMX_FOR_EACH_C(M, LG)
 #undef M
     default: break;
   }
   if (e != cudaSuccess) { cudaGetLastError(); return 0; }
   return b;
 }
+int k1_blocks_per_sm(int c, int lg, bool dirs) {
+  return lg == 32 ? k1_blocks_per_sm_lg<32>(c, dirs) : lg == 16 ? k1_blocks_per_sm_lg<16>(c, dirs) : k1_blocks_per_sm_lg<8>(c, dirs);
+}
 
-int launch_k1(gamx_ctx* ctx, Device& d, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
-              uint64_t stride, uint32_t* ops, DevResult* results) {
+template <int LG>
+int launch_k1_lg(gamx_ctx* ctx, Device& d, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
+                 uint64_t stride, uint32_t* ops, DevResult* results) {
   switch (g.c) {
-#define M(N) case N: return g.dirs ? launch_k1_t<N, true>(ctx, d, g, jobs, counter, dirs, stride, ops, results) \
-                                    : launch_k1_t<N, false>(ctx, d, g, jobs, counter, dirs, stride, ops, results);
-    GAMX_FOR_EACH_C(M)
+#define M(N, L) case N: return g.dirs ? launch_k1_t<N, L, true>(ctx, d, g, jobs, counter, dirs, stride, ops, results) \
+                                       : launch_k1_t<N, L, false>(ctx, d, g, jobs, counter, dirs, stride, ops, results);
+    GAMX_FOR_EACH_C(M, LG)
 #undef M
     default: ctx->err = "internal: bad stripe width"; return GAMX_ERR_INVALID;
   }
+}
+int launch_k1(gamx_ctx* ctx, Device& d, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
+              uint64_t stride, uint32_t* ops, DevResult* results) {
+  if (g.lg == 32) return launch_k1_lg<32>(ctx, d, g, jobs, counter, dirs, stride, ops, results);
+  if (g.lg == 16) return launch_k1_lg<16>(ctx, d, g, jobs, counter, dirs, stride, ops, results);
+  return launch_k1_lg<8>(ctx, d, g, jobs, counter, dirs, stride, ops, results);
 }
 
 bool resolve_views(const gamx_ctx* ctx, const gamx_job& j, SeqView* va, uint64_t* la, SeqView* vb, uint64_t* lb) {
@@ -597,20 +613,20 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
     DevPlan& dp = pl->dps[d];
     dp.n_jobs = (uint32_t)per_dev[d].size();
     std::vector<Group> groups;
-    auto find_group = [&](int c, bool dirs) -> Group& {
-      for (Group& g : groups) if (g.c == c && g.dirs == dirs) return g;
-      Group g; g.c = c; g.dirs = dirs;
+    auto find_group = [&](int c, int lg, bool dirs) -> Group& {
+      for (Group& g : groups) if (g.c == c && g.lg == lg && g.dirs == dirs) return g;
+      Group g; g.c = c; g.lg = lg; g.dirs = dirs;
       groups.push_back(g);
       return groups.back();
     };
     for (uint32_t i : per_dev[d]) {
       Prepared& P = pl->preps[i];
       if (P.cls == kClassWarp) {
-        Group& g = find_group(P.c, pl->modes[i] != GAMX_MODE_SCORE);
+        Group& g = find_group(P.c, P.lg, pl->modes[i] != GAMX_MODE_SCORE);
         g.job_idx.push_back(i);
         g.max_dir_words = std::max(g.max_dir_words, P.dir_words);
       } else {
-        Group& g = find_group(0, true);
+        Group& g = find_group(0, 32, true);
         g.job_idx.push_back(i);
       }
     }
@@ -671,13 +687,14 @@ static int plan_upload(gamx_plan* pl) {
     const uint64_t budget_words = (uint64_t)((free_b + d.dirs.cap) * 0.8) / 4;
     for (Group& g : dp.groups) {
       if (!g.c) { g.grid = (int)((g.job_idx.size() + 63) / 64); continue; }
-      int bps = k1_blocks_per_sm(g.c, g.dirs);
+      int bps = k1_blocks_per_sm(g.c, g.lg, g.dirs);
       if (bps <= 0) { ctx->err = "k1 kernel does not fit on the device"; return GAMX_ERR_CUDA; }
       uint64_t grid = (uint64_t)d.sm_count * bps;
-      const uint64_t need = (g.job_idx.size() + kWarpsPerBlock - 1) / kWarpsPerBlock;
+      const uint64_t pairs_per_block = (uint64_t)kWarpsPerBlock * (32 / g.lg);
+      const uint64_t need = (g.job_idx.size() + pairs_per_block - 1) / pairs_per_block;
       if (need < grid) grid = need;
       if (g.dirs && g.max_dir_words) {
-        const uint64_t per_block = g.max_dir_words * kWarpsPerBlock;
+        const uint64_t per_block = g.max_dir_words * pairs_per_block;
         if (per_block > budget_words) { ctx->err = "direction scratch of one job exceeds device memory"; return GAMX_ERR_NOMEM; }
         if (grid * per_block > budget_words) grid = budget_words / per_block;
         dirs_words = std::max(dirs_words, grid * per_block);

@@ -14,6 +14,7 @@
 #include <string.h>
 #include <ucontext.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../../gam_ngs_b200/csrc/bsw_generic.h"
@@ -30,9 +31,9 @@ struct SimWarp {
   int lane_;
   int lane() const { return lane_; }
   int exchange(int v, int src);
-  int shfl_up(int v, int d) { return exchange(v, lane_ - d >= 0 ? lane_ - d : lane_); }
-  int shfl_down(int v, int d) { return exchange(v, lane_ + d < 32 ? lane_ + d : lane_); }
-  int shfl_xor(int v, int m) { return exchange(v, lane_ ^ m); }
+  int shfl_up(int v, int d, int width) { return exchange(v, (lane_ % width) - d >= 0 ? lane_ - d : lane_); }
+  int shfl_down(int v, int d, int width) { return exchange(v, (lane_ % width) + d < width ? lane_ + d : lane_); }
+  int shfl_xor(int v, int m, int) { return exchange(v, lane_ ^ m); }
   void sync() { exchange(0, lane_); }
 };
 
@@ -97,41 +98,49 @@ int SimWarp::exchange(int v, int src) {
 }
 
 struct WarpArgs {
-  const DevJob* job;
+  const DevJob* job[4];   // per group (null: idle)
+  DevResult* out[4];
   SeqStore store;
   void* smem;
   uint32_t* dirs;
+  uint64_t group_stride;
   uint32_t* ops;
-  DevResult* out;
-  int c;
+  int c, lg;
   bool dirs_on;
 };
 
-template <int C>
+template <int C, int LG>
 void body_c(SimWarp& w, void* p) {
   WarpArgs* a = (WarpArgs*)p;
-  WarpSmem<C>& sm = *(WarpSmem<C>*)a->smem;
-  if (a->dirs_on) warp_align<C, true>(w, *a->job, a->store, sm, a->dirs, a->ops, a->out);
-  else warp_align<C, false>(w, *a->job, a->store, sm, a->dirs, a->ops, a->out);
+  WarpSmem<C, LG>& sm = *(WarpSmem<C, LG>*)a->smem;
+  const int grp = w.lane() / LG;
+  if (a->dirs_on) warp_align<C, LG, true>(w, a->job[grp], a->store, sm, a->dirs, a->group_stride, a->ops, a->out[grp]);
+  else warp_align<C, LG, false>(w, a->job[grp], a->store, sm, a->dirs, a->group_stride, a->ops, a->out[grp]);
 }
 
-template <int C>
+template <int C, int LG>
 void dispatch(WarpArgs& a, bool desc) {
-  std::vector<uint64_t> smem((sizeof(WarpSmem<C>) + 7) / 8);
+  std::vector<uint64_t> smem((sizeof(WarpSmem<C, LG>) + 7) / 8);
   a.smem = smem.data();
   Sched* s = new Sched();
-  s->run(body_c<C>, &a, desc);
+  s->run(body_c<C, LG>, &a, desc);
   delete s;
 }
 
-void run_warp(WarpArgs& a, bool desc) {
+template <int LG>
+void run_warp_lg(WarpArgs& a, bool desc) {
   switch (a.c) {
-#define CASE(N) case N: dispatch<N>(a, desc); break;
+#define CASE(N) case N: dispatch<N, LG>(a, desc); break;
     CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12)
     CASE(13) CASE(14) CASE(15) CASE(16) CASE(17)
 #undef CASE
     default: break;
   }
+}
+void run_warp(WarpArgs& a, bool desc) {
+  if (a.lg == 32) run_warp_lg<32>(a, desc);
+  else if (a.lg == 16) run_warp_lg<16>(a, desc);
+  else run_warp_lg<8>(a, desc);
 }
 
 }  // namespace
@@ -174,10 +183,16 @@ int sim_align(const uint8_t* a, uint64_t a_clen, int a_rc, uint64_t a_off, uint6
   memset(&dr, 0, sizeof(dr));
   std::vector<uint32_t> ops(P.ops_cap / 16 + 1, 0u);
   if (P.cls == kClassWarp) {
-    std::vector<uint32_t> dirs(P.dir_words + 1, 0xdeadbeefu);
+    const int G = 32 / P.lg;
+    std::vector<uint32_t> dirs((P.dir_words + 1) * G, 0xdeadbeefu);
     P.dj.ops_word = 0;
-    WarpArgs wa{&P.dj, st, nullptr, dirs.data(), ops.data(), &dr, P.c, mode != kModeScore};
-    run_warp(wa, lane_order != 0);
+    WarpArgs wa;
+    memset(&wa, 0, sizeof(wa));
+    const int g = (lane_order >> 1) % G;  // which group of the warp runs the job; the others idle
+    wa.job[g] = &P.dj; wa.out[g] = &dr;
+    wa.store = st; wa.dirs = dirs.data(); wa.group_stride = P.dir_words + 1; wa.ops = ops.data();
+    wa.c = P.c; wa.lg = P.lg; wa.dirs_on = mode != kModeScore;
+    run_warp(wa, (lane_order & 1) != 0);
   } else if (P.cls == kClassGeneric) {
     std::vector<int64_t> rows(P.gen_rows + 1, 0x5a5a5a5a5a5a5a5aLL);
     std::vector<uint32_t> dirs(P.dir_words + 1, 0xdeadbeefu);
@@ -192,6 +207,63 @@ int sim_align(const uint8_t* a, uint64_t a_clen, int a_rc, uint64_t a_off, uint6
     }
   }
   return P.cls;
+}
+
+
+// Up to 4 regular jobs with the same band in ONE simulated warp (one per lane group), to exercise
+// groups of different length sharing a step loop.  Jobs are full-contig views.  Returns the number
+// of jobs that ran on the warp kernel (others are skipped and get status -1).
+int sim_align_multi(int n_jobs, const uint8_t* const* a, const uint64_t* la, const uint8_t* const* b,
+                    const uint64_t* lb, const uint64_t* begin_a, const uint64_t* end_a, const uint64_t* begin_b,
+                    const uint64_t* end_b, uint64_t band, int64_t gap, const int* fs, const int* fe, int mode,
+                    int lane_order, gamx_result* results, uint8_t* const* ops_out, uint64_t ops_out_cap) {
+  HostStore hs;
+  std::vector<Prepared> P(n_jobs);
+  std::vector<DevResult> dr(n_jobs);
+  int c = 0, lg = 0, ran = 0;
+  uint64_t stride = 0, ops_words = 0;
+  for (int k = 0; k < n_jobs; k++) {
+    const int64_t ia = hs.add(a[k], la[k]), ib = hs.add(b[k], lb[k]);
+    P[k] = prepare_job(make_view(hs.start[ia], la[k], false, 0), la[k], make_view(hs.start[ib], lb[k], false, 0), lb[k],
+                       begin_a[k], end_a[k], begin_b[k], end_b[k], band, gap, fs[k] != 0, fe[k] != 0, mode);
+    memset(&dr[k], 0, sizeof(DevResult));
+    if (P[k].cls == kClassWarp) {
+      c = P[k].c; lg = P[k].lg;
+      stride = std::max<uint64_t>(stride, P[k].dir_words + 1);
+      P[k].dj.ops_word = ops_words;
+      ops_words += P[k].ops_cap / 16 + 1;
+    }
+  }
+  std::vector<uint32_t> ops(ops_words + 1, 0u);
+  SeqStore st{hs.packed.data(), hs.nmask.data()};
+  if (c) {
+    const int G = 32 / lg;
+    std::vector<uint32_t> dirs(stride * G + 1, 0xdeadbeefu);
+    WarpArgs wa;
+    memset(&wa, 0, sizeof(wa));
+    int g = 0;
+    for (int k = 0; k < n_jobs && g < G; k++)
+      if (P[k].cls == kClassWarp) { wa.job[g] = &P[k].dj; wa.out[g] = &dr[k]; g++; ran++; }
+    wa.store = st; wa.dirs = dirs.data(); wa.group_stride = stride; wa.ops = ops.data();
+    wa.c = c; wa.lg = lg; wa.dirs_on = mode != kModeScore;
+    run_warp(wa, (lane_order & 1) != 0);
+  }
+  int placed = 0;
+  for (int k = 0; k < n_jobs; k++) {
+    if (P[k].cls == kClassWarp && placed < 32 / (lg ? lg : 32)) {
+      placed++;
+      finalize_result(P[k], &dr[k], mode, &results[k]);
+      if (results[k].status == GAMX_JOB_OK && mode == kModeFull && ops_out && ops_out[k])
+        for (uint64_t q = 0; q < results[k].n_ops && q < ops_out_cap; q++) {
+          const uint64_t gpos = results[k].ops_offset + q;
+          ops_out[k][q] = (uint8_t)((ops[gpos >> 4] >> (2 * (gpos & 15))) & 3u);
+        }
+    } else {
+      memset(&results[k], 0, sizeof(gamx_result));
+      results[k].status = -1;
+    }
+  }
+  return ran;
 }
 
 }  // extern "C"

@@ -96,3 +96,33 @@ def sim_align(job, mode=2, force_class=0, lane_order=0, a_rc=0, a_off=0, a_len=U
                           job["gap"], int(job["force_start"]), int(job["force_end"]), mode,
                           force_class, lane_order, C.byref(r), ops.ctypes.data_as(u8p), cap)
     return cls, r, ops
+
+
+def sim_align_multi(jobs, mode=2, lane_order=0):
+    """Runs up to 4 regular jobs (same band and gap) in ONE simulated warp, one per lane group.
+    Returns [(result, ops) or None for jobs that did not run on the warp kernel]."""
+    L = lib()
+    if not hasattr(L, "_multi_ready"):
+        L.sim_align_multi.restype = C.c_int
+        L._multi_ready = True
+    n = len(jobs)
+    u8p, u64 = C.POINTER(C.c_uint8), C.c_uint64
+    keep = []
+    ap, bp, op = (u8p * n)(), (u8p * n)(), (u8p * n)()
+    la, lb, ba, ea, bb, eb = [(u64 * n)() for _ in range(6)]
+    fs, fe = (C.c_int * n)(), (C.c_int * n)()
+    cap = 0
+    for k, j in enumerate(jobs):
+        a = np.ascontiguousarray(j["a"], dtype=np.uint8); b = np.ascontiguousarray(j["b"], dtype=np.uint8)
+        keep += [a, b]
+        ap[k], bp[k] = a.ctypes.data_as(u8p), b.ctypes.data_as(u8p)
+        la[k], lb[k], ba[k], ea[k], bb[k], eb[k] = len(a), len(b), j["begin_a"], j["end_a"], j["begin_b"], j["end_b"]
+        fs[k], fe[k] = int(j["force_start"]), int(j["force_end"])
+        cap = max(cap, len(a) + len(b) + 2 * j["band"] + 64)
+    outs = [np.zeros(cap, dtype=np.uint8) for _ in range(n)]
+    for k in range(n):
+        op[k] = outs[k].ctypes.data_as(u8p)
+    res = (GamxResult * n)()
+    L.sim_align_multi(C.c_int(n), ap, la, bp, lb, ba, ea, bb, eb, u64(jobs[0]["band"]), C.c_int64(jobs[0]["gap"]),
+                      fs, fe, C.c_int(mode), C.c_int(lane_order), res, op, u64(cap))
+    return [(res[k], outs[k]) if res[k].status >= 0 else None for k in range(n)]

@@ -88,3 +88,37 @@ def test_sim_views_reverse_complement_and_offsets():
         _check(job_view, exp, modes=(2,), a_rc=1, a_off=a_off, a_len=a_len, b_rc=1, b_off=b_off, b_len=b_len)
         _check(dict(job_mat, a=a, b=b_store), exp, modes=(2,), a_rc=0, a_off=a_off, a_len=a_len,
                b_rc=1, b_off=b_off, b_len=b_len, force_class=2)
+
+
+@pytest.mark.parametrize("band", [20, 40, 64, 100, 130])
+def test_sim_lane_groups_share_a_step_loop(band):
+    """Bands that run 2 or 4 pairs per warp (LG = 16 / 8): pairs of different length and shape in the
+    same warp must not disturb each other (masked drain, per-group capture windows)."""
+    rng = np.random.default_rng(3000 + band)
+    for rep in range(4):
+        jobs = []
+        for g in range(4):
+            length = int(rng.integers(40, 420))
+            a, b = gen.make_pair(rng, length, div=float(rng.choice([0.0, 0.03, 0.2])), p_n=0.01)
+            la, lb = len(a), len(b)
+            shape = int(rng.integers(0, 3))
+            if shape == 0:
+                w = dict(begin_a=0, end_a=la - 1, begin_b=0, end_b=lb - 1, force_start=False, force_end=False)
+            elif shape == 1:
+                w = dict(begin_a=int(rng.integers(0, la // 2)), end_a=la - 1, begin_b=0, end_b=lb - 1,
+                         force_start=False, force_end=True)
+            else:
+                w = dict(begin_a=2, end_a=la + 9, begin_b=int(rng.integers(0, lb // 2)), end_b=lb + 3,
+                         force_start=True, force_end=False)
+            jobs.append(dict(a=a, b=b, band=band, gap=-8, **w))
+        for mode in (2, 0):
+            out = simlib.sim_align_multi(jobs, mode=mode, lane_order=rep)
+            ran = 0
+            for job, o in zip(jobs, out):
+                if o is None:
+                    continue
+                ran += 1
+                r, ops = o
+                got = simlib.result_to_expect(r, ops if mode == 2 else None, mode)
+                assert got == simlib.project(oracle_expect(job), mode), (band, rep, mode)
+            assert ran >= 1
