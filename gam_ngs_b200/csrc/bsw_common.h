@@ -145,7 +145,11 @@ GAMX_HD int viaddmax(int a, int b, int c) {
 // byte permute: result byte n = byte (sel nibble n & 7) of the 8-byte value {hi,lo}
 GAMX_HD uint32_t prmt(uint32_t lo, uint32_t hi, uint32_t sel) {
 #if defined(__CUDA_ARCH__)
-  return __byte_perm(lo, hi, sel);
+  // raw PRMT: only the low 16 selector bits are read and all our selector nibbles are <= 7, so
+  // the masking __byte_perm adds (one extra LOP3 per selector) is not needed
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(sel));
+  return r;
 #else
   const uint64_t v = ((uint64_t)hi << 32) | lo;
   uint32_t r = 0;

@@ -80,25 +80,29 @@ struct Prepared {
   uint32_t ops_cap;    // ops (multiple of 16), FULL mode only
 };
 
-// Lanes per pair and stripe width for a band: the combination with the fewest idle cell slots
-// (LG*C >= 2*band+1), preferring fewer lanes per pair (more pairs per warp, longer stripes, fewer
-// shuffles per cell) on ties.  LG < 32 only from C >= 5 (short stripes do not amortise a step).
-// GAMX_FORCE_LG=8|16|32 (environment, tuning/experiments only) restricts the choice when feasible.
-inline void geometry_for_band(uint64_t band, int* c_out, int* lg_out) {
+// Lanes per pair (LG) and stripe width (C) for a band.  Score = lane utilisation (2*band+1)/(LG*C),
+// discounted by 12 % when the stripe has to be split into sub-blocks (S < C: one extra shared-memory
+// load per sub-block and step) - the ranking measured on B200 for bands 64/150/256 in both modes
+// (profiles/r1b_geometry_probe.txt).  Ties go to fewer lanes per pair.
+// GAMX_FORCE_LG / GAMX_FORCE_C (environment) override the choice for experiments.
+inline void geometry_for_band(uint64_t band, bool dirs, int* c_out, int* lg_out) {
   static const int forced = [] { const char* e = getenv("GAMX_FORCE_LG"); return e ? atoi(e) : 0; }();
+  static const int forced_c = [] { const char* e = getenv("GAMX_FORCE_C"); return e ? atoi(e) : 0; }();
   const uint64_t y = 2 * band + 1;
   int best_c = 0, best_lg = 0;
-  uint64_t best_slots = ~0ull;
+  double best = -1.0;
   const int lgs[3] = {8, 16, 32};
   for (int n = 0; n < 3; n++) {
     const int lg = lgs[n];
     int c = (int)((y + lg - 1) / lg);
     if (c < 2) c = 2;
+    if (forced_c > c && forced_c <= kMaxC) c = forced_c;
+    while (c <= kMaxC && !stripe_supported(c)) c++;
     if (c > kMaxC) continue;
     if (forced && lg != forced && (y + forced - 1) / forced <= (uint64_t)kMaxC) continue;
-    if (!forced && lg < 32 && c < 5) continue;
-    const uint64_t slots = (uint64_t)lg * c;
-    if (slots < best_slots) { best_slots = slots; best_c = c; best_lg = lg; }
+    double score = (double)y / (double)(lg * c);
+    if (sub_block_of(c, dirs) < c) score *= 0.88;
+    if (score > best + 1e-9) { best = score; best_c = c; best_lg = lg; }
   }
   *c_out = best_c; *lg_out = best_lg;
 }
@@ -144,7 +148,7 @@ inline Prepared prepare_job(const SeqView& a_view, uint64_t la, const SeqView& b
   }
 
   P.cls = kClassWarp;
-  geometry_for_band(band, &P.c, &P.lg);
+  geometry_for_band(band, mode != kModeScore, &P.c, &P.lg);
   DevJob& d = P.dj;
   d.a = a_view;
   d.b = b_view;
@@ -180,7 +184,8 @@ inline Prepared prepare_job(const SeqView& a_view, uint64_t la, const SeqView& b
   d.col_imin = fe ? (x >= 11 ? (int32_t)(x - 1 - kForceMaxGap) : 0x7fffffff) : 0;  // .cc:201
   d.col_zero = end_a >= la ? 1 : 0;
   d.gap = (int32_t)gap;
-  d.mode = mode;
+  static const bool skip_tb = getenv("GAMX_DEBUG_SKIP_TRACEBACK") != nullptr;  // profiling experiments only
+  d.mode = mode | ((skip_tb && mode != kModeScore) ? 0x100 : 0);
   d.ops_cap = P.ops_cap;
   P.dir_words = (mode == kModeScore) ? 0 : k1_dir_words((int)x, (int)band, P.c, P.lg);
   return P;

@@ -38,7 +38,29 @@
 namespace gamx {
 
 constexpr int kTileSteps = 128;  // steps per shared-memory sequence tile
-constexpr int kMaxC = 17;        // widest lane stripe: band <= (32*17-1)/2 = 271
+constexpr int kMaxC = 18;        // widest lane stripe: band <= (32*18-1)/2 = 287
+
+// A lane's stripe of C slots is split into C/S sub-blocks of S slots.  The a-bases of a sub-block
+// live in S registers that are renamed (not moved) across an unrolled group of S steps; each
+// sub-block fetches one new base per step from shared memory.  Unrolling by S instead of C keeps
+// the steady-state loop body around 200-350 instructions for every C (an unroll by C grows as
+// C^2 and overflows the instruction cache: measured "no instruction" stalls at C = 9).
+// S = the largest divisor of C whose unrolled group stays within the budget (about 8 instructions
+// per cell with directions, 3.3 without, plus per-step overhead).
+GAMX_HD constexpr int sub_block_of(int c, bool dirs) {
+  int best = 1;
+  for (int sb = 1; sb <= c; sb++) {
+    if (c % sb) continue;
+    const int body = sb * ((dirs ? 80 : 33) * c / 10 + c / sb + 12);
+    if (body <= (dirs ? 400 : 460)) best = sb;
+  }
+  return best;
+}
+// stripes whose sub-block would degenerate to S = 1 (one shared-memory load per cell and step:
+// measured 2-3x slower) are rounded up to the next supported width by the host
+GAMX_HD constexpr bool stripe_supported(int c) {
+  return c >= 2 && c <= 18 && sub_block_of(c, true) >= 2 && sub_block_of(c, false) >= 2;
+}
 
 template <int C, int LG>
 struct GroupSmem {
@@ -70,9 +92,11 @@ struct EndBest {
 // the group's job (null: idle group) and its result slot.  dirs: the warp's direction scratch,
 // group g uses dirs + g*group_stride.
 template <int C, int LG, bool DIRS, class W>
-GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& S, WarpSmem<C, LG>& wsm, uint32_t* dirs,
+GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<C, LG>& wsm, uint32_t* dirs,
                         uint64_t group_stride, uint32_t* ops_buf, DevResult* out) {
-  static_assert(C >= 2 && C <= kMaxC, "lane stripe width");
+  static_assert(stripe_supported(C), "lane stripe width");
+  constexpr int S = sub_block_of(C, DIRS), NB = C / S;
+  static_assert(NB * S == C, "stripe = whole sub-blocks");
   static_assert(LG == 8 || LG == 16 || LG == 32, "lanes per pair");
   constexpr int SH = DIRS ? 2 : 0;
   const int lane = w.lane();
@@ -80,6 +104,7 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& S, WarpSmem<C, L
   const bool live = Jp != nullptr;
   GroupSmem<C, LG>& sm = wsm.g[grp];
   uint32_t* gdirs = DIRS ? dirs + (uint64_t)grp * group_stride : nullptr;
+  uint32_t* fp = DIRS ? gdirs + gl : nullptr;  // running flush pointer: step blocks are written in order
 
   const int X = live ? Jp->x : 0, B = live ? Jp->band : 0, Y = 2 * B + 1;
   const int ld = (Y - 1) / C, kd = (Y - 1) - ld * C;  // lane/slot of band column 2B
@@ -136,13 +161,13 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& S, WarpSmem<C, L
       const int pa0 = p0 + t0;
       for (int idx = gl; idx < na; idx += LG) {
         const int pos = pa0 + idx;
-        const uint32_t code = (live && pos >= 0 && pos < la) ? load_code(S, va, pos) : (uint32_t)kCodePad;
+        const uint32_t code = (live && pos >= 0 && pos < la) ? load_code(store, va, pos) : (uint32_t)kCodePad;
         sm.asel[idx] = (uint16_t)(0x7770u | code);
       }
       const int nb = kTileSteps + LG - 1;
       for (int idx = gl; idx < nb; idx += LG) {
         const int i = t0 - (LG - 1) + idx;
-        const uint32_t bc = (live && i >= 0 && i < X) ? load_code(S, vb, i) : (uint32_t)kCodePad;
+        const uint32_t bc = (live && i >= 0 && i < X) ? load_code(store, vb, i) : (uint32_t)kCodePad;
         uint32_t lo, hi;
         if (bc < 4u) { lo = (cdX * 0x01010101u) ^ ((cdX ^ cdM) << (8 * bc)); hi = cdZ | (cdP << 8); }
         else if (bc == (uint32_t)kCodeN) { lo = cdZ * 0x01010101u; hi = cdM | (cdP << 8); }
@@ -151,23 +176,24 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& S, WarpSmem<C, L
       }
     }
     w.sync();
-    const uint16_t* pa = sm.asel + (gl * (C - 1) + (C - 1) - t0);  // pa[t]: slot C-1's base at step t
-    const uint64_t* pb = sm.btab + ((LG - 1) - gl - t0);           // pb[t]: table of row t - gl
+    const uint16_t* pa = sm.asel + (gl * (C - 1) - t0);    // pa[t + k]: slot k's base at step t
+    const uint64_t* pb = sm.btab + ((LG - 1) - gl - t0);   // pb[t]: table of row t - gl
     if (t0 == 0) {
-      // slots 0..C-2 of step 0
+      // bases of step 0 (the last slot of every sub-block is (re)loaded by the step itself)
 #pragma unroll
-      for (int k = 0; k < C - 1; k++) A[k] = sm.asel[gl * (C - 1) + k];
+      for (int k = 0; k < C; k++) A[k] = pa[k];
     }
     const int tile_end = imin(t0 + kTileSteps, T_total);
 
-    // C unrolled steps starting at step t (every lane's row >= 1).
+    // S unrolled steps starting at step t (every lane's row >= 1).
     // CAPTURE: latch "last column" cells; MASKED: lanes whose row is past X-1 keep their registers.
 #define GAMX_STEP_GROUP(CAPTURE, MASKED)                                                              \
   {                                                                                                   \
     const int dcap = tcap0 - t;                                                                       \
-    _Pragma("unroll") for (int u = 0; u < C; u++) {                                                   \
+    _Pragma("unroll") for (int u = 0; u < S; u++) {                                                   \
       const int tt = t + u;                                                                           \
-      A[(u + C - 1) % C] = pa[tt];                                                                    \
+      _Pragma("unroll") for (int sb = 0; sb < NB; sb++)                                               \
+          A[sb * S + (u + S - 1) % S] = pa[tt + sb * S + S - 1];                                      \
       const uint64_t tb = pb[tt];                                                                     \
       const uint32_t tlo = (uint32_t)tb, thi = (uint32_t)(tb >> 32);                                  \
       int left = w.shfl_up(H[C - 1], 1, LG);                                                          \
@@ -176,7 +202,7 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& S, WarpSmem<C, L
       int right = 0;                                                                                  \
       _Pragma("unroll") for (int k = 0; k < C; k++) {                                                 \
         const int up = (k == C - 1) ? right : H[(k + 1) % C];                                         \
-        const int cd = (int)prmt(tlo, thi, A[(u + k) % C]);                                           \
+        const int cd = (int)prmt(tlo, thi, A[(k / S) * S + (u + k % S) % S]);                         \
         const int m = viaddmax(up, U[k], left);                                                       \
         const int v = viaddmax(H[k], cd, m);                                                          \
         int hc = v;                                                                                   \
@@ -191,19 +217,19 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& S, WarpSmem<C, L
         if (k == 0) right = w.shfl_down(H[0], 1, LG);                                                 \
       }                                                                                               \
       if (DIRS && (tt & 15) == 15) {                                                                  \
-        _Pragma("unroll") for (int k = 0; k < C; k++)                                                 \
-            gdirs[((uint32_t)(tt >> 4) * C + k) * LG + gl] = accV[k] - accH[k];                        \
+        _Pragma("unroll") for (int k = 0; k < C; k++) fp[k * LG] = accV[k] - accH[k];                  \
+        fp += C * LG;                                                                                 \
       }                                                                                               \
     }                                                                                                 \
-    t += C;                                                                                           \
+    t += S;                                                                                           \
   }
 
     while (t < tile_end) {
       // the warp's final step always takes the general path (it flushes the partial direction words)
-      const bool grouped = (t >= LG) && (t + C <= tile_end) && (t + C - 1 <= T_total - 2);
+      const bool grouped = (t >= LG) && (t + S <= tile_end) && (t + S - 1 <= T_total - 2);
       if (grouped) {
-        const bool masked = t + C - 1 > x_min - 1;
-        const bool capture = !(t + C - 1 < win_lo || t > win_hi);
+        const bool masked = t + S - 1 > x_min - 1;
+        const bool capture = !(t + S - 1 < win_lo || t > win_hi);
         if (!masked && !capture) GAMX_STEP_GROUP(false, false)
         else if (!masked) GAMX_STEP_GROUP(true, false)
         else GAMX_STEP_GROUP(true, true)
@@ -214,7 +240,8 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& S, WarpSmem<C, L
       {
         const int i = t - gl;
         const bool act = live && (i >= 0) && (i < X);
-        A[C - 1] = pa[t];
+#pragma unroll
+        for (int sb = 0; sb < NB; sb++) A[sb * S + S - 1] = pa[t + sb * S + S - 1];
         const uint64_t tb = pb[t];
         const uint32_t tlo = (uint32_t)tb, thi = (uint32_t)(tb >> 32);
         int left = w.shfl_up(H[C - 1], 1, LG);
@@ -267,11 +294,13 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& S, WarpSmem<C, L
         for (int k = 0; k < C; k++)
           if (dc == k) capv[k] = H[k];
 #pragma unroll
-        for (int k = 0; k < C - 1; k++) A[k] = A[k + 1];
+        for (int k = 0; k < C; k++)
+          if (k % S != S - 1) A[k] = A[k + 1];
         if (DIRS && ((t & 15) == 15 || t == T_total - 1)) {
           const int sh = 2 * (15 - (t & 15));
 #pragma unroll
-          for (int k = 0; k < C; k++) gdirs[((uint32_t)(t >> 4) * C + k) * LG + gl] = (accV[k] - accH[k]) << sh;
+          for (int k = 0; k < C; k++) fp[k * LG] = (accV[k] - accH[k]) << sh;
+          fp += C * LG;
         }
         t++;
       }
@@ -325,8 +354,8 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& S, WarpSmem<C, L
       R.score = best.val; R.end_i = ei; R.end_j = ej;
       if (p0 + ei + ej >= la) {
         R.status = kStatusOutOfRange;  // first traceback step reads a.at(pos), .cc:231/:265
-      } else if (DIRS) {
-        k1_traceback<C, LG>(gdirs, ei, ej, p0, Jp->mode == kModeFull, ops_buf + Jp->ops_word, Jp->ops_cap, R);
+      } else if (DIRS && !(Jp->mode & 0x100)) {  // 0x100: debug knob GAMX_DEBUG_SKIP_TRACEBACK
+        k1_traceback<C, LG>(gdirs, ei, ej, p0, (Jp->mode & 0xff) == kModeFull, ops_buf + Jp->ops_word, Jp->ops_cap, R);
         R.ops_start = Jp->ops_word * 16 + Jp->ops_cap - R.n_ops;
       }
     }
