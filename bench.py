@@ -202,38 +202,18 @@ def main():
         return
 
     import torch
-    import torch.distributed as dist
     import gam_ngs_b200 as g
+    from gam_ngs_b200.dist import Ranks, shard_seed
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    ranks = Ranks()  # NCCL when WORLD_SIZE > 1: barrier + max/sum over ranks only, no data-path collective
+    barrier, max_over_ranks, sum_over_ranks = ranks.barrier, ranks.max, ranks.sum
 
     # ---- synthetic workload (independent pairs per rank: the batch shards with no collective) ---
     t_gen = time.perf_counter()
-    a, al, b, bl = make_workload(spec, 1000 + rank)
+    a, al, b, bl = make_workload(spec, shard_seed(1000, rank))
     n = len(al)
     total_bases = len(a) + len(b)
     host = torch.empty(total_bases, dtype=torch.uint8, pin_memory=True)  # pinned host copy of the inputs
@@ -356,8 +336,7 @@ def main():
                 "wall_ms_per_step": wall_s / args.steps * 1e3, "jobs_ok": ok, "parity_checked": checked,
                 "gen_seconds": t_gen}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    ranks.close()
 
 
 if __name__ == "__main__":

@@ -73,6 +73,7 @@ EXPORTS = [
     "gamx_ops_capacity", "gamx_align_batch", "gamx_unpack_ops", "gamx_cigar_rle",
     "gamx_plan_create", "gamx_plan_run", "gamx_plan_sync", "gamx_plan_fetch", "gamx_plan_last_ms",
     "gamx_plan_cells", "gamx_plan_kernel_launches", "gamx_plan_destroy", "gamx_measure_int_peak",
+    "gamx_shard_by_cost",
 ]
 
 _lib = None

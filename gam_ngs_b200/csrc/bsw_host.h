@@ -73,11 +73,11 @@ struct Prepared {
   uint64_t cells;      // x_size * (2*band+1), the unit of the GCUPS metric
   uint64_t la, lb;
   uint64_t begin_b;
-  DevJob dj;
-  GenJob gj;
   uint64_t dir_words;  // direction scratch this job needs (fast: K1 layout, generic: row-major)
   uint64_t gen_rows;   // generic: int64 row scratch (2*y_size)
   uint32_t ops_cap;    // ops (multiple of 16), FULL mode only
+  uint32_t gen_idx;    // kClassGeneric: index of the job's GenJob in the caller's side array
+  DevJob dj;           // kClassWarp
 };
 
 // Lanes per pair (LG) and stripe width (C) for a band.  Score = lane utilisation (2*band+1)/(LG*C),
@@ -108,14 +108,14 @@ inline void geometry_for_band(uint64_t band, bool dirs, int* c_out, int* lg_out)
 }
 
 // a_view / b_view: views of position 0 of a and b; la / lb: view lengths (a.size(), b.size()).
-inline Prepared prepare_job(const SeqView& a_view, uint64_t la, const SeqView& b_view, uint64_t lb,
-                            uint64_t begin_a, uint64_t end_a, uint64_t begin_b, uint64_t end_b,
-                            uint64_t band, int64_t gap, bool fs, bool fe, int mode) {
-  Prepared P;
+// Fills P; for jobs classified kClassGeneric the raw arguments are written to *gj (when not null).
+inline void prepare_job(Prepared& P, GenJob* gj, const SeqView& a_view, uint64_t la, const SeqView& b_view,
+                        uint64_t lb, uint64_t begin_a, uint64_t end_a, uint64_t begin_b, uint64_t end_b,
+                        uint64_t band, int64_t gap, bool fs, bool fe, int mode) {
   memset(&P, 0, sizeof(P));
   P.la = la; P.lb = lb; P.begin_b = begin_b;
   // banded_smith_waterman.cc:90-95 with the reference's unsigned arithmetic
-  if (end_b < begin_b) { P.cls = kClassEarly; P.early_status = kStatusEmpty; return P; }
+  if (end_b < begin_b) { P.cls = kClassEarly; P.early_status = kStatusEmpty; return; }
   uint64_t eb = end_b;
   if (eb >= lb) eb = lb - 1;
   uint64_t x = eb - begin_b + 1;
@@ -125,7 +125,7 @@ inline Prepared prepare_job(const SeqView& a_view, uint64_t la, const SeqView& b
   P.x_size = x;
   const uint64_t y = 2 * band + 1;
   P.cells = x * y;
-  if (x == 0) { P.cls = kClassEarly; P.early_status = kStatusUndefined; return P; }
+  if (x == 0) { P.cls = kClassEarly; P.early_status = kStatusUndefined; return; }
 
   // upper bound on the edit-string length: (#DIAG+#UP) <= x, (#DIAG+#LEFT) <= |a|,
   // #LEFT <= #UP + 2*band + 1
@@ -137,14 +137,17 @@ inline Prepared prepare_job(const SeqView& a_view, uint64_t la, const SeqView& b
                        la < (1ull << 30) && lb < (1ull << 30) && band < (1ull << 20);
   if (!regular) {
     P.cls = kClassGeneric;
-    GenJob& g = P.gj;
-    g.a = a_view; g.b = b_view; g.la = la; g.lb = lb;
-    g.begin_a = begin_a; g.end_a = end_a; g.begin_b = begin_b; g.end_b = end_b;
-    g.band = band; g.gap = gap; g.force_start = fs; g.force_end = fe; g.mode = mode;
-    g.ops_cap = P.ops_cap; g.x_size = x;
+    if (gj) {
+      GenJob& g = *gj;
+      memset(&g, 0, sizeof(g));
+      g.a = a_view; g.b = b_view; g.la = la; g.lb = lb;
+      g.begin_a = begin_a; g.end_a = end_a; g.begin_b = begin_b; g.end_b = end_b;
+      g.band = band; g.gap = gap; g.force_start = fs; g.force_end = fe; g.mode = mode;
+      g.ops_cap = P.ops_cap; g.x_size = x;
+    }
     P.dir_words = (x * y + 15) / 16;
     P.gen_rows = 2 * y;
-    return P;
+    return;
   }
 
   P.cls = kClassWarp;
@@ -188,7 +191,6 @@ inline Prepared prepare_job(const SeqView& a_view, uint64_t la, const SeqView& b
   d.mode = mode | ((skip_tb && mode != kModeScore) ? 0x100 : 0);
   d.ops_cap = P.ops_cap;
   P.dir_words = (mode == kModeScore) ? 0 : k1_dir_words((int)x, (int)band, P.c, P.lg);
-  return P;
 }
 
 // ---- device result -> gamx_result -----------------------------------------------------------

@@ -18,7 +18,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <memory>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -364,7 +368,8 @@ struct DevPlan {
 struct gamx_plan {
   gamx_ctx* ctx = nullptr;
   uint64_t n = 0;
-  std::vector<Prepared> preps;
+  std::unique_ptr<Prepared[]> preps;  // uninitialised storage, filled in parallel
+  std::vector<GenJob> gens;           // raw arguments of the (rare) generic-kernel jobs
   std::vector<uint8_t> modes;
   std::vector<int> job_dev;       // device of each job (-1: early)
   std::vector<uint32_t> job_res;  // index into that device's result array
@@ -428,6 +433,59 @@ int launch_k1(gamx_ctx* ctx, Device& d, const Group& g, const DevJob* jobs, int*
   if (g.lg == 32) return launch_k1_lg<32>(ctx, d, g, jobs, counter, dirs, stride, ops, results);
   if (g.lg == 16) return launch_k1_lg<16>(ctx, d, g, jobs, counter, dirs, stride, ops, results);
   return launch_k1_lg<8>(ctx, d, g, jobs, counter, dirs, stride, ops, results);
+}
+
+// splits [0, n) over the host's cores; fn(begin, end) must be thread-safe
+template <class F>
+void parallel_for(uint64_t n, F fn) {
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt == 0) nt = 4;
+  if (nt > 32) nt = 32;
+  if (n < 20000 || nt == 1) { fn((uint64_t)0, n); return; }
+  std::vector<std::thread> th;
+  const uint64_t chunk = (n + nt - 1) / nt;
+  for (unsigned t = 0; t < nt; t++) {
+    const uint64_t b = t * chunk, e = std::min(n, b + chunk);
+    if (b >= e) break;
+    th.emplace_back([=] { fn(b, e); });
+  }
+  for (auto& t : th) t.join();
+}
+
+// stable LSD radix sort of job indices by descending cost
+void sort_by_cost_desc(std::vector<uint32_t>& order, const Prepared* preps) {
+  const size_t m = order.size();
+  if (m < 2) return;
+  uint64_t maxc = 0;
+  for (uint32_t i : order) maxc = std::max(maxc, preps[i].cells);
+  std::vector<uint64_t> key(m), key2(m);
+  for (size_t k = 0; k < m; k++) key[k] = maxc - preps[order[k]].cells;  // ascending key = descending cost
+  std::vector<uint32_t> tmp(m);
+  int bits = 0;
+  while (bits < 64 && (maxc >> bits)) bits++;
+  for (int sh = 0; sh < bits; sh += 11) {
+    size_t cnt[2049] = {0};
+    for (size_t k = 0; k < m; k++) cnt[((key[k] >> sh) & 2047) + 1]++;
+    for (int b = 0; b < 2048; b++) cnt[b + 1] += cnt[b];
+    for (size_t k = 0; k < m; k++) {
+      const size_t pos = cnt[(key[k] >> sh) & 2047]++;
+      tmp[pos] = order[k]; key2[pos] = key[k];
+    }
+    order.swap(tmp); key.swap(key2);
+  }
+}
+
+// Longest-processing-time greedy: jobs visited in descending cost, each to the least loaded shard.
+// `order` must already be sorted by descending cost.
+template <class CostOf>
+void lpt_assign(const std::vector<uint32_t>& order, int n_shards, CostOf cost_of, int* shard_of) {
+  std::vector<uint64_t> load(n_shards, 0);
+  for (uint32_t i : order) {
+    int best = 0;
+    for (int d = 1; d < n_shards; d++) if (load[d] < load[best]) best = d;
+    load[best] += cost_of(i) + 1;
+    shard_of[i] = best;
+  }
 }
 
 bool resolve_views(const gamx_ctx* ctx, const gamx_job& j, SeqView* va, uint64_t* la, SeqView* vb, uint64_t* lb) {
@@ -524,14 +582,23 @@ int64_t gamx_add_contig_ascii(gamx_ctx* ctx, const char* seq, uint64_t len) {
 int64_t gamx_add_contigs(gamx_ctx* ctx, const uint8_t* codes, const uint64_t* lengths, uint64_t n) {
   if (!ctx || !lengths || n == 0) return GAMX_ERR_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  static const bool timing = getenv("GAMX_TIMING") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
   if (int rc = flush_pending(ctx)) return rc;
   const size_t first = ctx->store.start.size();
+  ctx->store.start.reserve(first + n);
+  ctx->store.length.reserve(first + n);
   for (uint64_t c = 0; c < n; c++) {
     if (lengths[c] >= (1ull << 31)) { ctx->err = "contig longer than 2^31 bases"; return GAMX_ERR_INVALID; }
     index_add(ctx, lengths[c]);
   }
   ctx->pending_first = ctx->store.start.size();
+  const auto t1 = std::chrono::steady_clock::now();
   if (int rc = store_upload(ctx, codes, first, n)) return rc;
+  if (timing)
+    fprintf(stderr, "[gamx] add_contigs n=%llu: index %.1f ms, upload+pack %.1f ms\n", (unsigned long long)n,
+            std::chrono::duration<double, std::milli>(t1 - t0).count(),
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
   return (int64_t)first;
 }
 
@@ -557,8 +624,9 @@ uint64_t gamx_ops_capacity(const gamx_ctx* ctx, const gamx_job* jobs, uint64_t n
     SeqView va, vb;
     uint64_t la, lb;
     if (!resolve_views(ctx, jobs[i], &va, &la, &vb, &lb)) continue;
-    Prepared P = prepare_job(va, la, vb, lb, jobs[i].begin_a, jobs[i].end_a, jobs[i].begin_b, jobs[i].end_b,
-                             jobs[i].band, jobs[i].gap, jobs[i].force_start != 0, jobs[i].force_end != 0, jobs[i].mode);
+    Prepared P;
+    prepare_job(P, nullptr, va, la, vb, lb, jobs[i].begin_a, jobs[i].end_a, jobs[i].begin_b, jobs[i].end_b,
+                jobs[i].band, jobs[i].gap, jobs[i].force_start != 0, jobs[i].force_end != 0, jobs[i].mode);
     total += P.ops_cap;
   }
   return total;
@@ -570,64 +638,89 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
   gamx_plan* pl = new gamx_plan();
   pl->ctx = ctx;
   pl->n = n;
-  pl->preps.resize(n);
+  pl->preps.reset(new Prepared[n ? n : 1]);
   pl->modes.resize(n);
   pl->job_dev.assign(n, -1);
   pl->job_res.assign(n, 0);
   const int nd = (int)ctx->devs.size();
   pl->dps.resize(nd);
   for (int d = 0; d < nd; d++) pl->dps[d].dev = d;
+  Prepared* preps = pl->preps.get();
 
+  // 1. guards, sizes and classification of every job (banded_smith_waterman.cc:90-97), in parallel
+  std::atomic<int64_t> bad(-1);
+  parallel_for(n, [&](uint64_t b, uint64_t e) {
+    for (uint64_t i = b; i < e; i++) {
+      const gamx_job& j = jobs[i];
+      SeqView va, vb;
+      uint64_t la, lb;
+      if (j.mode > GAMX_MODE_FULL || !resolve_views(ctx, j, &va, &la, &vb, &lb)) {
+        bad.store((int64_t)i);
+        preps[i].cls = kClassEarly; preps[i].cells = 0;
+        continue;
+      }
+      pl->modes[i] = j.mode;
+      prepare_job(preps[i], nullptr, va, la, vb, lb, j.begin_a, j.end_a, j.begin_b, j.end_b, j.band, j.gap,
+                  j.force_start != 0, j.force_end != 0, j.mode);
+    }
+  });
+  if (bad.load() >= 0) {
+    ctx->err = "job " + std::to_string(bad.load()) + ": unknown contig id, view outside the contig, or bad mode";
+    delete pl;
+    return GAMX_ERR_INVALID;
+  }
   std::vector<uint32_t> order;
   order.reserve(n);
   for (uint64_t i = 0; i < n; i++) {
-    const gamx_job& j = jobs[i];
-    SeqView va, vb;
-    uint64_t la, lb;
-    if (j.mode > GAMX_MODE_FULL || !resolve_views(ctx, j, &va, &la, &vb, &lb)) {
-      ctx->err = "job " + std::to_string(i) + ": unknown contig id, view outside the contig, or bad mode";
-      delete pl;
-      return GAMX_ERR_INVALID;
+    pl->cells += preps[i].cells;
+    if (preps[i].cls == kClassEarly) continue;
+    order.push_back((uint32_t)i);
+    if (preps[i].cls == kClassGeneric) {  // rare: keep the raw arguments for the literal kernel
+      const gamx_job& j = jobs[i];
+      SeqView va, vb;
+      uint64_t la, lb;
+      resolve_views(ctx, j, &va, &la, &vb, &lb);
+      Prepared tmp;
+      GenJob gj;
+      prepare_job(tmp, &gj, va, la, vb, lb, j.begin_a, j.end_a, j.begin_b, j.end_b, j.band, j.gap,
+                  j.force_start != 0, j.force_end != 0, j.mode);
+      preps[i].gen_idx = (uint32_t)pl->gens.size();
+      pl->gens.push_back(gj);
     }
-    pl->modes[i] = j.mode;
-    pl->preps[i] = prepare_job(va, la, vb, lb, j.begin_a, j.end_a, j.begin_b, j.end_b, j.band, j.gap,
-                               j.force_start != 0, j.force_end != 0, j.mode);
-    pl->cells += pl->preps[i].cells;
-    if (pl->preps[i].cls != kClassEarly) order.push_back((uint32_t)i);
   }
-  // cost-balanced sharding (longest-processing-time greedy on DP cells); no collective is needed,
-  // every job is independent
-  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return pl->preps[x].cells > pl->preps[y].cells; });
-  std::vector<uint64_t> load(nd, 0);
+  // 2. cost-balanced sharding (longest-processing-time greedy on DP cells); no collective is needed,
+  //    every job is independent.  The descending order is also the launch order, so
+  //    the persistent warps of a kernel pick up the expensive jobs first.
+  sort_by_cost_desc(order, preps);
   std::vector<std::vector<uint32_t>> per_dev(nd);
-  for (uint32_t i : order) {
-    int best = 0;
-    for (int d = 1; d < nd; d++) if (load[d] < load[best]) best = d;
-    load[best] += pl->preps[i].cells + 1;
-    per_dev[best].push_back(i);
-    pl->job_dev[i] = best;
+  if (nd == 1) {
+    per_dev[0].swap(order);
+    for (uint32_t i : per_dev[0]) pl->job_dev[i] = 0;
+  } else {
+    lpt_assign(order, nd, [&](uint32_t i) { return preps[i].cells; }, pl->job_dev.data());
+    for (uint32_t i : order) per_dev[pl->job_dev[i]].push_back(i);
   }
-  // per device: group by kernel family
+  // 3. per device: group by kernel family
   uint64_t ops_base = 0;
   for (int d = 0; d < nd; d++) {
     DevPlan& dp = pl->dps[d];
     dp.n_jobs = (uint32_t)per_dev[d].size();
     std::vector<Group> groups;
-    auto find_group = [&](int c, int lg, bool dirs) -> Group& {
-      for (Group& g : groups) if (g.c == c && g.lg == lg && g.dirs == dirs) return g;
+    auto find_group = [&](int c, int lg, bool dirs) -> int {
+      for (size_t g = 0; g < groups.size(); g++)
+        if (groups[g].c == c && groups[g].lg == lg && groups[g].dirs == dirs) return (int)g;
       Group g; g.c = c; g.lg = lg; g.dirs = dirs;
       groups.push_back(g);
-      return groups.back();
+      return (int)groups.size() - 1;
     };
     for (uint32_t i : per_dev[d]) {
-      Prepared& P = pl->preps[i];
+      const Prepared& P = preps[i];
       if (P.cls == kClassWarp) {
-        Group& g = find_group(P.c, P.lg, pl->modes[i] != GAMX_MODE_SCORE);
+        Group& g = groups[find_group(P.c, P.lg, pl->modes[i] != GAMX_MODE_SCORE)];
         g.job_idx.push_back(i);
         g.max_dir_words = std::max(g.max_dir_words, P.dir_words);
       } else {
-        Group& g = find_group(0, 32, true);
-        g.job_idx.push_back(i);
+        groups[find_group(0, 32, true)].job_idx.push_back(i);
       }
     }
     uint32_t res_off = 0, dj_off = 0, gj_off = 0;
@@ -639,13 +732,14 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
       else { g.job_off = gj_off; gj_off += (uint32_t)g.job_idx.size(); }
       for (size_t k = 0; k < g.job_idx.size(); k++) {
         const uint32_t i = g.job_idx[k];
-        Prepared& P = pl->preps[i];
+        Prepared& P = preps[i];
         pl->job_res[i] = g.res_off + (uint32_t)k;
         if (g.c) { P.dj.ops_word = ops_words; }
         else {
-          P.gj.ops_word = ops_words;
-          P.gj.rows_off = dp.grows; dp.grows += P.gen_rows;
-          P.gj.dirs_off = dp.gdirs; dp.gdirs += P.dir_words;
+          GenJob& gj = pl->gens[P.gen_idx];
+          gj.ops_word = ops_words;
+          gj.rows_off = dp.grows; dp.grows += P.gen_rows;
+          gj.dirs_off = dp.gdirs; dp.gdirs += P.dir_words;
         }
         ops_words += P.ops_cap / 16;
       }
@@ -705,11 +799,15 @@ static int plan_upload(gamx_plan* pl) {
     if (int rc = ensure_dev(ctx, d.dirs, dirs_words * 4 + 64)) return rc;
     DevJob* hj = (DevJob*)d.h_jobs.p;
     GenJob* hg = (GenJob*)d.h_gjobs.p;
-    for (const Group& g : dp.groups)
-      for (size_t k = 0; k < g.job_idx.size(); k++) {
-        if (g.c) hj[g.job_off + k] = pl->preps[g.job_idx[k]].dj;
-        else hg[g.job_off + k] = pl->preps[g.job_idx[k]].gj;
-      }
+    for (const Group& g : dp.groups) {
+      const Prepared* preps = pl->preps.get();
+      parallel_for(g.job_idx.size(), [&](uint64_t b, uint64_t e) {
+        for (uint64_t k = b; k < e; k++) {
+          if (g.c) hj[g.job_off + k] = preps[g.job_idx[k]].dj;
+          else hg[g.job_off + k] = pl->gens[preps[g.job_idx[k]].gen_idx];
+        }
+      });
+    }
     if (dp.n_dev_jobs)
       CU(cudaMemcpyAsync(d.jobs.p, hj, (size_t)dp.n_dev_jobs * sizeof(DevJob), cudaMemcpyHostToDevice, d.stream));
     if (dp.n_gen_jobs)
@@ -807,18 +905,20 @@ static int plan_fetch_locked(gamx_plan* pl, gamx_result* results, uint8_t* ops_b
     CU(cudaStreamSynchronize(d.stream));
     if (dp.ops_words) memcpy(ops_buf + dp.ops_base / 4, d.h_ops.p, dp.ops_words * 4);
   }
-  for (uint64_t i = 0; i < pl->n; i++) {
-    const Prepared& P = pl->preps[i];
-    const DevResult* dr = nullptr;
-    uint64_t base = 0;
-    if (pl->job_dev[i] >= 0) {
-      const DevPlan& dp = pl->dps[pl->job_dev[i]];
-      dr = (const DevResult*)ctx->devs[dp.dev].h_results.p + pl->job_res[i];
-      base = dp.ops_base;
+  parallel_for(pl->n, [&](uint64_t b, uint64_t e) {
+    for (uint64_t i = b; i < e; i++) {
+      const Prepared& P = pl->preps[i];
+      const DevResult* dr = nullptr;
+      uint64_t base = 0;
+      if (pl->job_dev[i] >= 0) {
+        const DevPlan& dp = pl->dps[pl->job_dev[i]];
+        dr = (const DevResult*)ctx->devs[dp.dev].h_results.p + pl->job_res[i];
+        base = dp.ops_base;
+      }
+      finalize_result(P, dr, pl->modes[i], &results[i]);
+      results[i].ops_offset += base;
     }
-    finalize_result(P, dr, pl->modes[i], &results[i]);
-    results[i].ops_offset += base;
-  }
+  });
   return GAMX_OK;
 }
 
@@ -843,6 +943,12 @@ int gamx_align_batch(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_resul
                      uint64_t ops_cap) {
   if (!ctx || (!jobs && n) || (!results && n)) return GAMX_ERR_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  static const bool timing = getenv("GAMX_TIMING") != nullptr;  // prints a host-side phase breakdown
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
+  const auto t0 = now();
   gamx_plan* pl = nullptr;
   int rc = plan_build(ctx, jobs, n, &pl);
   if (rc) return rc;
@@ -851,11 +957,18 @@ int gamx_align_batch(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_resul
     delete pl;
     return GAMX_ERR_OPS_CAPACITY;
   }
+  const auto t1 = now();
   rc = plan_upload(pl);
+  const auto t2 = now();
   if (!rc) rc = plan_run_locked(pl);
   if (!rc) rc = plan_sync_locked(pl);
+  const auto t3 = now();
   if (!rc) rc = plan_fetch_locked(pl, results, ops_buf, ops_cap);
+  const auto t4 = now();
   delete pl;
+  if (timing)
+    fprintf(stderr, "[gamx] align_batch n=%llu: build %.1f ms, upload %.1f ms, run+sync %.1f ms, fetch %.1f ms, free %.1f ms\n",
+            (unsigned long long)n, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, now()));
   return rc;
 }
 
@@ -878,6 +991,15 @@ uint64_t gamx_cigar_rle(const uint8_t* ops_buf, uint64_t ops_offset, uint64_t n_
   }
   if (len) { if (n_runs < cap && runs) runs[n_runs] = (len << 2) | cur; n_runs++; }
   return n_runs;
+}
+
+int gamx_shard_by_cost(const uint64_t* cost, uint64_t n, int n_shards, int32_t* shard_out) {
+  if (!cost || !shard_out || n_shards <= 0 || n >= (1ull << 32)) return GAMX_ERR_INVALID;
+  std::vector<uint32_t> order(n);
+  for (uint64_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost[a] > cost[b]; });
+  lpt_assign(order, n_shards, [&](uint32_t i) { return cost[i]; }, shard_out);
+  return GAMX_OK;
 }
 
 double gamx_measure_int_peak(gamx_ctx* ctx, int dev_index, int which) {

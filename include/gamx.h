@@ -190,6 +190,13 @@ GAMX_API uint64_t gamx_plan_cells(const gamx_plan* plan);        /* sum of x_siz
 GAMX_API uint64_t gamx_plan_kernel_launches(const gamx_plan* plan); /* kernels launched per run        */
 GAMX_API void gamx_plan_destroy(gamx_plan* plan);
 
+/* ---- sharding ------------------------------------------------------------------------ */
+
+/* The cost-balanced split gamx_align_batch applies over a context's devices (longest-processing-
+ * time greedy on DP cells), exposed so callers that run one process per GPU can shard a batch the
+ * same way: shard_out[i] in [0, n_shards) for job i of cost cost[i].  Pure host code. */
+GAMX_API int gamx_shard_by_cost(const uint64_t* cost, uint64_t n, int n_shards, int32_t* shard_out);
+
 /* ---- microbenchmarks used for the roofline denominators (bench.py) ------------------ */
 
 /* Measures the integer/DPX issue peak of device `dev_index` of the context with a

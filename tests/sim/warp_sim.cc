@@ -161,21 +161,21 @@ int sim_align(const uint8_t* a, uint64_t a_clen, int a_rc, uint64_t a_off, uint6
   if (b_len == UINT64_MAX) b_len = b_clen - b_off;
   const SeqView va = make_view(hs.start[ia], a_clen, a_rc != 0, a_off);
   const SeqView vb = make_view(hs.start[ib], b_clen, b_rc != 0, b_off);
-  Prepared P = prepare_job(va, a_len, vb, b_len, begin_a, end_a, begin_b, end_b, band, gap, fs != 0,
-                           fe != 0, mode);
+  Prepared P;
+  GenJob GJ;
+  memset(&GJ, 0, sizeof(GJ));
+  prepare_job(P, &GJ, va, a_len, vb, b_len, begin_a, end_a, begin_b, end_b, band, gap, fs != 0, fe != 0, mode);
   if (force_class == kClassGeneric && P.cls == kClassWarp) {
     // re-prepare as generic
-    Prepared Q = P;
-    Q.cls = kClassGeneric;
-    GenJob& g = Q.gj;
+    P.cls = kClassGeneric;
+    GenJob& g = GJ;
     memset(&g, 0, sizeof(g));
     g.a = va; g.b = vb; g.la = a_len; g.lb = b_len;
     g.begin_a = begin_a; g.end_a = end_a; g.begin_b = begin_b; g.end_b = end_b;
     g.band = band; g.gap = gap; g.force_start = fs; g.force_end = fe; g.mode = mode;
     g.ops_cap = P.ops_cap; g.x_size = P.x_size;
-    Q.dir_words = (P.x_size * (2 * band + 1) + 15) / 16;
-    Q.gen_rows = 2 * (2 * band + 1);
-    P = Q;
+    P.dir_words = (P.x_size * (2 * band + 1) + 15) / 16;
+    P.gen_rows = 2 * (2 * band + 1);
   }
   SeqStore st{hs.packed.data(), hs.nmask.data()};
   DevResult dr;
@@ -195,8 +195,8 @@ int sim_align(const uint8_t* a, uint64_t a_clen, int a_rc, uint64_t a_off, uint6
   } else if (P.cls == kClassGeneric) {
     std::vector<int64_t> rows(P.gen_rows + 1, 0x5a5a5a5a5a5a5a5aLL);
     std::vector<uint32_t> dirs(P.dir_words + 1, 0xdeadbeefu);
-    P.gj.ops_word = 0;
-    generic_align(P.gj, st, rows.data(), dirs.data(), ops.data(), dr);
+    GJ.ops_word = 0;
+    generic_align(GJ, st, rows.data(), dirs.data(), ops.data(), dr);
   }
   finalize_result(P, &dr, mode, result);
   if (result->status == GAMX_JOB_OK && mode == kModeFull && ops_out) {
@@ -223,8 +223,8 @@ int sim_align_multi(int n_jobs, const uint8_t* const* a, const uint64_t* la, con
   uint64_t stride = 0, ops_words = 0;
   for (int k = 0; k < n_jobs; k++) {
     const int64_t ia = hs.add(a[k], la[k]), ib = hs.add(b[k], lb[k]);
-    P[k] = prepare_job(make_view(hs.start[ia], la[k], false, 0), la[k], make_view(hs.start[ib], lb[k], false, 0), lb[k],
-                       begin_a[k], end_a[k], begin_b[k], end_b[k], band, gap, fs[k] != 0, fe[k] != 0, mode);
+    prepare_job(P[k], nullptr, make_view(hs.start[ia], la[k], false, 0), la[k], make_view(hs.start[ib], lb[k], false, 0),
+                lb[k], begin_a[k], end_a[k], begin_b[k], end_b[k], band, gap, fs[k] != 0, fe[k] != 0, mode);
     memset(&dr[k], 0, sizeof(DevResult));
     if (P[k].cls == kClassWarp) {
       c = P[k].c; lg = P[k].lg;

@@ -1,0 +1,25 @@
+"""Host-side breakdown of the end-to-end path (run with GAMX_TIMING=1)."""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+import gen
+import gam_ngs_b200 as g
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+rng = np.random.default_rng(1)
+a, al, b, bl = gen.bulk_pairs(rng, n, 1000)
+host = torch.empty(len(a) + len(b), dtype=torch.uint8, pin_memory=True)
+hv = host.numpy(); hv[:len(a)] = a; hv[len(a):] = b
+lengths = np.concatenate([al, bl]).astype(np.uint64)
+jobs = g.make_jobs(n)
+jobs["a_id"] = np.arange(n); jobs["b_id"] = np.arange(n, 2 * n)
+jobs["end_a"] = al - 1; jobs["end_b"] = bl - 1; jobs["band"] = 64; jobs["mode"] = 1
+ctx = g.Context(devices=[0])
+for it in range(3):
+    t0 = time.perf_counter(); ctx.clear_contigs()
+    t1 = time.perf_counter(); ctx.add_contigs(host.data_ptr(), lengths)
+    t2 = time.perf_counter(); res, ops = ctx.align_batch(jobs)
+    t3 = time.perf_counter()
+    print(f"iter {it}: clear {1e3*(t1-t0):.1f} add_contigs {1e3*(t2-t1):.1f} align_batch {1e3*(t3-t2):.1f} total {1e3*(t3-t0):.1f} ms", flush=True)
