@@ -62,7 +62,7 @@ inline SeqView make_view(uint64_t cstart, uint64_t clen, bool rc, uint64_t off) 
 }
 
 // ---- classification -------------------------------------------------------------------------
-enum { kClassEarly = 0, kClassWarp = 1, kClassGeneric = 2 };
+enum { kClassEarly = 0, kClassWarp = 1, kClassGeneric = 2, kClassCta = 3 };
 
 struct Prepared {
   int cls;             // kClass*
@@ -107,6 +107,33 @@ inline void geometry_for_band(uint64_t band, bool dirs, int* c_out, int* lg_out)
   *c_out = best_c; *lg_out = best_lg;
 }
 
+// K2 geometry (one pair per CTA): the fewest threads whose stripes cover the band, C <= kMaxC.
+inline bool geometry_cta(uint64_t band, int* c_out, int* lg_out) {
+  const uint64_t y = 2 * band + 1;
+  const int lgs[3] = {64, 128, 256};
+  for (int n = 0; n < 3; n++) {
+    const int lg = lgs[n];
+    int c = (int)((y + lg - 1) / lg);
+    if (c < 2) c = 2;
+    while (c <= kMaxC && !stripe_supported(c)) c++;
+    if (c > kMaxC) continue;
+    *c_out = c; *lg_out = lg;
+    return true;
+  }
+  return false;
+}
+constexpr uint64_t kMaxBandCta = (256ull * kMaxC - 1) / 2;  // 2303
+
+// Latency mode: a band that fits one warp, spread over a 64-lane CTA instead (half the cells per
+// lane and step) for batches too small to fill the device with one warp per pair.
+inline void cta_geometry_for_latency(uint64_t band, int* c_out, int* lg_out) {
+  const uint64_t y = 2 * band + 1;
+  int c = (int)((y + 63) / 64);
+  if (c < 2) c = 2;
+  while (c <= kMaxC && !stripe_supported(c)) c++;
+  *c_out = c; *lg_out = 64;
+}
+
 // a_view / b_view: views of position 0 of a and b; la / lb: view lengths (a.size(), b.size()).
 // Fills P; for jobs classified kClassGeneric the raw arguments are written to *gj (when not null).
 inline void prepare_job(Prepared& P, GenJob* gj, const SeqView& a_view, uint64_t la, const SeqView& b_view,
@@ -133,8 +160,8 @@ inline void prepare_job(Prepared& P, GenJob* gj, const SeqView& a_view, uint64_t
   P.ops_cap = (mode == kModeFull) ? (uint32_t)((ops + 15) & ~uint64_t(15)) : 0u;
 
   const bool regular = la >= 1 && lb >= 1 && begin_b <= eb && eb < lb && begin_a < la + band &&
-                       gap >= -29 && gap <= -5 && y <= 32ull * kMaxC && !(fs && la <= (uint64_t)kForceMaxGap) &&
-                       la < (1ull << 30) && lb < (1ull << 30) && band < (1ull << 20);
+                       gap >= -29 && gap <= -5 && band <= kMaxBandCta && !(fs && la <= (uint64_t)kForceMaxGap) &&
+                       la < (1ull << 30) && lb < (1ull << 30);
   if (!regular) {
     P.cls = kClassGeneric;
     if (gj) {
@@ -150,8 +177,13 @@ inline void prepare_job(Prepared& P, GenJob* gj, const SeqView& a_view, uint64_t
     return;
   }
 
-  P.cls = kClassWarp;
-  geometry_for_band(band, mode != kModeScore, &P.c, &P.lg);
+  if (y <= 32ull * kMaxC) {
+    P.cls = kClassWarp;
+    geometry_for_band(band, mode != kModeScore, &P.c, &P.lg);
+  } else {
+    P.cls = kClassCta;  // band too wide for one warp: CTA-per-pair kernel
+    geometry_cta(band, &P.c, &P.lg);
+  }
   DevJob& d = P.dj;
   d.a = a_view;
   d.b = b_view;

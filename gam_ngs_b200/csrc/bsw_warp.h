@@ -1,5 +1,7 @@
 // K1 - warp-level banded overlap DP with inter-task parallelism: every group of LG lanes
 // (LG = 32, 16 or 8; 1, 2 or 4 pairs per warp) owns one pair.
+// K2 - the same skewed anti-diagonal wavefront with LG = 64, 128 or 256 lanes: one pair per CTA
+// (wide bands, or few long pairs); only the exchange policy W differs.
 //
 // Computes what BandedSmithWaterman::find_alignment computes
 // (/root/reference/lib/src/alignment/banded_smith_waterman.cc:69-323) for the jobs the host
@@ -70,7 +72,7 @@ struct GroupSmem {
 };
 template <int C, int LG>
 struct WarpSmem {
-  GroupSmem<C, LG> g[32 / LG];
+  GroupSmem<C, LG> g[LG >= 32 ? 1 : 32 / LG];
 };
 
 // number of direction words one job needs in the K1 layout (a few extra step blocks because the
@@ -97,7 +99,9 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
   static_assert(stripe_supported(C), "lane stripe width");
   constexpr int S = sub_block_of(C, DIRS), NB = C / S;
   static_assert(NB * S == C, "stripe = whole sub-blocks");
-  static_assert(LG == 8 || LG == 16 || LG == 32, "lanes per pair");
+  // LG <= 32: groups inside one warp (K1).  LG = 64..256: one pair per CTA (K2); the policy W then
+  // implements the neighbour exchanges through shared memory and a block barrier.
+  static_assert(LG == 8 || LG == 16 || LG == 32 || LG == 64 || LG == 128 || LG == 256, "lanes per pair");
   constexpr int SH = DIRS ? 2 : 0;
   const int lane = w.lane();
   const int grp = lane / LG, gl = lane % LG;

@@ -73,6 +73,53 @@ k1_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counter
   }
 }
 
+// K2: one pair per CTA of LG = 64/128/256 threads.  Same kernel body as K1; a lane's neighbours may
+// sit in another warp, so the two per-step exchanges go through shared memory and a block barrier
+// (double-buffered slots: one barrier per exchange).
+template <int LG>
+struct CtaPolicy {
+  int* xch;  // [2][LG]
+  int p;
+  __device__ __forceinline__ int lane() const { return (int)threadIdx.x; }
+  __device__ __forceinline__ int exchange(int v, int src) {
+    xch[p * LG + (int)threadIdx.x] = v;
+    __syncthreads();
+    const int r = xch[p * LG + src];
+    p ^= 1;
+    return r;
+  }
+  __device__ __forceinline__ int shfl_up(int v, int d, int width) {
+    const int t = (int)threadIdx.x;
+    return exchange(v, (t % width) >= d ? t - d : t);
+  }
+  __device__ __forceinline__ int shfl_down(int v, int d, int width) {
+    const int t = (int)threadIdx.x;
+    return exchange(v, (t % width) + d < width ? t + d : t);
+  }
+  __device__ __forceinline__ int shfl_xor(int v, int m, int) { return exchange(v, (int)threadIdx.x ^ m); }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+
+template <int C, int LG, bool DIRS>
+__global__ void __launch_bounds__(LG)
+k2_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counter, SeqStore store,
+          uint32_t* __restrict__ dirs, uint64_t group_stride, uint32_t* __restrict__ ops,
+          DevResult* __restrict__ results) {
+  __shared__ WarpSmem<C, LG> sm;
+  __shared__ int xch[2 * LG];
+  __shared__ int next_job;
+  CtaPolicy<LG> w{xch, 0};
+  uint32_t* my_dirs = DIRS ? dirs + (uint64_t)blockIdx.x * group_stride : nullptr;
+  for (;;) {
+    if (threadIdx.x == 0) next_job = atomicAdd(counter, 1);
+    __syncthreads();
+    const int j = next_job;
+    __syncthreads();
+    if (j >= n_jobs) break;
+    warp_align<C, LG, DIRS>(w, jobs + j, store, sm, my_dirs, group_stride, ops, results + j);
+  }
+}
+
 __global__ void __launch_bounds__(64)
 generic_kernel(const GenJob* __restrict__ jobs, int n_jobs, SeqStore store, int64_t* __restrict__ rows,
                uint32_t* __restrict__ dirs, uint32_t* __restrict__ ops, DevResult* __restrict__ results) {
@@ -488,6 +535,44 @@ void lpt_assign(const std::vector<uint32_t>& order, int n_shards, CostOf cost_of
   }
 }
 
+// ---- K2 dispatch: LG = 64 takes every stripe width, LG = 128/256 only the wide ones -----------
+template <int C, int LG, bool DIRS>
+int launch_k2_t(gamx_ctx* ctx, Device& d, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
+                uint64_t stride, uint32_t* ops, DevResult* results) {
+  SeqStore st{(const uint32_t*)d.packed.p, (const uint32_t*)d.nmask.p};
+  k2_kernel<C, LG, DIRS><<<g.grid, LG, 0, d.stream>>>(jobs, (int)g.job_idx.size(), counter, st, dirs, stride, ops, results);
+  CU(cudaGetLastError());
+  return GAMX_OK;
+}
+template <int C, int LG, bool DIRS>
+int occupancy_k2_t(int* blocks_per_sm) {
+  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k2_kernel<C, LG, DIRS>, LG, 0);
+}
+#define GAMX_FOR_EACH_WIDE_C(M, LG) M(10, LG) M(12, LG) M(14, LG) M(16, LG) M(18, LG)
+
+int k2_blocks_per_sm(int c, int lg, bool dirs) {
+  int b = 0;
+  cudaError_t e = cudaErrorInvalidValue;
+#define M(N, L) if (c == N && lg == L) e = (cudaError_t)(dirs ? occupancy_k2_t<N, L, true>(&b) : occupancy_k2_t<N, L, false>(&b));
+  GAMX_FOR_EACH_C(M, 64)
+  GAMX_FOR_EACH_WIDE_C(M, 128)
+  GAMX_FOR_EACH_WIDE_C(M, 256)
+#undef M
+  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+  return b;
+}
+int launch_k2(gamx_ctx* ctx, Device& d, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
+              uint64_t stride, uint32_t* ops, DevResult* results) {
+#define M(N, L) if (g.c == N && g.lg == L) return g.dirs ? launch_k2_t<N, L, true>(ctx, d, g, jobs, counter, dirs, stride, ops, results) \
+                                                          : launch_k2_t<N, L, false>(ctx, d, g, jobs, counter, dirs, stride, ops, results);
+  GAMX_FOR_EACH_C(M, 64)
+  GAMX_FOR_EACH_WIDE_C(M, 128)
+  GAMX_FOR_EACH_WIDE_C(M, 256)
+#undef M
+  ctx->err = "internal: no K2 kernel for this geometry";
+  return GAMX_ERR_INVALID;
+}
+
 bool resolve_views(const gamx_ctx* ctx, const gamx_job& j, SeqView* va, uint64_t* la, SeqView* vb, uint64_t* lb) {
   const StoreIndex& hs = ctx->store;
   if (j.a_id >= hs.start.size() || j.b_id >= hs.start.size()) return false;
@@ -715,12 +800,32 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
     };
     for (uint32_t i : per_dev[d]) {
       const Prepared& P = preps[i];
-      if (P.cls == kClassWarp) {
+      if (P.cls == kClassWarp || P.cls == kClassCta) {
         Group& g = groups[find_group(P.c, P.lg, pl->modes[i] != GAMX_MODE_SCORE)];
         g.job_idx.push_back(i);
         g.max_dir_words = std::max(g.max_dir_words, P.dir_words);
       } else {
         groups[find_group(0, 32, true)].job_idx.push_back(i);
+      }
+    }
+    // Latency mode: a launch of few long pairs cannot fill the device with one warp per pair, so
+    // those pairs go to the CTA-per-pair kernel (64 lanes per pair) instead.
+    for (Group& g : groups) {
+      if (g.c == 0 || g.lg != 32 || g.job_idx.size() >= (size_t)2 * ctx->devs[d].sm_count) continue;
+      uint64_t min_x = ~0ull;
+      for (uint32_t i : g.job_idx) min_x = std::min(min_x, preps[i].x_size);
+      if (min_x < 2048) continue;
+      int c2 = 0, lg2 = 0;
+      cta_geometry_for_latency((uint64_t)preps[g.job_idx[0]].dj.band, &c2, &lg2);
+      bool same_band = true;
+      for (uint32_t i : g.job_idx) same_band = same_band && preps[i].dj.band == preps[g.job_idx[0]].dj.band;
+      if (!same_band || c2 < 2) continue;
+      g.c = c2; g.lg = lg2; g.max_dir_words = 0;
+      for (uint32_t i : g.job_idx) {
+        Prepared& P = preps[i];
+        P.cls = kClassCta; P.c = c2; P.lg = lg2;
+        if (g.dirs) P.dir_words = k1_dir_words((int)P.x_size, P.dj.band, c2, lg2);
+        g.max_dir_words = std::max(g.max_dir_words, P.dir_words);
       }
     }
     uint32_t res_off = 0, dj_off = 0, gj_off = 0;
@@ -781,10 +886,11 @@ static int plan_upload(gamx_plan* pl) {
     const uint64_t budget_words = (uint64_t)((free_b + d.dirs.cap) * 0.8) / 4;
     for (Group& g : dp.groups) {
       if (!g.c) { g.grid = (int)((g.job_idx.size() + 63) / 64); continue; }
-      int bps = k1_blocks_per_sm(g.c, g.lg, g.dirs);
-      if (bps <= 0) { ctx->err = "k1 kernel does not fit on the device"; return GAMX_ERR_CUDA; }
+      const bool cta = g.lg > 32;
+      int bps = cta ? k2_blocks_per_sm(g.c, g.lg, g.dirs) : k1_blocks_per_sm(g.c, g.lg, g.dirs);
+      if (bps <= 0) { ctx->err = "alignment kernel does not fit on the device"; return GAMX_ERR_CUDA; }
       uint64_t grid = (uint64_t)d.sm_count * bps;
-      const uint64_t pairs_per_block = (uint64_t)kWarpsPerBlock * (32 / g.lg);
+      const uint64_t pairs_per_block = cta ? 1 : (uint64_t)kWarpsPerBlock * (32 / g.lg);
       const uint64_t need = (g.job_idx.size() + pairs_per_block - 1) / pairs_per_block;
       if (need < grid) grid = need;
       if (g.dirs && g.max_dir_words) {
@@ -840,9 +946,12 @@ static int plan_run_locked(gamx_plan* pl) {
       const Group& g = dp.groups[gi];
       DevResult* res = (DevResult*)d.results.p + g.res_off;
       if (g.c) {
-        if (int rc = launch_k1(ctx, d, g, (const DevJob*)d.jobs.p + g.job_off, (int*)d.counters.p + gi,
-                               (uint32_t*)d.dirs.p, g.max_dir_words, (uint32_t*)d.ops.p, res))
-          return rc;
+        const DevJob* dj = (const DevJob*)d.jobs.p + g.job_off;
+        const int rc = g.lg > 32 ? launch_k2(ctx, d, g, dj, (int*)d.counters.p + gi, (uint32_t*)d.dirs.p,
+                                             g.max_dir_words, (uint32_t*)d.ops.p, res)
+                                 : launch_k1(ctx, d, g, dj, (int*)d.counters.p + gi, (uint32_t*)d.dirs.p,
+                                             g.max_dir_words, (uint32_t*)d.ops.p, res);
+        if (rc) return rc;
       } else {
         SeqStore st{(const uint32_t*)d.packed.p, (const uint32_t*)d.nmask.p};
         generic_kernel<<<g.grid, 64, 0, d.stream>>>((const GenJob*)d.gjobs.p + g.job_off, (int)g.job_idx.size(), st,

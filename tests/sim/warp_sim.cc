@@ -37,25 +37,27 @@ struct SimWarp {
   void sync() { exchange(0, lane_); }
 };
 
+constexpr int kMaxLanes = 256;  // K2 runs up to 256 lanes (one CTA) per pair
 struct Sched {
   ucontext_t main_ctx;
-  ucontext_t ctx[32];
-  std::vector<char> stacks[32];
-  bool done[32];
-  int slot[32];
+  ucontext_t ctx[kMaxLanes];
+  std::vector<char> stacks[kMaxLanes];
+  bool done[kMaxLanes];
+  int slot[kMaxLanes];
+  int n = 32;  // lanes in this run
   int arrived = 0;
   unsigned gen = 0;
   int cur = 0;
   bool descending = false;
   void (*body)(SimWarp&, void*) = nullptr;
   void* arg = nullptr;
-  SimWarp warps[32];
+  SimWarp warps[kMaxLanes];
 
   void yield(int lane) { swapcontext(&ctx[lane], &main_ctx); }
   // two-phase rendezvous: everybody publishes, then everybody reads
   void barrier(int lane) {
     const unsigned g = gen;
-    if (++arrived == 32) { arrived = 0; gen++; }
+    if (++arrived == n) { arrived = 0; gen++; }
     while (gen == g) yield(lane);
   }
   static void tramp(int lane_lo, int sp_lo, int sp_hi) {
@@ -64,9 +66,9 @@ struct Sched {
     s->done[lane_lo] = true;
     swapcontext(&s->ctx[lane_lo], &s->main_ctx);
   }
-  void run(void (*b)(SimWarp&, void*), void* a, bool desc) {
-    body = b; arg = a; descending = desc; arrived = 0; gen = 0;
-    for (int l = 0; l < 32; l++) {
+  void run(void (*b)(SimWarp&, void*), void* a, bool desc, int lanes = 32) {
+    body = b; arg = a; descending = desc; arrived = 0; gen = 0; n = lanes;
+    for (int l = 0; l < n; l++) {
       warps[l].s = this; warps[l].lane_ = l; done[l] = false;
       stacks[l].assign(1 << 18, 0);
       getcontext(&ctx[l]);
@@ -78,8 +80,8 @@ struct Sched {
     }
     for (;;) {
       bool any = false;
-      for (int n = 0; n < 32; n++) {
-        const int l = descending ? 31 - n : n;
+      for (int q = 0; q < n; q++) {
+        const int l = descending ? n - 1 - q : q;
         if (done[l]) continue;
         any = true;
         swapcontext(&main_ctx, &ctx[l]);
@@ -113,7 +115,7 @@ template <int C, int LG>
 void body_c(SimWarp& w, void* p) {
   WarpArgs* a = (WarpArgs*)p;
   WarpSmem<C, LG>& sm = *(WarpSmem<C, LG>*)a->smem;
-  const int grp = w.lane() / LG;
+  const int grp = LG >= 32 ? 0 : w.lane() / LG;
   if (a->dirs_on) warp_align<C, LG, true>(w, a->job[grp], a->store, sm, a->dirs, a->group_stride, a->ops, a->out[grp]);
   else warp_align<C, LG, false>(w, a->job[grp], a->store, sm, a->dirs, a->group_stride, a->ops, a->out[grp]);
 }
@@ -123,7 +125,7 @@ void dispatch(WarpArgs& a, bool desc) {
   std::vector<uint64_t> smem((sizeof(WarpSmem<C, LG>) + 7) / 8);
   a.smem = smem.data();
   Sched* s = new Sched();
-  s->run(body_c<C, LG>, &a, desc);
+  s->run(body_c<C, LG>, &a, desc, LG > 32 ? LG : 32);
   delete s;
 }
 
@@ -139,7 +141,10 @@ void run_warp_lg(WarpArgs& a, bool desc) {
 void run_warp(WarpArgs& a, bool desc) {
   if (a.lg == 32) run_warp_lg<32>(a, desc);
   else if (a.lg == 16) run_warp_lg<16>(a, desc);
-  else run_warp_lg<8>(a, desc);
+  else if (a.lg == 8) run_warp_lg<8>(a, desc);
+  else if (a.lg == 64) run_warp_lg<64>(a, desc);
+  else if (a.lg == 128) run_warp_lg<128>(a, desc);
+  else run_warp_lg<256>(a, desc);
 }
 
 }  // namespace
@@ -165,7 +170,7 @@ int sim_align(const uint8_t* a, uint64_t a_clen, int a_rc, uint64_t a_off, uint6
   GenJob GJ;
   memset(&GJ, 0, sizeof(GJ));
   prepare_job(P, &GJ, va, a_len, vb, b_len, begin_a, end_a, begin_b, end_b, band, gap, fs != 0, fe != 0, mode);
-  if (force_class == kClassGeneric && P.cls == kClassWarp) {
+  if (force_class == kClassGeneric && (P.cls == kClassWarp || P.cls == kClassCta)) {
     // re-prepare as generic
     P.cls = kClassGeneric;
     GenJob& g = GJ;
@@ -177,12 +182,18 @@ int sim_align(const uint8_t* a, uint64_t a_clen, int a_rc, uint64_t a_off, uint6
     P.dir_words = (P.x_size * (2 * band + 1) + 15) / 16;
     P.gen_rows = 2 * (2 * band + 1);
   }
+  if (force_class == kClassCta && P.cls == kClassWarp) {
+    // a warp-class job on the CTA kernel (what the dispatcher does for small batches of long pairs)
+    P.cls = kClassCta;
+    cta_geometry_for_latency(band, &P.c, &P.lg);
+    P.dir_words = (mode == kModeScore) ? 0 : k1_dir_words((int)P.x_size, (int)band, P.c, P.lg);
+  }
   SeqStore st{hs.packed.data(), hs.nmask.data()};
   DevResult dr;
   memset(&dr, 0, sizeof(dr));
   std::vector<uint32_t> ops(P.ops_cap / 16 + 1, 0u);
-  if (P.cls == kClassWarp) {
-    const int G = 32 / P.lg;
+  if (P.cls == kClassWarp || P.cls == kClassCta) {
+    const int G = P.lg >= 32 ? 1 : 32 / P.lg;
     std::vector<uint32_t> dirs((P.dir_words + 1) * G, 0xdeadbeefu);
     P.dj.ops_word = 0;
     WarpArgs wa;

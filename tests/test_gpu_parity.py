@@ -242,3 +242,46 @@ def test_cpp_dropin_runs_on_gpu(tmp_path):
     exe = _build_dropin(tmp_path)
     p = subprocess.run([exe], capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr
+
+
+@pytest.mark.parametrize("band", [288, 400, 512, 1024, 1500])
+def test_cta_per_pair_kernel_wide_bands(ctx, band):
+    """K2 (one pair per CTA) handles bands wider than a warp's stripes (BASELINE config 5 sweeps
+    the band up to 1024)."""
+    rng = np.random.default_rng(5000 + band)
+    cases = []
+    for length in (150, 700, 2500):
+        for _ in range(4):
+            a, b = gen.make_pair(rng, length, div=float(rng.choice([0.0, 0.02, 0.1])), p_n=0.003)
+            b = b[int(rng.integers(0, min(band // 2, length // 4) + 1)):]
+            la, lb = len(a), len(b)
+            shape = int(rng.integers(0, 3))
+            if shape == 0:
+                w = dict(begin_a=0, end_a=la - 1, begin_b=0, end_b=lb - 1, force_start=False, force_end=False)
+            elif shape == 1:
+                w = dict(begin_a=int(rng.integers(0, la // 2)), end_a=la - 1, begin_b=0, end_b=lb - 1,
+                         force_start=False, force_end=True)
+            else:
+                w = dict(begin_a=3, end_a=la + 40, begin_b=int(rng.integers(0, lb // 2)), end_b=lb + 5,
+                         force_start=True, force_end=False)
+            cases.append(dict(a=a, b=b, band=band, gap=-8, **w))
+    exps = [oracle_expect(c) for c in cases]
+    for mode in (capi.MODE_FULL, capi.MODE_SCORE):
+        got = run_batch(ctx, cases, mode)
+        for k in range(len(cases)):
+            assert got[k] == project(exps[k], mode), (k, mode)
+
+
+def test_cta_per_pair_latency_mode_for_few_long_pairs(ctx):
+    """A handful of long overlaps (too few to fill 148 SMs with one warp each) is routed to the
+    CTA-per-pair kernel; results must not depend on which kernel ran."""
+    rng = np.random.default_rng(77)
+    cases = []
+    for length, band in [(6000, 150), (9000, 256), (4000, 64), (12000, 150)]:
+        a, b = gen.make_pair(rng, length, div=0.02, offset=int(rng.integers(0, band // 2)))
+        cases.append(dict(a=a, b=b, begin_a=0, end_a=len(a) - 1, begin_b=0, end_b=len(b) - 1, band=band, gap=-8,
+                          force_start=False, force_end=False))
+    exps = [oracle_expect(c) for c in cases]
+    got = run_batch(ctx, cases, capi.MODE_FULL)
+    for k in range(len(cases)):
+        assert got[k] == exps[k], k

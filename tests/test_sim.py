@@ -122,3 +122,26 @@ def test_sim_lane_groups_share_a_step_loop(band):
                 got = simlib.result_to_expect(r, ops if mode == 2 else None, mode)
                 assert got == simlib.project(oracle_expect(job), mode), (band, rep, mode)
             assert ran >= 1
+
+
+@pytest.mark.parametrize("band,force", [(300, 0), (512, 0), (1024, 0), (2303, 0), (64, 3), (150, 3), (256, 3)])
+def test_sim_cta_per_pair_kernel(band, force):
+    """K2: one pair per CTA (64/128/256 lanes, neighbour exchange through shared memory).  Bands
+    wider than a warp can hold, and warp-sized bands in latency mode (force=3)."""
+    rng = np.random.default_rng(4000 + band)
+    for length in (90, 400):
+        a, b = gen.make_pair(rng, length, div=0.05, p_n=0.004)
+        b = b[int(rng.integers(0, min(band // 2, length // 4) + 1)):]
+        la, lb = len(a), len(b)
+        for shape in range(3):
+            if shape == 0:
+                w = dict(begin_a=0, end_a=la - 1, begin_b=0, end_b=lb - 1, force_start=False, force_end=False)
+            elif shape == 1:
+                w = dict(begin_a=int(rng.integers(0, la // 2)), end_a=la - 1, begin_b=0, end_b=lb - 1,
+                         force_start=False, force_end=True)
+            else:
+                w = dict(begin_a=3, end_a=la + 40, begin_b=int(rng.integers(0, lb // 2)), end_b=lb + 5,
+                         force_start=True, force_end=False)
+            job = dict(a=a, b=b, band=band, gap=-8, **w)
+            cls = _check(job, oracle_expect(job), modes=(2, 0), lane_order=shape, force_class=force)
+            assert cls == 3
