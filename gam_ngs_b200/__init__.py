@@ -2,7 +2,7 @@
 hot path: BandedSmithWaterman::find_alignment
 (/root/reference/lib/src/alignment/banded_smith_waterman.cc:69-323) behind the reference's
 own call interface.  See DESIGN.md and INTEGRATION.md."""
-from .capi import (Context, GamxError, Plan, make_jobs, load_library, JOB_DTYPE, RESULT_DTYPE,  # noqa: F401
+from .capi import (Context, GamxError, Plan, make_jobs, make_hits_jobs, load_library, JOB_DTYPE, RESULT_DTYPE,  # noqa: F401
                    MODE_SCORE, MODE_ENDPOINTS, MODE_FULL, JOB_OK, JOB_EMPTY, JOB_OUT_OF_RANGE,
                    JOB_UNDEFINED, DEFAULT_BAND, DEFAULT_GAP)
 from .aligner import BandedSmithWaterman, Contig, MyAlignment  # noqa: F401

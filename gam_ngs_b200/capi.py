@@ -55,6 +55,13 @@ JOB_DTYPE = np.dtype([
     ("begin_a", "<u8"), ("end_a", "<u8"), ("begin_b", "<u8"), ("end_b", "<u8"),
     ("band", "<u4"), ("gap", "<i4")], align=True)
 
+HITS_JOB_DTYPE = np.dtype([
+    ("a_id", "<u4"), ("b_id", "<u4"), ("a_rc", "u1"), ("b_rc", "u1"), ("reserved_", "u1", (6,)),
+    ("a_off", "<u8"), ("a_len", "<u8"), ("b_off", "<u8"), ("b_len", "<u8"),
+    ("a_start", "<u8"), ("a_end", "<u8"), ("b_start", "<u8"), ("b_end", "<u8")], align=True)
+HITS_RESULT_DTYPE = np.dtype([("n_hits", "<u4"), ("max_count", "<u4"), ("first_hit", "<u8"), ("last_hit", "<u8")],
+                             align=True)
+
 RESULT_DTYPE = np.dtype([
     ("status", "<i4"), ("has_match", "<i4"), ("score", "<i8"),
     ("begin_a", "<u8"), ("begin_b", "<u8"), ("a_size", "<u8"), ("b_size", "<u8"),
@@ -73,7 +80,7 @@ EXPORTS = [
     "gamx_ops_capacity", "gamx_align_batch", "gamx_unpack_ops", "gamx_cigar_rle",
     "gamx_plan_create", "gamx_plan_run", "gamx_plan_sync", "gamx_plan_fetch", "gamx_plan_last_ms",
     "gamx_plan_cells", "gamx_plan_kernel_launches", "gamx_plan_destroy", "gamx_measure_int_peak",
-    "gamx_shard_by_cost",
+    "gamx_shard_by_cost", "gamx_find_hits_batch",
 ]
 
 _lib = None
@@ -136,10 +143,19 @@ def load_library(build_if_missing: bool = True):
     L.gamx_plan_kernel_launches.restype = u64
     L.gamx_plan_destroy.argtypes = [vp]
     L.gamx_plan_destroy.restype = None
+    L.gamx_find_hits_batch.argtypes = [vp, vp, u64, vp]
+    L.gamx_find_hits_batch.restype = C.c_int
     L.gamx_measure_int_peak.argtypes = [vp, C.c_int, C.c_int]
     L.gamx_measure_int_peak.restype = C.c_double
     _lib = L
     return L
+
+
+def make_hits_jobs(n: int) -> np.ndarray:
+    jobs = np.zeros(n, dtype=HITS_JOB_DTYPE)
+    jobs["a_len"] = U64_MAX
+    jobs["b_len"] = U64_MAX
+    return jobs
 
 
 def make_jobs(n: int) -> np.ndarray:
@@ -264,6 +280,13 @@ class Context:
         self._check(self.lib.gamx_align_batch(self._h, jobs.ctypes.data, n, results.ctypes.data,
                                               ops.ctypes.data, cap))
         return results, ops
+
+    def find_hits_batch(self, jobs: np.ndarray) -> np.ndarray:
+        """ABlast::findHits for a batch of (a window, b window) jobs (HITS_JOB_DTYPE)."""
+        jobs = np.ascontiguousarray(jobs, dtype=HITS_JOB_DTYPE)
+        res = np.zeros(len(jobs), dtype=HITS_RESULT_DTYPE)
+        self._check(self.lib.gamx_find_hits_batch(self._h, jobs.ctypes.data, len(jobs), res.ctypes.data))
+        return res
 
     def plan(self, jobs: np.ndarray) -> Plan:
         return Plan(self, jobs)

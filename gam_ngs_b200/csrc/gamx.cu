@@ -13,6 +13,7 @@
 // context's devices), launch, gather.  No CPU compute path exists here: if CUDA is not usable
 // every entry point fails.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -163,6 +164,102 @@ pack_kernel(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ roff, 
   nmask[G] = m;
 }
 
+// ---- f3: ABlast::findHits on the device (ablast.cc:41-76, ablast.hpp:52-107) ----------------------
+// k-mer (w = 20) diagonal voting.  A job's a-window k-mers are keyed (job << 42) | code and sorted
+// (cub radix sort); every b-window k-mer then looks its key up and votes for the diagonals
+// idx_a - idx_b >= 0 with atomics; a block per job reduces the vote array to (max, count, first, last).
+constexpr int kWord = 20;  // ABLAST_DEFAULT_WORD_SIZE, ablast.hpp:33
+
+struct HitsJob {
+  SeqView a, b;          // view position 0
+  uint64_t a_start, b_start;
+  uint64_t na, nb, nf;   // k-mers of the a / b window, vote counters (a_end - a_start + 1)
+  uint64_t ka_off, kb_off, f_off;  // offsets into the flattened arrays
+};
+
+// code = sum base * 4^(19-k), digits 0..4: N (4) aliases with a carry exactly like ablast.hpp:53-59
+__device__ __forceinline__ uint64_t kmer_code(const SeqStore& st, const SeqView& v, uint64_t p) {
+  uint64_t c = 0;
+#pragma unroll 4
+  for (int k = 0; k < kWord; k++) c = 4 * c + load_code(st, v, (int64_t)(p + k));
+  return c;
+}
+__device__ __forceinline__ int find_job(const uint64_t* off, int n, uint64_t t) {  // last j with off[j] <= t
+  int lo = 0, hi = n;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= t) lo = mid; else hi = mid; }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256)
+hits_codes_kernel(const HitsJob* __restrict__ jobs, int n_jobs, const uint64_t* __restrict__ ka_offs,
+                  const uint64_t* __restrict__ kb_offs, uint64_t total_a, uint64_t total_b, SeqStore st,
+                  uint64_t* __restrict__ a_keys, uint32_t* __restrict__ a_vals, uint64_t* __restrict__ b_keys) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < total_a) {
+    const int j = find_job(ka_offs, n_jobs, t);
+    const HitsJob J = jobs[j];
+    const uint64_t idx = t - J.ka_off;
+    a_keys[t] = ((uint64_t)j << 42) | kmer_code(st, J.a, J.a_start + idx);
+    a_vals[t] = (uint32_t)idx;
+  } else if (t - total_a < total_b) {
+    const uint64_t u = t - total_a;
+    const int j = find_job(kb_offs, n_jobs, u);
+    const HitsJob J = jobs[j];
+    b_keys[u] = ((uint64_t)j << 42) | kmer_code(st, J.b, J.b_start + (u - J.kb_off));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+hits_vote_kernel(const HitsJob* __restrict__ jobs, int n_jobs, const uint64_t* __restrict__ kb_offs, uint64_t total_a,
+                 uint64_t total_b, const uint64_t* __restrict__ a_keys, const uint32_t* __restrict__ a_vals,
+                 const uint64_t* __restrict__ b_keys, uint32_t* __restrict__ f) {
+  const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= total_b) return;
+  const uint64_t key = b_keys[u];
+  const int j = (int)(key >> 42);
+  const uint64_t idx_b = u - jobs[j].kb_off;
+  const uint64_t f_off = jobs[j].f_off;
+  uint64_t lo = 0, hi = total_a;  // lower bound of key in the sorted a-side keys
+  while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (a_keys[mid] < key) lo = mid + 1; else hi = mid; }
+  for (uint64_t k = lo; k < total_a && a_keys[k] == key; k++) {
+    const uint64_t idx_a = a_vals[k];
+    if (idx_a >= idx_b) atomicAdd(&f[f_off + (idx_a - idx_b)], 1u);  // mark_found, ablast.hpp:71-76
+  }
+}
+
+struct HitsOut { uint32_t n_hits, max_count; uint64_t first_d, last_d; };
+
+__global__ void __launch_bounds__(256)
+hits_reduce_kernel(const HitsJob* __restrict__ jobs, const uint32_t* __restrict__ f, HitsOut* __restrict__ out) {
+  __shared__ uint32_t s_max[256];
+  __shared__ uint32_t s_cnt[256];
+  __shared__ uint64_t s_first[256], s_last[256];
+  const HitsJob J = jobs[blockIdx.x];
+  const uint32_t* fj = f + J.f_off;
+  uint32_t m = 0;
+  for (uint64_t i = threadIdx.x; i < J.nf; i += blockDim.x) m = max(m, fj[i]);
+  s_max[threadIdx.x] = m;
+  __syncthreads();
+  for (int d = 128; d >= 1; d >>= 1) { if ((int)threadIdx.x < d) s_max[threadIdx.x] = max(s_max[threadIdx.x], s_max[threadIdx.x + d]); __syncthreads(); }
+  m = s_max[0];
+  uint32_t cnt = 0;
+  uint64_t first = ~0ull, last = 0;
+  if (m > 0)
+    for (uint64_t i = threadIdx.x; i < J.nf; i += blockDim.x)
+      if (fj[i] == m) { cnt++; first = min(first, i); last = max(last, i); }
+  s_cnt[threadIdx.x] = cnt; s_first[threadIdx.x] = first; s_last[threadIdx.x] = last;
+  __syncthreads();
+  for (int d = 128; d >= 1; d >>= 1) {
+    if ((int)threadIdx.x < d) {
+      s_cnt[threadIdx.x] += s_cnt[threadIdx.x + d];
+      s_first[threadIdx.x] = min(s_first[threadIdx.x], s_first[threadIdx.x + d]);
+      s_last[threadIdx.x] = max(s_last[threadIdx.x], s_last[threadIdx.x + d]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { HitsOut o; o.n_hits = s_cnt[0]; o.max_count = m; o.first_d = s_first[0]; o.last_d = s_last[0]; out[blockIdx.x] = o; }
+}
+
 // ---- issue-rate microbenchmarks -------------------------------------------------------------
 template <int WHICH>
 __global__ void __launch_bounds__(256) intpeak_kernel(int* out, int iters, int seed) {
@@ -225,6 +322,7 @@ struct Device {
   uint64_t store_groups = 0;      // 32-base groups already packed on this device
   DevBuf raw, meta;               // staging for K0: raw base codes + per-contig offsets
   DevBuf jobs, gjobs, results, dirs, ops, grows, gdirs, counters, peak;
+  DevBuf hjobs, hoffs, hkeys_a, hkeys_a2, hvals_a, hvals_a2, hkeys_b, hvotes, hout, htemp;  // findHits scratch
   PinBuf h_jobs, h_gjobs, h_results, h_ops, h_stage, h_stage2, h_meta;
   cudaEvent_t ev_stage[2] = {nullptr, nullptr};
 };
@@ -633,7 +731,8 @@ void gamx_destroy(gamx_ctx* ctx) {
   for (Device& d : ctx->devs) {
     cudaSetDevice(d.id);
     cudaStreamSynchronize(d.stream);
-    DevBuf* dbs[] = {&d.packed, &d.nmask, &d.raw, &d.meta, &d.jobs, &d.gjobs, &d.results, &d.dirs, &d.ops, &d.grows, &d.gdirs, &d.counters, &d.peak};
+    DevBuf* dbs[] = {&d.packed, &d.nmask, &d.raw, &d.meta, &d.hjobs, &d.hoffs, &d.hkeys_a, &d.hkeys_a2, &d.hvals_a,
+                     &d.hvals_a2, &d.hkeys_b, &d.hvotes, &d.hout, &d.htemp, &d.jobs, &d.gjobs, &d.results, &d.dirs, &d.ops, &d.grows, &d.gdirs, &d.counters, &d.peak};
     for (DevBuf* b : dbs) if (b->p) cudaFree(b->p);
     PinBuf* pbs[] = {&d.h_jobs, &d.h_gjobs, &d.h_results, &d.h_ops, &d.h_stage, &d.h_stage2, &d.h_meta};
     for (PinBuf* b : pbs) if (b->p) cudaFreeHost(b->p);
@@ -810,7 +909,9 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
     }
     // Latency mode: a launch of few long pairs cannot fill the device with one warp per pair, so
     // those pairs go to the CTA-per-pair kernel (64 lanes per pair) instead.
+    static const bool no_latency_mode = getenv("GAMX_NO_LATENCY_MODE") != nullptr;  // experiments only
     for (Group& g : groups) {
+      if (no_latency_mode) break;
       if (g.c == 0 || g.lg != 32 || g.job_idx.size() >= (size_t)2 * ctx->devs[d].sm_count) continue;
       uint64_t min_x = ~0ull;
       for (uint32_t i : g.job_idx) min_x = std::min(min_x, preps[i].x_size);
@@ -1100,6 +1201,102 @@ uint64_t gamx_cigar_rle(const uint8_t* ops_buf, uint64_t ops_offset, uint64_t n_
   }
   if (len) { if (n_runs < cap && runs) runs[n_runs] = (len << 2) | cur; n_runs++; }
   return n_runs;
+}
+
+int gamx_find_hits_batch(gamx_ctx* ctx, const gamx_hits_job* jobs, uint64_t n, gamx_hits_result* results) {
+  if (!ctx || (!jobs && n) || (!results && n)) return GAMX_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (n >= (1ull << 22)) { ctx->err = "at most 2^22 findHits jobs per batch"; return GAMX_ERR_INVALID; }
+  if (int rc = flush_pending(ctx)) return rc;
+  // guards of ablast.cc:47-53 on the host; surviving jobs go to the first device
+  std::vector<HitsJob> hj;
+  std::vector<uint32_t> idx;
+  std::vector<uint64_t> ka_offs, kb_offs;
+  uint64_t ta = 0, tb = 0, tf = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    gamx_hits_result& r = results[i];
+    r.n_hits = 0; r.max_count = 0; r.first_hit = 0; r.last_hit = 0;
+    gamx_job view = {};
+    view.a_id = jobs[i].a_id; view.b_id = jobs[i].b_id; view.a_rc = jobs[i].a_rc; view.b_rc = jobs[i].b_rc;
+    view.a_off = jobs[i].a_off; view.a_len = jobs[i].a_len; view.b_off = jobs[i].b_off; view.b_len = jobs[i].b_len;
+    SeqView va, vb;
+    uint64_t la, lb;
+    if (!resolve_views(ctx, view, &va, &la, &vb, &lb)) {
+      ctx->err = "findHits job " + std::to_string(i) + ": unknown contig id or view outside the contig";
+      return GAMX_ERR_INVALID;
+    }
+    uint64_t a_start = jobs[i].a_start, a_end = jobs[i].a_end, b_start = jobs[i].b_start, b_end = jobs[i].b_end;
+    if (la == 0 || lb == 0) continue;                                   // ablast.cc:47
+    if (a_end >= la) a_end = la - 1;                                    // :49-50
+    if (b_end >= lb) b_end = lb - 1;
+    if (a_start > a_end || b_start > b_end) continue;                   // :52
+    if (a_end + 1 < kWord + a_start || b_end + 1 < kWord + b_start) continue;  // :53
+    HitsJob J;
+    J.a = va; J.b = vb; J.a_start = a_start; J.b_start = b_start;
+    J.na = a_end - kWord + 1 - a_start + 1;
+    J.nb = b_end - kWord + 1 - b_start + 1;
+    J.nf = a_end - a_start + 1;
+    J.ka_off = ta; J.kb_off = tb; J.f_off = tf;
+    ka_offs.push_back(ta); kb_offs.push_back(tb);
+    ta += J.na; tb += J.nb; tf += J.nf;
+    hj.push_back(J);
+    idx.push_back((uint32_t)i);
+  }
+  const int m = (int)hj.size();
+  if (m == 0) return GAMX_OK;
+  ka_offs.push_back(ta); kb_offs.push_back(tb);
+  Device& d = ctx->devs[0];
+  CU(cudaSetDevice(d.id));
+  if (int rc = ensure_dev(ctx, d.hjobs, (size_t)m * sizeof(HitsJob))) return rc;
+  if (int rc = ensure_dev(ctx, d.hoffs, (size_t)(2 * (m + 1)) * 8)) return rc;
+  if (int rc = ensure_dev(ctx, d.hkeys_a, ta * 8 + 64)) return rc;
+  if (int rc = ensure_dev(ctx, d.hkeys_a2, ta * 8 + 64)) return rc;
+  if (int rc = ensure_dev(ctx, d.hvals_a, ta * 4 + 64)) return rc;
+  if (int rc = ensure_dev(ctx, d.hvals_a2, ta * 4 + 64)) return rc;
+  if (int rc = ensure_dev(ctx, d.hkeys_b, tb * 8 + 64)) return rc;
+  if (int rc = ensure_dev(ctx, d.hvotes, tf * 4 + 64)) return rc;
+  if (int rc = ensure_dev(ctx, d.hout, (size_t)m * sizeof(HitsOut))) return rc;
+  CU(cudaMemcpyAsync(d.hjobs.p, hj.data(), (size_t)m * sizeof(HitsJob), cudaMemcpyHostToDevice, d.stream));
+  uint64_t* d_ka = (uint64_t*)d.hoffs.p;
+  uint64_t* d_kb = d_ka + (m + 1);
+  CU(cudaMemcpyAsync(d_ka, ka_offs.data(), (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, d.stream));
+  CU(cudaMemcpyAsync(d_kb, kb_offs.data(), (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, d.stream));
+  CU(cudaMemsetAsync(d.hvotes.p, 0, tf * 4, d.stream));
+  SeqStore st{(const uint32_t*)d.packed.p, (const uint32_t*)d.nmask.p};
+  const uint64_t tot = ta + tb;
+  hits_codes_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, d.stream>>>(
+      (const HitsJob*)d.hjobs.p, m, d_ka, d_kb, ta, tb, st, (uint64_t*)d.hkeys_a.p, (uint32_t*)d.hvals_a.p,
+      (uint64_t*)d.hkeys_b.p);
+  CU(cudaGetLastError());
+  // sort the a-side (key, index) pairs by key
+  int end_bit = 42;
+  while (end_bit < 64 && ((uint64_t)m >> (end_bit - 42))) end_bit++;
+  size_t temp_bytes = 0;
+  CU(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const uint64_t*)d.hkeys_a.p, (uint64_t*)d.hkeys_a2.p,
+                                     (const uint32_t*)d.hvals_a.p, (uint32_t*)d.hvals_a2.p, (int)ta, 0, end_bit, d.stream));
+  if (int rc = ensure_dev(ctx, d.htemp, temp_bytes + 64)) return rc;
+  if (ta >= (1ull << 31)) { ctx->err = "findHits batch too large (2^31 k-mers)"; return GAMX_ERR_INVALID; }
+  CU(cub::DeviceRadixSort::SortPairs(d.htemp.p, temp_bytes, (const uint64_t*)d.hkeys_a.p, (uint64_t*)d.hkeys_a2.p,
+                                     (const uint32_t*)d.hvals_a.p, (uint32_t*)d.hvals_a2.p, (int)ta, 0, end_bit, d.stream));
+  hits_vote_kernel<<<(unsigned)((tb + 255) / 256), 256, 0, d.stream>>>(
+      (const HitsJob*)d.hjobs.p, m, d_kb, ta, tb, (const uint64_t*)d.hkeys_a2.p, (const uint32_t*)d.hvals_a2.p,
+      (const uint64_t*)d.hkeys_b.p, (uint32_t*)d.hvotes.p);
+  CU(cudaGetLastError());
+  hits_reduce_kernel<<<m, 256, 0, d.stream>>>((const HitsJob*)d.hjobs.p, (const uint32_t*)d.hvotes.p, (HitsOut*)d.hout.p);
+  CU(cudaGetLastError());
+  std::vector<HitsOut> ho(m);
+  CU(cudaMemcpyAsync(ho.data(), d.hout.p, (size_t)m * sizeof(HitsOut), cudaMemcpyDeviceToHost, d.stream));
+  CU(cudaStreamSynchronize(d.stream));
+  for (int k = 0; k < m; k++) {
+    gamx_hits_result& r = results[idx[k]];
+    r.n_hits = ho[k].n_hits;
+    r.max_count = ho[k].max_count;
+    if (ho[k].n_hits) {  // hits are a_start + d truncated to 32 bits (std::list<uint32_t>, ablast.cc:43,66,70)
+      r.first_hit = (uint32_t)(hj[k].a_start + ho[k].first_d);
+      r.last_hit = (uint32_t)(hj[k].a_start + ho[k].last_d);
+    }
+  }
+  return GAMX_OK;
 }
 
 int gamx_shard_by_cost(const uint64_t* cost, uint64_t n, int n_shards, int32_t* shard_out) {

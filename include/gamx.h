@@ -190,6 +190,30 @@ GAMX_API uint64_t gamx_plan_cells(const gamx_plan* plan);        /* sum of x_siz
 GAMX_API uint64_t gamx_plan_kernel_launches(const gamx_plan* plan); /* kernels launched per run        */
 GAMX_API void gamx_plan_destroy(gamx_plan* plan);
 
+/* ---- seed finder: ABlast::findHits (lib/src/alignment/ablast.cc:41-76) ----------------- */
+
+/* One findHits(a, a_start, a_end, b, b_start, b_end) call on views of stored contigs: k-mer
+ * (w = 20) diagonal voting, only diagonals idx_a >= idx_b (ablast.hpp:71-76), code aliasing of N
+ * as in ablast.hpp:53-59.  The reference returns every diagonal with the maximal count in
+ * ascending order and its callers use front() or back() (PctgBuilder.cc:1544,1560,1584,1602): the
+ * result carries both plus the list length. */
+typedef struct {
+  uint32_t a_id, b_id;
+  uint8_t a_rc, b_rc;
+  uint8_t reserved_[6];
+  uint64_t a_off, a_len, b_off, b_len; /* views, as in gamx_job */
+  uint64_t a_start, a_end, b_start, b_end;
+} gamx_hits_job;
+
+typedef struct {
+  uint32_t n_hits;     /* hits.size() */
+  uint32_t max_count;  /* votes of the best diagonal(s) */
+  uint64_t first_hit;  /* hits.front(): a_start + smallest best diagonal (32-bit truncated like the reference) */
+  uint64_t last_hit;   /* hits.back() */
+} gamx_hits_result;
+
+GAMX_API int gamx_find_hits_batch(gamx_ctx* ctx, const gamx_hits_job* jobs, uint64_t n, gamx_hits_result* results);
+
 /* ---- sharding ------------------------------------------------------------------------ */
 
 /* The cost-balanced split gamx_align_batch applies over a context's devices (longest-processing-

@@ -107,6 +107,9 @@ class Restatement:
         self.lib.bswo_align.restype = C.c_int
         self.lib.bswo_cells.argtypes = [u64] * 6
         self.lib.bswo_cells.restype = u64
+        self.lib.bswo_find_hits.argtypes = [u8p, u64, u64, u64, u8p, u64, u64, u64, C.POINTER(C.c_uint32), u64,
+                                            C.POINTER(u64)]
+        self.lib.bswo_find_hits.restype = u64
 
     def align(self, a, begin_a, end_a, b, begin_b, end_b, band=150, gap=GAP_DEFAULT,
               force_start=False, force_end=False, want_ops=True):
@@ -119,6 +122,16 @@ class Restatement:
                             int(force_start), int(force_end), C.byref(r),
                             ops.ctypes.data_as(C.POINTER(C.c_uint8)) if want_ops else None, cap)
         return r, (ops if want_ops else None)
+
+    def find_hits(self, a, a_start, a_end, b, b_start, b_end, cap=1 << 16):
+        """ABlast::findHits restated: returns (hits ascending, max_count)."""
+        a, pa = _u8(a)
+        b, pb = _u8(b)
+        hits = np.zeros(cap, dtype=np.uint32)
+        mc = C.c_uint64(0)
+        n = self.lib.bswo_find_hits(pa, len(a), a_start, a_end, pb, len(b), b_start, b_end,
+                                    hits.ctypes.data_as(C.POINTER(C.c_uint32)), cap, C.byref(mc))
+        return hits[: min(n, cap)].copy(), int(mc.value)
 
     def cells(self, la, begin_a, lb, begin_b, end_b, band):
         return self.lib.bswo_cells(la, begin_a, lb, begin_b, end_b, band)

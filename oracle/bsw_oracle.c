@@ -327,3 +327,62 @@ uint64_t bswo_cells(uint64_t la, uint64_t begin_a, uint64_t lb, uint64_t begin_b
   if (x > BSWO_MAX_ALIGNMENT) x = BSWO_MAX_ALIGNMENT;
   return x * (2 * band + 1);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * ABlast::findHits restated:
+ *   /root/reference/lib/src/alignment/ablast.cc:41-76, helpers lib/include/alignment/ablast.hpp:52-107.
+ * k-mer (w = 20) diagonal voting.  Codes are radix-4 numbers whose digits are the base codes 0..4
+ * (N = 4 aliases with a carry, ablast.hpp:53-59); only diagonals idx_a >= idx_b are counted
+ * (ablast.hpp:71-76).  Returns the number of hits (diagonals with the maximal non-zero count, in
+ * ascending order) and writes up to cap of them as a_start + d truncated to 32 bits (ablast.cc:58-73).
+ * Pinned against the compiled reference (gamref_find_hits) in tests/test_oracle.py.
+ * ---------------------------------------------------------------------------------------------- */
+#define BSWO_WORD 20 /* ABLAST_DEFAULT_WORD_SIZE, ablast.hpp:33 */
+
+typedef struct { uint64_t code; uint64_t pos; } bswo_kmer;
+static int bswo_kmer_cmp(const void* x, const void* y) {
+  const bswo_kmer* a = (const bswo_kmer*)x; const bswo_kmer* b = (const bswo_kmer*)y;
+  if (a->code != b->code) return a->code < b->code ? -1 : 1;
+  return a->pos < b->pos ? -1 : (a->pos > b->pos);
+}
+static uint64_t bswo_code(const uint8_t* s, uint64_t p) {
+  uint64_t c = 0;
+  for (uint64_t i = p; i < p + BSWO_WORD; i++) c = 4 * c + s[i]; /* (LAST_BASE-1)*code + base */
+  return c;
+}
+
+uint64_t bswo_find_hits(const uint8_t* a, uint64_t la, uint64_t a_start, uint64_t a_end,
+                        const uint8_t* b, uint64_t lb, uint64_t b_start, uint64_t b_end,
+                        uint32_t* hits, uint64_t cap, uint64_t* max_count_out) {
+  if (max_count_out) *max_count_out = 0;
+  if (la == 0 || lb == 0) return 0;                                   /* ablast.cc:47 */
+  if (a_end >= la) a_end = la - 1;                                    /* :49-50 */
+  if (b_end >= lb) b_end = lb - 1;
+  if (a_start > a_end || b_start > b_end) return 0;                   /* :52 */
+  if (a_end + 1 < BSWO_WORD + a_start || b_end + 1 < BSWO_WORD + b_start) return 0; /* :53 */
+  const uint64_t na = a_end - BSWO_WORD + 1 - a_start + 1, nb = b_end - BSWO_WORD + 1 - b_start + 1;
+  const uint64_t nf = a_end - a_start + 1;
+  bswo_kmer* ka = (bswo_kmer*)malloc((size_t)na * sizeof(bswo_kmer));
+  uint64_t* f = (uint64_t*)calloc((size_t)nf, sizeof(uint64_t));
+  if (!ka || !f) { free(ka); free(f); return 0; }
+  for (uint64_t i = 0; i < na; i++) { ka[i].code = bswo_code(a, a_start + i); ka[i].pos = a_start + i; }
+  qsort(ka, (size_t)na, sizeof(bswo_kmer), bswo_kmer_cmp);
+  for (uint64_t j = 0; j < nb; j++) {
+    const uint64_t code = bswo_code(b, b_start + j);
+    uint64_t lo = 0, hi = na; /* lower bound */
+    while (lo < hi) { uint64_t mid = (lo + hi) / 2; if (ka[mid].code < code) lo = mid + 1; else hi = mid; }
+    for (uint64_t k = lo; k < na && ka[k].code == code; k++) {
+      const uint64_t idx_a = ka[k].pos - a_start, idx_b = j;
+      if (idx_a >= idx_b) f[idx_a - idx_b] += 1;                      /* mark_found, ablast.hpp:71-76 */
+    }
+  }
+  uint64_t max_score = 0, n = 0;
+  for (uint64_t i = 0; i < nf; i++) {                                 /* ablast.cc:58-73 */
+    if (f[i] == 0) continue;
+    if (f[i] > max_score) { max_score = f[i]; n = 0; if (n < cap) hits[n] = (uint32_t)(a_start + i); n = 1; }
+    else if (f[i] == max_score) { if (n < cap) hits[n] = (uint32_t)(a_start + i); n++; }
+  }
+  if (max_count_out) *max_count_out = max_score;
+  free(ka); free(f);
+  return n;
+}

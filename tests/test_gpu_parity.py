@@ -285,3 +285,44 @@ def test_cta_per_pair_latency_mode_for_few_long_pairs(ctx):
     got = run_batch(ctx, cases, capi.MODE_FULL)
     for k in range(len(cases)):
         assert got[k] == exps[k], k
+
+
+def test_find_hits_matches_oracle(ctx):
+    """f3: ABlast::findHits on the GPU (k-mer diagonal voting) vs the restatement pinned to the
+    reference: list length, front() and back() of the hit list, incl. N aliasing and tied diagonals."""
+    import oracle
+    from test_oracle import _hits_case
+    rst = oracle.restatement()
+    rng = np.random.default_rng(43)
+    ctx.clear_contigs()
+    cases = [_hits_case(rng) for _ in range(600)]
+    # a few larger, realistic tail windows
+    for _ in range(6):
+        a = gen.random_seq(rng, int(rng.integers(3000, 9000)), 0.001)
+        s = int(rng.integers(0, len(a) // 2))
+        b = gen.mutate(rng, a[s:s + int(rng.integers(500, 2500))], div=0.02)
+        cases.append((a, b, (0, len(a) - 1, 0, len(b) - 1)))
+    jobs = g.make_hits_jobs(len(cases))
+    for k, (a, b, w) in enumerate(cases):
+        jobs[k]["a_id"], jobs[k]["b_id"] = ctx.add_contig(a), ctx.add_contig(b)
+        jobs[k]["a_start"], jobs[k]["a_end"], jobs[k]["b_start"], jobs[k]["b_end"] = w
+    res = ctx.find_hits_batch(jobs)
+    nonempty = ties = 0
+    for k, (a, b, w) in enumerate(cases):
+        want, mc = rst.find_hits(a, w[0], w[1], b, w[2], w[3])
+        assert res[k]["n_hits"] == len(want), k
+        if len(want):
+            assert (res[k]["first_hit"], res[k]["last_hit"], res[k]["max_count"]) == (want[0], want[-1], mc), k
+            nonempty += 1
+            ties += len(want) > 1
+    assert nonempty > 150 and ties > 20
+    # reverse-complement views: the store holds rc(a); the job asks for view rc -> a
+    a, b, w = cases[-1]
+    ctx.clear_contigs()
+    j = g.make_hits_jobs(1)
+    j[0]["a_id"], j[0]["b_id"] = ctx.add_contig(gen.revcomp(a)), ctx.add_contig(b)
+    j[0]["a_rc"] = 1
+    j[0]["a_start"], j[0]["a_end"], j[0]["b_start"], j[0]["b_end"] = w
+    r = ctx.find_hits_batch(j)[0]
+    want, mc = rst.find_hits(a, w[0], w[1], b, w[2], w[3])
+    assert (r["n_hits"], r["first_hit"], r["last_hit"]) == (len(want), want[0], want[-1])

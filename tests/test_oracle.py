@@ -64,3 +64,44 @@ def test_revcomp_matches_reference_semantics():
     assert (gen.revcomp(rc) == s).all()
     if oracle.reference_available():
         assert (oracle.reference().revcomp(s) == rc).all()
+
+
+def _hits_case(rng):
+    la = int(rng.integers(0, 400))
+    p_n = float(rng.choice([0.0, 0.0, 0.02, 0.2]))
+    a = gen.random_seq(rng, la, p_n)
+    kind = rng.integers(0, 4)
+    if kind == 0 or la < 30:
+        b = gen.random_seq(rng, int(rng.integers(0, 400)), p_n)
+    elif kind == 1:  # b = mutated window of a: one dominant diagonal
+        s = int(rng.integers(0, la // 2)); e = int(rng.integers(s + 1, la + 1))
+        b = gen.mutate(rng, a[s:e], div=float(rng.choice([0.0, 0.02, 0.1])))
+    elif kind == 2:  # low complexity: many equal k-mers, ties between diagonals
+        unit = gen.random_seq(rng, int(rng.integers(1, 6)))
+        a = np.resize(unit, la).astype(np.uint8)
+        b = np.resize(unit, int(rng.integers(20, 200))).astype(np.uint8)
+    else:            # b longer than a / prefix
+        b = np.concatenate([gen.random_seq(rng, int(rng.integers(0, 50))), a, gen.random_seq(rng, int(rng.integers(0, 50)))])
+    lb = len(b)
+    if rng.random() < 0.5:
+        w = (0, max(la - 1, 0), 0, max(lb - 1, 0))
+    else:
+        w = (int(rng.integers(0, la + 3)), int(rng.integers(0, la + 30)), int(rng.integers(0, lb + 3)), int(rng.integers(0, lb + 30)))
+    return a, b, w
+
+
+@pytest.mark.skipif(not oracle.reference_available(), reason="reference build not present")
+def test_find_hits_restatement_matches_reference():
+    """ABlast::findHits (ablast.cc:41-76) restated in oracle/bsw_oracle.c vs the compiled reference,
+    including the radix-4 aliasing of N and ties between diagonals."""
+    ref, rst = oracle.reference(), oracle.restatement()
+    rng = np.random.default_rng(42)
+    nonempty = ties = 0
+    for _ in range(1500):
+        a, b, w = _hits_case(rng)
+        want = ref.find_hits(a, w[0], w[1], b, w[2], w[3])
+        got, mc = rst.find_hits(a, w[0], w[1], b, w[2], w[3])
+        assert list(got) == list(want), (w, len(a), len(b))
+        nonempty += len(want) > 0
+        ties += len(want) > 1
+    assert nonempty > 300 and ties > 50
