@@ -59,8 +59,26 @@ HITS_JOB_DTYPE = np.dtype([
     ("a_id", "<u4"), ("b_id", "<u4"), ("a_rc", "u1"), ("b_rc", "u1"), ("reserved_", "u1", (6,)),
     ("a_off", "<u8"), ("a_len", "<u8"), ("b_off", "<u8"), ("b_len", "<u8"),
     ("a_start", "<u8"), ("a_end", "<u8"), ("b_start", "<u8"), ("b_end", "<u8")], align=True)
-HITS_RESULT_DTYPE = np.dtype([("n_hits", "<u4"), ("max_count", "<u4"), ("first_hit", "<u8"), ("last_hit", "<u8")],
+HITS_BLOCK_DTYPE = np.dtype([("num_reads", "<i4"), ("m_strand", "u1"), ("s_strand", "u1"), ("reserved_", "u1", (2,)),
+                        ("m_begin", "<i4"), ("m_end", "<i4"), ("s_begin", "<i4"), ("s_end", "<i4")], align=True)
+MERGE_BLOCK_DTYPE = np.dtype([("m_id", "<u4"), ("s_id", "<u4"), ("first_block", "<u4"), ("n_blocks", "<u4"),
+                              ("m_ltail", "u1"), ("m_rtail", "u1"), ("s_ltail", "u1"), ("s_rtail", "u1")], align=True)
+MERGE_RESULT_DTYPE = np.dtype([("status", "<i4"), ("align_ok", "<i4"), ("align_rev", "<i4"), ("coords_set", "<i4"),
+                               ("m_start", "<i4"), ("m_end", "<i4"), ("s_start", "<i4"), ("s_end", "<i4"),
+                               ("n_alignments", "<u4"), ("n_hits_calls", "<u4")], align=True)
+MERGE_STATS_DTYPE = np.dtype([("rounds", "<u8"), ("alignments", "<u8"), ("hits_calls", "<u8"), ("cells", "<u8")])
+
+RESULT_DTYPE = np.dtype([("n_hits", "<u4"), ("max_count", "<u4"), ("first_hit", "<u8"), ("last_hit", "<u8")],
                              align=True)
+
+BLOCK_DTYPE = np.dtype([("num_reads", "<i4"), ("m_strand", "u1"), ("s_strand", "u1"), ("reserved_", "u1", (2,)),
+                        ("m_begin", "<i4"), ("m_end", "<i4"), ("s_begin", "<i4"), ("s_end", "<i4")], align=True)
+MERGE_BLOCK_DTYPE = np.dtype([("m_id", "<u4"), ("s_id", "<u4"), ("first_block", "<u4"), ("n_blocks", "<u4"),
+                              ("m_ltail", "u1"), ("m_rtail", "u1"), ("s_ltail", "u1"), ("s_rtail", "u1")], align=True)
+MERGE_RESULT_DTYPE = np.dtype([("status", "<i4"), ("align_ok", "<i4"), ("align_rev", "<i4"), ("coords_set", "<i4"),
+                               ("m_start", "<i4"), ("m_end", "<i4"), ("s_start", "<i4"), ("s_end", "<i4"),
+                               ("n_alignments", "<u4"), ("n_hits_calls", "<u4")], align=True)
+MERGE_STATS_DTYPE = np.dtype([("rounds", "<u8"), ("alignments", "<u8"), ("hits_calls", "<u8"), ("cells", "<u8")])
 
 RESULT_DTYPE = np.dtype([
     ("status", "<i4"), ("has_match", "<i4"), ("score", "<i8"),
@@ -80,7 +98,7 @@ EXPORTS = [
     "gamx_ops_capacity", "gamx_align_batch", "gamx_unpack_ops", "gamx_cigar_rle",
     "gamx_plan_create", "gamx_plan_run", "gamx_plan_sync", "gamx_plan_fetch", "gamx_plan_last_ms",
     "gamx_plan_cells", "gamx_plan_kernel_launches", "gamx_plan_destroy", "gamx_measure_int_peak",
-    "gamx_shard_by_cost", "gamx_find_hits_batch",
+    "gamx_shard_by_cost", "gamx_find_hits_batch", "gamx_merge_align",
 ]
 
 _lib = None
@@ -145,6 +163,8 @@ def load_library(build_if_missing: bool = True):
     L.gamx_plan_destroy.restype = None
     L.gamx_find_hits_batch.argtypes = [vp, vp, u64, vp]
     L.gamx_find_hits_batch.restype = C.c_int
+    L.gamx_merge_align.argtypes = [vp, vp, u64, vp, u64, vp, vp]
+    L.gamx_merge_align.restype = C.c_int
     L.gamx_measure_int_peak.argtypes = [vp, C.c_int, C.c_int]
     L.gamx_measure_int_peak.restype = C.c_double
     _lib = L
@@ -287,6 +307,17 @@ class Context:
         res = np.zeros(len(jobs), dtype=HITS_RESULT_DTYPE)
         self._check(self.lib.gamx_find_hits_batch(self._h, jobs.ctypes.data, len(jobs), res.ctypes.data))
         return res
+
+    def merge_align(self, merge_blocks: np.ndarray, blocks: np.ndarray):
+        """gam-merge's alignment stage (PctgBuilder::alignMergeBlock) for a set of merge blocks, as
+        rounds of GPU batches.  Returns (results[MERGE_RESULT_DTYPE], stats dict)."""
+        mbs = np.ascontiguousarray(merge_blocks, dtype=MERGE_BLOCK_DTYPE)
+        blk = np.ascontiguousarray(blocks, dtype=BLOCK_DTYPE)
+        res = np.zeros(len(mbs), dtype=MERGE_RESULT_DTYPE)
+        stats = np.zeros(1, dtype=MERGE_STATS_DTYPE)
+        self._check(self.lib.gamx_merge_align(self._h, mbs.ctypes.data, len(mbs), blk.ctypes.data, len(blk),
+                                              res.ctypes.data, stats.ctypes.data))
+        return res, {k: int(stats[0][k]) for k in stats.dtype.names}
 
     def plan(self, jobs: np.ndarray) -> Plan:
         return Plan(self, jobs)

@@ -33,6 +33,7 @@
 #include "bsw_host.h"
 #include "bsw_traceback.h"
 #include "bsw_warp.h"
+#include "merge_collector.h"
 
 using namespace gamx;
 
@@ -1296,6 +1297,237 @@ int gamx_find_hits_batch(gamx_ctx* ctx, const gamx_hits_job* jobs, uint64_t n, g
       r.last_hit = (uint32_t)(hj[k].a_start + ho[k].last_d);
     }
   }
+  return GAMX_OK;
+}
+
+int gamx_merge_align(gamx_ctx* ctx, const gamx_merge_block* mbs, uint64_t n, const gamx_block* blocks,
+                     uint64_t n_blocks, gamx_merge_result* results, gamx_merge_stats* stats) {
+  if (!ctx || (!mbs && n) || (!results && n) || (!blocks && n_blocks)) return GAMX_ERR_INVALID;
+  gamx_merge_stats S = {};
+  std::vector<MergeState> st(n);
+  std::vector<uint32_t> n_aln(n, 0), n_hits(n, 0);
+  const uint32_t band = GAMX_DEFAULT_BAND;
+  // ---- INIT (alignMergeBlock .cc:741-744, findBestAlignment .cc:1380-1408) ----
+  for (uint64_t i = 0; i < n; i++) {
+    MergeState& m = st[i];
+    memset(&results[i], 0, sizeof(gamx_merge_result));
+    m.mb = &mbs[i]; m.blocks = blocks;
+    if ((uint64_t)mbs[i].first_block + mbs[i].n_blocks > n_blocks) { ctx->err = "merge block outside the block array"; return GAMX_ERR_INVALID; }
+    m.msz = gamx_contig_length(ctx, mbs[i].m_id); m.ssz = gamx_contig_length(ctx, mbs[i].s_id);
+    if (mbs[i].n_blocks == 0) { m.phase = MergeState::kDone; continue; }  // bad alignment (.cc:1512)
+    const gamx_block& f = blocks[mbs[i].first_block];
+    const gamx_block& l = blocks[mbs[i].first_block + mbs[i].n_blocks - 1];
+    m.reversed_order = !(f.m_begin <= l.m_begin);
+    m.master_start = std::min(f.m_begin, l.m_begin);
+    const int64_t s_start = std::min(f.s_begin, l.s_begin), s_end = std::max(f.s_end, l.s_end);
+    uint64_t con = 0, dis = 0;
+    int32_t min_frame_len = 100;
+    for (uint32_t k = 0; k < mbs[i].n_blocks; k++) {
+      const gamx_block& b = blocks[mbs[i].first_block + k];
+      const int32_t ml = std::min(frame_len(b.m_begin, b.m_end), frame_len(b.s_begin, b.s_end));
+      if (k == 0 || min_frame_len > ml) min_frame_len = ml;
+      if (b.m_strand != b.s_strand) dis += (uint64_t)(int64_t)b.num_reads; else con += (uint64_t)(int64_t)b.num_reads;
+    }
+    m.con_prob = double(con) / double(con + dis);
+    const size_t mt = (size_t)(0.3 * m.msz), stt = (size_t)(0.3 * m.ssz);
+    m.align_threshold = (int32_t)(0.7 * min_frame_len);
+    m.threshold = (int32_t)std::min<size_t>(200, std::min(mt, stt));
+    m.s_start_fwd = s_start; m.s_end_fwd = s_end;
+    if (m.con_prob >= 0.5) start_chain(m, false, s_start, s_end);
+    else if (m.con_prob < 0.5) start_chain(m, true, s_start, s_end);
+    else m.phase = MergeState::kDone;  // NaN: neither branch runs -> bad alignment
+  }
+  std::vector<gamx_job> jobs;
+  std::vector<gamx_hits_job> hjobs;
+  std::vector<gamx_result> jres;
+  std::vector<gamx_hits_result> hres;
+  auto mk_job = [&](uint32_t a_id, bool a_rc, uint64_t a_off, uint32_t b_id, bool b_rc, uint64_t begin_a, uint64_t end_a,
+                    uint64_t begin_b, uint64_t end_b, bool fs, bool fe) {
+    gamx_job j = {};
+    j.a_id = a_id; j.b_id = b_id; j.a_rc = a_rc; j.b_rc = b_rc; j.a_off = a_off; j.a_len = UINT64_MAX; j.b_len = UINT64_MAX;
+    j.begin_a = begin_a; j.end_a = end_a; j.begin_b = begin_b; j.end_b = end_b;
+    j.band = band; j.gap = GAMX_DEFAULT_GAP; j.force_start = fs; j.force_end = fe; j.mode = GAMX_MODE_ENDPOINTS;
+    jobs.push_back(j);
+    return jobs.size() - 1;
+  };
+  auto mk_hits = [&](uint32_t a_id, bool a_rc, uint64_t a_off, uint32_t b_id, bool b_rc, uint64_t a_start, uint64_t a_end,
+                     uint64_t b_start, uint64_t b_end) {
+    gamx_hits_job j = {};
+    j.a_id = a_id; j.b_id = b_id; j.a_rc = a_rc; j.b_rc = b_rc; j.a_off = a_off; j.a_len = UINT64_MAX; j.b_len = UINT64_MAX;
+    j.a_start = a_start; j.a_end = a_end; j.b_start = b_start; j.b_end = b_end;
+    hjobs.push_back(j);
+    return hjobs.size() - 1;
+  };
+  // ---- rounds ----
+  for (;;) {
+    jobs.clear(); hjobs.clear();
+    for (uint64_t i = 0; i < n; i++) {
+      MergeState& m = st[i];
+      const uint32_t mid = m.mb->m_id, sid = m.mb->s_id;
+      if (m.phase == MergeState::kChain) {
+        // alignBlocks: the k-th chained window (.cc:1657-1669)
+        const gamx_block& b = block_at(m, m.k);
+        const int32_t mlen = frame_len(b.m_begin, b.m_end), slen = frame_len(b.s_begin, b.s_end);
+        if (m.k > 0) {
+          const gamx_block& p = block_at(m, m.k - 1);
+          const int32_t mgap = p.m_begin <= b.m_begin ? (b.m_begin - p.m_end - 1) : (p.m_begin - b.m_end - 1);
+          const int32_t sgap = p.s_begin <= b.s_begin ? (b.s_begin - p.s_end - 1) : (p.s_begin - b.s_end - 1);
+          m.m_at = std::max<int64_t>((int64_t)m.lm_a + mgap, 0);
+          m.s_at = std::max<int64_t>((int64_t)m.lm_b + sgap, 0);
+        }
+        m.job_main = mk_job(mid, false, 0, sid, m.rev, (uint64_t)m.m_at, (uint64_t)(m.m_at + mlen - 1), (uint64_t)m.s_at,
+                            (uint64_t)(m.s_at + slen - 1), false, false);
+      } else if (m.phase == MergeState::kTailHits) {
+        // findHits seeds, .cc:1539,1555,1579,1597
+        if (m.want_left) {
+          if (m.left_rev) m.job_left = mk_hits(sid, m.rev, 0, mid, false, 0, m.as_b - 1, 0, m.as_a - 1);
+          else m.job_left = mk_hits(mid, false, 0, sid, m.rev, 0, m.as_a - 1, 0, m.as_b - 1);
+        }
+        if (m.want_right) {
+          if (m.right_rev) {  // rightTail = chop_begin(slave, alignEnd.second + 1)
+            const uint64_t tl = m.ssz - (m.ae_b + 1);
+            m.job_right = mk_hits(sid, m.rev, m.ae_b + 1, mid, false, 0, tl - 1, m.ae_a + 1, m.msz - 1);
+          } else {
+            const uint64_t tl = m.msz - (m.ae_a + 1);
+            m.job_right = mk_hits(mid, false, m.ae_a + 1, sid, m.rev, 0, tl - 1, m.ae_b + 1, m.ssz - 1);
+          }
+        }
+      } else if (m.phase == MergeState::kTailAlign) {
+        // tail alignments, .cc:1544-1607: left with force_end, right with force_start
+        if (m.want_left) {
+          if (m.left_rev) {
+            const uint64_t ba = m.left_hits.n_hits ? m.left_hits.last_hit : m.as_b - m.as_a;
+            m.job_left = mk_job(sid, m.rev, 0, mid, false, ba, m.as_b - 1, 0, m.as_a - 1, false, true);
+          } else {
+            const uint64_t ba = m.left_hits.n_hits ? m.left_hits.last_hit : m.as_a - m.as_b;
+            m.job_left = mk_job(mid, false, 0, sid, m.rev, ba, m.as_a - 1, 0, m.as_b - 1, false, true);
+          }
+        }
+        if (m.want_right) {
+          const uint64_t ba = m.right_hits.n_hits ? m.right_hits.first_hit : 0;
+          if (m.right_rev) {
+            const uint64_t tl = m.ssz - (m.ae_b + 1);
+            m.job_right = mk_job(sid, m.rev, m.ae_b + 1, mid, false, ba, tl - 1, m.ae_a + 1, m.msz - 1, true, false);
+          } else {
+            const uint64_t tl = m.msz - (m.ae_a + 1);
+            m.job_right = mk_job(mid, false, m.ae_a + 1, sid, m.rev, ba, tl - 1, m.ae_b + 1, m.ssz - 1, true, false);
+          }
+        }
+      }
+    }
+    if (jobs.empty() && hjobs.empty()) break;
+    S.rounds++;
+    if (!hjobs.empty()) {
+      hres.assign(hjobs.size(), gamx_hits_result());
+      if (int rc = gamx_find_hits_batch(ctx, hjobs.data(), hjobs.size(), hres.data())) return rc;
+      S.hits_calls += hjobs.size();
+    }
+    if (!jobs.empty()) {
+      jres.assign(jobs.size(), gamx_result());
+      if (int rc = gamx_align_batch(ctx, jobs.data(), jobs.size(), jres.data(), nullptr, 0)) return rc;
+      S.alignments += jobs.size();
+      for (const gamx_result& r : jres) S.cells += r.x_size * (2ull * band + 1);
+    }
+    // ---- advance every live merge block ----
+    for (uint64_t i = 0; i < n; i++) {
+      MergeState& m = st[i];
+      if (m.phase == MergeState::kChain) {
+        const gamx_result& r = jres[m.job_main];
+        n_aln[i]++;
+        if (r.status == GAMX_JOB_OUT_OF_RANGE || r.status == GAMX_JOB_UNDEFINED) { m.status = 2; m.phase = MergeState::kDone; continue; }
+        const AlnLite al = lite_from(r);
+        m.aligns.push_back(al);
+        m.lm_a = al.last_a; m.lm_b = al.last_b;  // last_match_pos (default alignment: (0,0))
+        if (++m.k < m.mb->n_blocks) continue;
+        // chain finished in this orientation: is_good? (.cc:1435,1454,1485,1503)
+        if (!is_good_list(m.aligns, (uint64_t)m.align_threshold)) {
+          if (m.attempts < 2) {
+            start_chain(m, !m.rev, m.s_start_fwd, m.s_end_fwd);
+          } else {
+            m.aligns.clear();  // bad alignment: interrupts the merge (.cc:1512)
+            m.phase = MergeState::kDone;
+          }
+          continue;
+        }
+        // ENDS (.cc:1515-1526)
+        m.as_a = m.aligns.front().first_a; m.as_b = m.aligns.front().first_b;
+        m.ae_a = m.aligns.back().last_a; m.ae_b = m.aligns.back().last_b;
+        const uint64_t i1 = m.as_a, i2 = m.msz - m.ae_a - 1, j1 = m.as_b, j2 = m.ssz - m.ae_b - 1;
+        const uint64_t thr = (uint64_t)m.threshold;
+        m.left_hits = gamx_hits_result(); m.right_hits = gamx_hits_result();
+        if (std::min(i1, j1) < thr && std::min(i2, j2) < thr) { m.phase = MergeState::kDone; continue; }
+        m.want_left = std::min(i1, j1) >= thr;
+        m.want_right = std::min(i2, j2) >= thr;
+        m.left_rev = i1 < j1;   // slave tail is `a` (.cc:1537)
+        m.right_rev = i2 < j2;  // (.cc:1575)
+        if (m.want_right) {     // chop_begin throws std::domain_error when nothing is left (contig.code.hpp:235-237)
+          const bool empty_tail = m.right_rev ? (m.ssz <= m.ae_b + 1) : (m.msz <= m.ae_a + 1);
+          if (empty_tail) { m.status = 2; m.phase = MergeState::kDone; continue; }
+        }
+        m.phase = MergeState::kTailHits;
+      } else if (m.phase == MergeState::kTailHits) {
+        if (m.want_left) { m.left_hits = hres[m.job_left]; n_hits[i]++; }
+        if (m.want_right) { m.right_hits = hres[m.job_right]; n_hits[i]++; }
+        m.phase = MergeState::kTailAlign;
+      } else if (m.phase == MergeState::kTailAlign) {
+        bool threw = false;
+        if (m.want_left) {
+          const gamx_result& r = jres[m.job_left];
+          n_aln[i]++;
+          if (r.status == GAMX_JOB_OUT_OF_RANGE || r.status == GAMX_JOB_UNDEFINED) threw = true;
+          m.left = lite_from(r); m.have_left = true;
+        }
+        if (m.want_right) {
+          const gamx_result& r = jres[m.job_right];
+          n_aln[i]++;
+          if (r.status == GAMX_JOB_OUT_OF_RANGE || r.status == GAMX_JOB_UNDEFINED) threw = true;
+          m.right = lite_from(r); m.have_right = true;
+        }
+        if (threw) m.status = 2;
+        m.phase = MergeState::kDone;
+      }
+    }
+  }
+  // ---- FINISH: alignMergeBlock .cc:757-843 ----
+  for (uint64_t i = 0; i < n; i++) {
+    MergeState& m = st[i];
+    gamx_merge_result& R = results[i];
+    R.n_alignments = n_aln[i]; R.n_hits_calls = n_hits[i];
+    if (m.status) { R.status = m.status; continue; }
+    double main_hom = 0.0;
+    for (size_t k = 0; k < m.aligns.size(); k++) if (k == 0 || m.aligns[k].homology < main_hom) main_hom = m.aligns[k].homology;
+    R.align_ok = 1;
+    if (m.aligns.empty() || !(main_hom >= kMinHomology)) { R.align_ok = 0; continue; }  // bad alignment between blocks
+    uint64_t as_a = m.aligns.front().first_a, as_b = m.aligns.front().first_b;
+    uint64_t ae_a = m.aligns.back().last_a, ae_b = m.aligns.back().last_b;
+    const uint64_t i1 = as_a, i2 = m.msz - ae_a - 1, j1 = as_b, j2 = m.ssz - ae_b - 1;
+    AlnLite left, right;
+    left.homology = right.homology = 100.0;  // MyAlignment(100): not computed
+    if (m.have_left) left = m.left;
+    if (m.have_right) right = m.right;
+    const size_t mt = (size_t)(0.3 * m.msz), stt = (size_t)(0.3 * m.ssz);
+    const uint64_t left_min = (uint64_t)(0.7 * std::min(i1, j1)), right_min = (uint64_t)(0.7 * std::min(i2, j2));
+    const uint64_t thr = std::min<size_t>(100, std::min(mt, stt));
+    const bool s_lt = m.rev ? m.mb->s_rtail : m.mb->s_ltail, s_rt = m.rev ? m.mb->s_ltail : m.mb->s_rtail;
+    if (m.mb->m_ltail && s_lt && std::min(i1, j1) >= thr) {
+      if (is_good_one(left, left_min)) {
+        as_a = left.first_a; as_b = left.first_b;
+        if (m.have_left && m.left_rev) std::swap(as_a, as_b);
+      } else R.align_ok = 0;
+    }
+    if (m.mb->m_rtail && s_rt && std::min(i2, j2) >= thr) {
+      if (is_good_one(right, right_min)) {
+        uint64_t ta = right.last_a, tb = right.last_b;
+        if (m.have_right && m.right_rev) { std::swap(ta, tb); ae_a = ta; ae_b += tb + 1; }
+        else { ae_a += ta + 1; ae_b = tb; }
+      } else R.align_ok = 0;
+    }
+    if (m.rev) { const uint64_t t = as_b; as_b = m.ssz - ae_b - 1; ae_b = m.ssz - t - 1; }
+    R.align_rev = m.rev;
+    R.m_start = (int32_t)as_a; R.m_end = (int32_t)ae_a; R.s_start = (int32_t)as_b; R.s_end = (int32_t)ae_b;
+    R.coords_set = 1;
+  }
+  if (stats) *stats = S;
   return GAMX_OK;
 }
 

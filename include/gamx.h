@@ -214,6 +214,47 @@ typedef struct {
 
 GAMX_API int gamx_find_hits_batch(gamx_ctx* ctx, const gamx_hits_job* jobs, uint64_t n, gamx_hits_result* results);
 
+/* ---- gam-merge alignment stage as batched rounds (the "batch collector") ---------------- */
+
+/* One block of a merge block: the two frames (0-based inclusive contig coordinates, Frame.hpp:53-60)
+ * and the read count (Block.hpp:68-71).  strand: 0 '+', 1 '-'. */
+typedef struct {
+  int32_t num_reads;
+  uint8_t m_strand, s_strand;
+  uint8_t reserved_[2];
+  int32_t m_begin, m_end, s_begin, s_end;
+} gamx_block;
+
+/* One merge block = one CompactAssemblyGraph vertex (MergeDescriptor.hpp:40-69): a master contig,
+ * a slave contig (ids in the context's store), its blocks [first_block, first_block + n_blocks) and
+ * the tail flags the graph code sets. */
+typedef struct {
+  uint32_t m_id, s_id;
+  uint32_t first_block, n_blocks;
+  uint8_t m_ltail, m_rtail, s_ltail, s_rtail;
+} gamx_merge_block;
+
+/* What PctgBuilder::alignMergeBlock (PctgBuilder.cc:726-844) writes into the MergeBlock. */
+typedef struct {
+  int32_t status;      /* 0 ok; 2: the reference would throw (std::out_of_range / std::domain_error) and
+                          drop the graph (ThreadedBuildPctg.cc:322-329) */
+  int32_t align_ok, align_rev;
+  int32_t coords_set;  /* 0 when alignMergeBlock returns before assigning the coordinates (.cc:825-829) */
+  int32_t m_start, m_end, s_start, s_end;
+  uint32_t n_alignments, n_hits_calls; /* find_alignment / findHits calls this merge block needed */
+} gamx_merge_result;
+
+typedef struct {
+  uint64_t rounds, alignments, hits_calls, cells; /* GPU batches issued, jobs in them, DP cells */
+} gamx_merge_stats;
+
+/* Runs the alignment stage of gam-merge for n merge blocks: per merge block the chained block
+ * alignments in the orientation the strand evidence suggests, the retry in the other orientation,
+ * then up to two tail alignments seeded by findHits - as rounds of GPU batches over all merge
+ * blocks.  Band 150 and gap -8 as at every reference call site (PctgBuilder.cc:1410,1628). */
+GAMX_API int gamx_merge_align(gamx_ctx* ctx, const gamx_merge_block* mbs, uint64_t n, const gamx_block* blocks,
+                              uint64_t n_blocks, gamx_merge_result* results, gamx_merge_stats* stats);
+
 /* ---- sharding ------------------------------------------------------------------------ */
 
 /* The cost-balanced split gamx_align_batch applies over a context's devices (longest-processing-

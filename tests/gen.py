@@ -140,3 +140,92 @@ def bulk_pairs(rng, n, length, div=0.02, indel_share=0.5, len_lo=None, len_hi=No
         done += m
     return (np.concatenate(a_parts), np.concatenate(a_lens_all).astype(np.uint64),
             np.concatenate(b_parts), np.concatenate(b_lens_all).astype(np.uint64))
+
+
+def mutate_with_map(rng, s, div=0.01, indel_share=0.5):
+    """Like mutate(), but also returns pos_map with pos_map[p] = index in the result of source
+    position p (for a deleted base: the index of the next surviving base); pos_map[len(s)] = len(result)."""
+    n = len(s)
+    u = rng.random(n)
+    p_sub = div * (1.0 - indel_share)
+    p_ins = div * indel_share / 2
+    p_del = div * indel_share / 2
+    is_sub = u < p_sub
+    is_ins = (u >= p_sub) & (u < p_sub + p_ins)
+    is_del = (u >= p_sub + p_ins) & (u < p_sub + p_ins + p_del)
+    out = s.copy()
+    shift = rng.integers(1, 4, size=n, dtype=np.uint8)
+    out = np.where(is_sub & (s < 4), (s + shift) % 4, out).astype(np.uint8)
+    reps = np.where(is_del, 0, np.where(is_ins, 2, 1)).astype(np.int64)
+    res = np.repeat(out, reps)
+    pos_map = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(reps, out=pos_map[1:])
+    ins_pos = np.nonzero(is_ins)[0]
+    res[pos_map[ins_pos] + 1] = rng.integers(0, 4, size=len(ins_pos), dtype=np.uint8)
+    return res, pos_map
+
+
+def make_assembly(rng, genome_len=200_000, master_mean=60_000, slave_mean=40_000, div=0.01, rc_frac=0.5,
+                  frame_lo=500, frame_hi=5000, min_overlap=500, p_n=0.0, trim_prob=0.0, wrong_strand_prob=0.0):
+    """Synthetic master/slave assembly pair: a random genome cut at Poisson
+    breakpoints into master contigs; a mutated copy cut independently into slave contigs, a fraction of
+    them reverse-complemented; for every overlapping (master, slave) pair one merge block whose blocks
+    are consecutive frames tiling the overlap.  Returns (masters, slaves, merge_blocks) with
+    merge_blocks = [dict(m=idx, s=idx, blocks=[dict(num_reads, m_strand, s_strand, m_begin, m_end, s_begin, s_end)])]."""
+    G = random_seq(rng, genome_len, p_n)
+    Gs, pmap = mutate_with_map(rng, G, div)
+
+    def cuts(total, mean):
+        pts = [0]
+        while pts[-1] < total:
+            pts.append(pts[-1] + max(2000, int(rng.exponential(mean))))
+        pts[-1] = total
+        if len(pts) > 2 and pts[-1] - pts[-2] < 2000:
+            pts.pop(-2)
+        return pts
+
+    mc = cuts(genome_len, master_mean)          # master contig k = G[mc[k]:mc[k+1]]
+    sc_g = cuts(genome_len, slave_mean)         # slave cut points in genome coordinates
+    masters = [G[mc[k]:mc[k + 1]].copy() for k in range(len(mc) - 1)]
+    slaves, s_rc = [], []
+    for k in range(len(sc_g) - 1):
+        seq = Gs[pmap[sc_g[k]]:pmap[sc_g[k + 1]]].copy()
+        rc = bool(rng.random() < rc_frac)
+        slaves.append(revcomp(seq) if rc else seq)
+        s_rc.append(rc)
+    merge_blocks = []
+    for mi in range(len(masters)):
+        for si in range(len(slaves)):
+            lo, hi = max(mc[mi], sc_g[si]), min(mc[mi + 1], sc_g[si + 1])   # overlap in genome coordinates
+            if hi - lo < min_overlap:
+                continue
+            blocks = []
+            p = lo
+            while p < hi:
+                q = min(hi, p + int(rng.integers(frame_lo, frame_hi + 1)))
+                if hi - q < frame_lo // 2:
+                    q = hi
+                m_b, m_e = p - mc[mi], q - 1 - mc[mi]
+                sb, se = int(pmap[p] - pmap[sc_g[si]]), int(pmap[q] - 1 - pmap[sc_g[si]])
+                if se < sb:
+                    p = q
+                    continue
+                if s_rc[si]:
+                    L = len(slaves[si])
+                    sb, se = L - 1 - se, L - 1 - sb
+                blocks.append(dict(num_reads=max(1, (q - p) // 50), m_strand=0, s_strand=1 if s_rc[si] else 0,
+                                   m_begin=int(m_b), m_end=int(m_e), s_begin=int(sb), s_end=int(se)))
+                p = q
+            # real blocks rarely tile the whole overlap: dropping leading / trailing frames leaves contig
+            # tails beyond the aligned blocks, which triggers the findHits-seeded tail alignments
+            if len(blocks) >= 3 and rng.random() < trim_prob:
+                blocks = blocks[int(rng.integers(0, 2)):len(blocks) - int(rng.integers(0, 2))]
+                if len(blocks) >= 3 and rng.random() < 0.5:
+                    blocks = blocks[1:]
+            # wrong strand evidence makes findBestAlignment try the other orientation first
+            if rng.random() < wrong_strand_prob:
+                for b in blocks:
+                    b["s_strand"] ^= 1
+            if blocks:
+                merge_blocks.append(dict(m=mi, s=si, blocks=blocks))
+    return masters, slaves, merge_blocks
