@@ -100,8 +100,12 @@ class MergeOracle:
         r, _ = self.chk.align(a, begin_a, end_a, b, begin_b, end_b, self.band, -8, force_start, force_end,
                               want_ops=False)
         self.stats.alignments += 1
-        x = getattr(r, "x_size", 0)
-        self.stats.cells += int(x) * (2 * self.band + 1)
+        # DP cells of this call: x_size * (2*band+1), banded_smith_waterman.cc:90-97
+        la, lb = len(a), len(b)
+        if end_b >= begin_b:
+            eb = end_b if end_b < lb else (lb - 1) % U64
+            x = min((eb - begin_b + 1) % U64, (la + self.band - begin_a) % U64, 500000)
+            self.stats.cells += x * (2 * self.band + 1)
         if r.status == 2:
             raise IndexError("Contig::at")
         if r.status != 0 or r.n_ops == 0:
