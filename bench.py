@@ -309,7 +309,7 @@ def main():
     ach_int = cells_rank / (dev_ms * 1e-3 / args.steps) * ALGO_LANE_OPS_PER_CELL / 1e12
     roofline = {"bound": "int_alu", "achieved": ach_int, "peak": int_peak / 1e12, "unit": "Tlaneop/s",
                 "frac": ach_int / (int_peak / 1e12) if int_peak else None, "traffic": None,
-                "kernel": "k1_kernel<5,32,true>" if spec["mode"] else "k1_kernel<9,16,false>",
+                "kernel": "k1_kernel<9,16,true>" if spec["mode"] else "k1_kernel<9,16,false>",
                 "algorithmic": f"{ALGO_LANE_OPS_PER_CELL} int32 lane-ops per cell (SURVEY 8d) x {int(cells_rank)} cells per launch",
                 "peak_source": "VIADDMNMX issue rate measured live by gamx_measure_int_peak (register-only kernel)"}
     seq_bytes = total_bases * 3 / 8

@@ -59,16 +59,7 @@ HITS_JOB_DTYPE = np.dtype([
     ("a_id", "<u4"), ("b_id", "<u4"), ("a_rc", "u1"), ("b_rc", "u1"), ("reserved_", "u1", (6,)),
     ("a_off", "<u8"), ("a_len", "<u8"), ("b_off", "<u8"), ("b_len", "<u8"),
     ("a_start", "<u8"), ("a_end", "<u8"), ("b_start", "<u8"), ("b_end", "<u8")], align=True)
-HITS_BLOCK_DTYPE = np.dtype([("num_reads", "<i4"), ("m_strand", "u1"), ("s_strand", "u1"), ("reserved_", "u1", (2,)),
-                        ("m_begin", "<i4"), ("m_end", "<i4"), ("s_begin", "<i4"), ("s_end", "<i4")], align=True)
-MERGE_BLOCK_DTYPE = np.dtype([("m_id", "<u4"), ("s_id", "<u4"), ("first_block", "<u4"), ("n_blocks", "<u4"),
-                              ("m_ltail", "u1"), ("m_rtail", "u1"), ("s_ltail", "u1"), ("s_rtail", "u1")], align=True)
-MERGE_RESULT_DTYPE = np.dtype([("status", "<i4"), ("align_ok", "<i4"), ("align_rev", "<i4"), ("coords_set", "<i4"),
-                               ("m_start", "<i4"), ("m_end", "<i4"), ("s_start", "<i4"), ("s_end", "<i4"),
-                               ("n_alignments", "<u4"), ("n_hits_calls", "<u4")], align=True)
-MERGE_STATS_DTYPE = np.dtype([("rounds", "<u8"), ("alignments", "<u8"), ("hits_calls", "<u8"), ("cells", "<u8")])
-
-RESULT_DTYPE = np.dtype([("n_hits", "<u4"), ("max_count", "<u4"), ("first_hit", "<u8"), ("last_hit", "<u8")],
+HITS_RESULT_DTYPE = np.dtype([("n_hits", "<u4"), ("max_count", "<u4"), ("first_hit", "<u8"), ("last_hit", "<u8")],
                              align=True)
 
 BLOCK_DTYPE = np.dtype([("num_reads", "<i4"), ("m_strand", "u1"), ("s_strand", "u1"), ("reserved_", "u1", (2,)),
@@ -113,11 +104,12 @@ def load_library(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_missing and _build.needs_build():
+    lib_path = os.environ.get("GAMX_LIB", _build.LIB)  # GAMX_LIB: alternative build, experiments only
+    if lib_path == _build.LIB and build_if_missing and _build.needs_build():
         _build.build()
-    if not os.path.exists(_build.LIB):
+    if not os.path.exists(lib_path):
         raise GamxError("libgamx.so is missing: run `python -m gam_ngs_b200.build`")
-    L = C.CDLL(_build.LIB)
+    L = C.CDLL(lib_path)
     vp, u64, u8p = C.c_void_p, C.c_uint64, C.POINTER(C.c_uint8)
     L.gamx_abi_version.restype = C.c_int
     L.gamx_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]

@@ -161,6 +161,16 @@ GAMX_HD uint32_t prmt(uint32_t lo, uint32_t hi, uint32_t sel) {
 #endif
 }
 
+// c + (byte n of a): IDP.4A with a one-hot multiplier, runs on the FMA pipe at full rate
+// (measured 18.5 T lane-ops/s, the same as IMAD and VIADDMNMX)
+GAMX_HD int add_byte(uint32_t a, int n, int c) {
+#if defined(__CUDA_ARCH__)
+  return (int)__dp4a(a, 1u << (8 * n), (uint32_t)c);
+#else
+  return (int)((uint32_t)c + ((a >> (8 * n)) & 0xffu));
+#endif
+}
+
 GAMX_HD int popc32(uint32_t v) {
 #if defined(__CUDA_ARCH__)
   return __popc(v);

@@ -80,12 +80,13 @@ struct Prepared {
   DevJob dj;           // kClassWarp
 };
 
-// Lanes per pair (LG) and stripe width (C) for a band.  Score = lane utilisation (2*band+1)/(LG*C),
-// discounted by 12 % when the stripe has to be split into sub-blocks (S < C: one extra shared-memory
-// load per sub-block and step) - the ranking measured on B200 for bands 64/150/256 in both modes
-// (profiles/r1b_geometry_probe.txt).  Ties go to fewer lanes per pair.
+// Lanes per pair (LG) and stripe width (C) for a band: the combination with the best lane
+// utilisation (2*band+1)/(LG*C), discounted by 6 % for stripes wider than 12 slots (their selector
+// loads conflict in shared-memory banks; measured on B200 for band 64: LG=16,C=9 beats LG=8,C=17,
+// profiles/r1c_geometry_probe.txt); ties go to fewer lanes per pair.  LG < 32 only from C >= 5.
 // GAMX_FORCE_LG / GAMX_FORCE_C (environment) override the choice for experiments.
 inline void geometry_for_band(uint64_t band, bool dirs, int* c_out, int* lg_out) {
+  (void)dirs;
   static const int forced = [] { const char* e = getenv("GAMX_FORCE_LG"); return e ? atoi(e) : 0; }();
   static const int forced_c = [] { const char* e = getenv("GAMX_FORCE_C"); return e ? atoi(e) : 0; }();
   const uint64_t y = 2 * band + 1;
@@ -97,11 +98,10 @@ inline void geometry_for_band(uint64_t band, bool dirs, int* c_out, int* lg_out)
     int c = (int)((y + lg - 1) / lg);
     if (c < 2) c = 2;
     if (forced_c > c && forced_c <= kMaxC) c = forced_c;
-    while (c <= kMaxC && !stripe_supported(c)) c++;
     if (c > kMaxC) continue;
     if (forced && lg != forced && (y + forced - 1) / forced <= (uint64_t)kMaxC) continue;
-    double score = (double)y / (double)(lg * c);
-    if (sub_block_of(c, dirs) < c) score *= 0.88;
+    if (!forced && lg < 32 && c < 5 && y > 64) continue;
+    const double score = (double)y / (double)(lg * c) * (c > 12 ? 0.94 : 1.0);
     if (score > best + 1e-9) { best = score; best_c = c; best_lg = lg; }
   }
   *c_out = best_c; *lg_out = best_lg;
@@ -115,7 +115,6 @@ inline bool geometry_cta(uint64_t band, int* c_out, int* lg_out) {
     const int lg = lgs[n];
     int c = (int)((y + lg - 1) / lg);
     if (c < 2) c = 2;
-    while (c <= kMaxC && !stripe_supported(c)) c++;
     if (c > kMaxC) continue;
     *c_out = c; *lg_out = lg;
     return true;

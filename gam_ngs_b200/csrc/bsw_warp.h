@@ -22,17 +22,26 @@
 // alpha = -2*gap, which makes both gap moves free:
 //      V = max( diag + Cd , up + 1 , left )        Cd = ((S + alpha) << 2) | (2 + is_match)
 // The low two bits of the max are the direction with exactly the reference's priority
-// diag > up > left on ties (.cc:272-307), and tag^1 is the edit op.  Per cell: one PRMT (Cd
-// from an 8-byte per-row table indexed by the a-base), two VIADDMNMX, one LOP3 (strip the
-// tag) on the ALU pipe, plus two IMADs on the FMA pipe that append the tag to the lane's
-// direction word.  The score-only variant (DIRS=false) drops the tag handling: 3 ALU ops/cell.
+// diag > up > left on ties (.cc:272-307), and tag^1 is the edit op.
 //
-// Step variants.  Steps run in unrolled groups of C (register renaming for the sliding a-window):
-//   <CAPTURE=false, MASKED=false>  steady state
-//   <CAPTURE=true,  *>             additionally latches the "last column" cells (pos == end_a,
-//                                  .cc:197-212) of the anti-diagonals that contain them
-//   <*, MASKED=true>               pipeline drain: lanes past their last row keep their registers
-// and a general single step handles the pipeline fill (first row, .cc:112-132).
+// Instruction mix per cell (the ALU pipe is the binding resource):
+//   ALU pipe : VIADDMNMX  m = max(up + U, left)          FMA pipe : IDP.4A  d = diag + Cd
+//              VIMNMX     v = max(d, m)                             IMAD    accV = 4*accV + v
+//              LOP3       h = v & ~3                                IMAD    accH = 4*accH + h
+//              1/4 PRMT   four Cd bytes at once
+// Cd comes from an 8-byte per-row table (indexed by the a-base; N and padding need no branch):
+// the a-bases of the tile sit in shared memory as overlapping 4-nibble windows, so one LDS.U16 is
+// the PRMT selector of four consecutive slots and one PRMT yields their four Cd bytes; IDP.4A with
+// a one-hot multiplier adds byte k to the diagonal.  accV - accH is the lane's direction word (16
+// tags).  Score-only (DIRS=false) keeps VIADDMNMX + VIMNMX + 1/4 PRMT on the ALU pipe.
+//
+// The first row (.cc:112-132: a running maximum that takes its left neighbour without the gap
+// penalty) is computed for all lanes at once by a prefix-max scan before the step loop.  Steps
+// then run in unrolled groups of UF in two variants (a small code footprint matters: the kernel is
+// issue-bound and the instruction cache is shared by warps in different phases):
+//   FAST  steady state: every lane on a row in [1, X-1], nothing to latch
+//   SLOW  pipeline fill / drain, tile and job tails: lanes outside their row range keep their
+//         registers; also latches the "last column" cells (pos == end_a, .cc:197-212)
 #pragma once
 #include "bsw_common.h"
 #include "bsw_traceback.h"
@@ -42,33 +51,15 @@ namespace gamx {
 constexpr int kTileSteps = 128;  // steps per shared-memory sequence tile
 constexpr int kMaxC = 18;        // widest lane stripe: band <= (32*18-1)/2 = 287
 
-// A lane's stripe of C slots is split into C/S sub-blocks of S slots.  The a-bases of a sub-block
-// live in S registers that are renamed (not moved) across an unrolled group of S steps; each
-// sub-block fetches one new base per step from shared memory.  Unrolling by S instead of C keeps
-// the steady-state loop body around 200-350 instructions for every C (an unroll by C grows as
-// C^2 and overflows the instruction cache: measured "no instruction" stalls at C = 9).
-// S = the largest divisor of C whose unrolled group stays within the budget (about 8 instructions
-// per cell with directions, 3.3 without, plus per-step overhead).
-GAMX_HD constexpr int sub_block_of(int c, bool dirs) {
-  int best = 1;
-  for (int sb = 1; sb <= c; sb++) {
-    if (c % sb) continue;
-    const int body = sb * ((dirs ? 80 : 33) * c / 10 + c / sb + 12);
-    if (body <= (dirs ? 400 : 460)) best = sb;
-  }
-  return best;
-}
-// stripes whose sub-block would degenerate to S = 1 (one shared-memory load per cell and step:
-// measured 2-3x slower) are rounded up to the next supported width by the host
-GAMX_HD constexpr bool stripe_supported(int c) {
-  return c >= 2 && c <= 18 && sub_block_of(c, true) >= 2 && sub_block_of(c, false) >= 2;
-}
+GAMX_HD constexpr bool stripe_supported(int c) { return c >= 2 && c <= kMaxC; }
+// steps per unrolled group: keeps the steady-state loop body around 150-350 instructions
+GAMX_HD constexpr int unroll_of(int c) { return c <= 6 ? 4 : (c <= 12 ? 3 : 2); }
 
 template <int C, int LG>
 struct GroupSmem {
-  // a-bases of the tile as PRMT selectors (0x7770 | code), b-rows as 8-byte Cd tables
-  uint64_t btab[kTileSteps + LG];
-  uint16_t asel[kTileSteps + LG * C + 2];
+  uint64_t btab[kTileSteps + LG];            // b-rows of the tile as 8-byte Cd tables
+  uint16_t asel[kTileSteps + LG * C + 8];    // a-bases as 4-nibble windows: codes of positions p..p+3
+  int cap[C * LG];                           // latched "last column" cells, [slot][lane]
 };
 template <int C, int LG>
 struct WarpSmem {
@@ -97,12 +88,12 @@ template <int C, int LG, bool DIRS, class W>
 GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<C, LG>& wsm, uint32_t* dirs,
                         uint64_t group_stride, uint32_t* ops_buf, DevResult* out) {
   static_assert(stripe_supported(C), "lane stripe width");
-  constexpr int S = sub_block_of(C, DIRS), NB = C / S;
-  static_assert(NB * S == C, "stripe = whole sub-blocks");
   // LG <= 32: groups inside one warp (K1).  LG = 64..256: one pair per CTA (K2); the policy W then
   // implements the neighbour exchanges through shared memory and a block barrier.
   static_assert(LG == 8 || LG == 16 || LG == 32 || LG == 64 || LG == 128 || LG == 256, "lanes per pair");
   constexpr int SH = DIRS ? 2 : 0;
+  constexpr int UF = unroll_of(C);
+  constexpr int NQ = (C + 3) / 4;  // 4-slot selector groups
   const int lane = w.lane();
   const int grp = lane / LG, gl = lane % LG;
   const bool live = Jp != nullptr;
@@ -145,172 +136,165 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
   // Direction words are accumulated as the difference of two multiply-add chains (both on the
   // FMA pipe, leaving the ALU pipe to the DP): accV = 4*accV + v, accH = 4*accH + (v & ~3);
   // accV - accH (mod 2^32) = the last 16 tags, oldest in the top bit pair.
-  int H[C], capv[C];
-  uint32_t A[C], accV[C], accH[C];
+  int H[C];
+  uint32_t accV[C], accH[C];
   int U[C];
 #pragma unroll
   for (int k = 0; k < C; k++) {
-    H[k] = 0; capv[k] = 0; A[k] = 0x7775u; accV[k] = 0; accH[k] = 0;
+    H[k] = 0; accV[k] = 0; accH[k] = 0;
     U[k] = (gl == ld && k == kd) ? kBlock : (DIRS ? 1 : 0);
   }
   const int tcap0 = kc - gl * (C - 1);  // step at which slot 0 holds a "last column" cell (slot k: tcap0 - k)
 
-  int t = 0;
-  while (t < T_total) {
-    // ---- stage the sequence tile for steps [t0, t0 + kTileSteps) -------------------------
-    const int t0 = t;
-    w.sync();
-    {
-      const int na = kTileSteps + LG * C - (LG - 1);
-      const int pa0 = p0 + t0;
-      for (int idx = gl; idx < na; idx += LG) {
-        const int pos = pa0 + idx;
-        const uint32_t code = (live && pos >= 0 && pos < la) ? load_code(store, va, pos) : (uint32_t)kCodePad;
-        sm.asel[idx] = (uint16_t)(0x7770u | code);
-      }
-      const int nb = kTileSteps + LG - 1;
-      for (int idx = gl; idx < nb; idx += LG) {
-        const int i = t0 - (LG - 1) + idx;
-        const uint32_t bc = (live && i >= 0 && i < X) ? load_code(store, vb, i) : (uint32_t)kCodePad;
-        uint32_t lo, hi;
-        if (bc < 4u) { lo = (cdX * 0x01010101u) ^ ((cdX ^ cdM) << (8 * bc)); hi = cdZ | (cdP << 8); }
-        else if (bc == (uint32_t)kCodeN) { lo = cdZ * 0x01010101u; hi = cdM | (cdP << 8); }
-        else { lo = cdP * 0x01010101u; hi = cdP | (cdP << 8); }
-        sm.btab[idx] = ((uint64_t)hi << 32) | lo;
-      }
-    }
-    w.sync();
-    const uint16_t* pa = sm.asel + (gl * (C - 1) - t0);    // pa[t + k]: slot k's base at step t
-    const uint64_t* pb = sm.btab + ((LG - 1) - gl - t0);   // pb[t]: table of row t - gl
-    if (t0 == 0) {
-      // bases of step 0 (the last slot of every sub-block is (re)loaded by the step itself)
-#pragma unroll
-      for (int k = 0; k < C; k++) A[k] = pa[k];
-    }
-    const int tile_end = imin(t0 + kTileSteps, T_total);
-
-    // S unrolled steps starting at step t (every lane's row >= 1).
-    // CAPTURE: latch "last column" cells; MASKED: lanes whose row is past X-1 keep their registers.
-#define GAMX_STEP_GROUP(CAPTURE, MASKED)                                                              \
+  // Stages the sequence tile for steps [t0, t0 + kTileSteps): a-bases as 4-nibble windows (every
+  // lane decodes runs of 8 positions + 3 look-ahead), b-rows as 8-byte Cd tables.
+#define GAMX_STAGE_TILE(T0)                                                                           \
   {                                                                                                   \
-    const int dcap = tcap0 - t;                                                                       \
-    _Pragma("unroll") for (int u = 0; u < S; u++) {                                                   \
-      const int tt = t + u;                                                                           \
-      _Pragma("unroll") for (int sb = 0; sb < NB; sb++)                                               \
-          A[sb * S + (u + S - 1) % S] = pa[tt + sb * S + S - 1];                                      \
-      const uint64_t tb = pb[tt];                                                                     \
-      const uint32_t tlo = (uint32_t)tb, thi = (uint32_t)(tb >> 32);                                  \
-      int left = w.shfl_up(H[C - 1], 1, LG);                                                          \
-      if (gl == 0) left = kNegInf;                                                                    \
-      const bool act = !(MASKED) || (tt - gl < X);                                                    \
-      int right = 0;                                                                                  \
-      _Pragma("unroll") for (int k = 0; k < C; k++) {                                                 \
-        const int up = (k == C - 1) ? right : H[(k + 1) % C];                                         \
-        const int cd = (int)prmt(tlo, thi, A[(k / S) * S + (u + k % S) % S]);                         \
-        const int m = viaddmax(up, U[k], left);                                                       \
-        const int v = viaddmax(H[k], cd, m);                                                          \
-        int hc = v;                                                                                   \
-        if (DIRS) {                                                                                   \
-          hc = v & ~3;                                                                                \
-          accV[k] = accV[k] * 4u + (uint32_t)v;                                                       \
-          accH[k] = accH[k] * 4u + (uint32_t)hc;                                                      \
-        }                                                                                             \
-        if (MASKED) { if (act) H[k] = hc; } else H[k] = hc;                                           \
-        if (CAPTURE) { if (dcap == u + k) capv[k] = H[k]; }                                           \
-        left = H[k];                                                                                  \
-        if (k == 0) right = w.shfl_down(H[0], 1, LG);                                                 \
-      }                                                                                               \
-      if (DIRS && (tt & 15) == 15) {                                                                  \
-        _Pragma("unroll") for (int k = 0; k < C; k++) fp[k * LG] = accV[k] - accH[k];                  \
-        fp += C * LG;                                                                                 \
+    w.sync();                                                                                         \
+    const int na = kTileSteps + LG * C - (LG - 1) + 3;                                                \
+    const int pa0 = p0 + (T0);                                                                        \
+    for (int c0 = gl * 8; c0 < na; c0 += LG * 8) {                                                    \
+      uint32_t win = 0;                                                                               \
+      _Pragma("unroll") for (int q = 0; q < 11; q++) {                                                \
+        const int pos = pa0 + c0 + q;                                                                 \
+        const uint32_t code = (live && pos >= 0 && pos < la) ? load_code(store, va, pos) : (uint32_t)kCodePad; \
+        win = (win >> 4) | (code << 12);                                                              \
+        if (q >= 3) sm.asel[c0 + q - 3] = (uint16_t)win;                                              \
       }                                                                                               \
     }                                                                                                 \
-    t += S;                                                                                           \
+    const int nb = kTileSteps + LG - 1;                                                               \
+    for (int idx = gl; idx < nb; idx += LG) {                                                         \
+      const int i = (T0) - (LG - 1) + idx;                                                            \
+      const uint32_t bc = (live && i >= 0 && i < X) ? load_code(store, vb, i) : (uint32_t)kCodePad;   \
+      uint32_t lo, hi;                                                                                \
+      if (bc < 4u) { lo = (cdX * 0x01010101u) ^ ((cdX ^ cdM) << (8 * bc)); hi = cdZ | (cdP << 8); }   \
+      else if (bc == (uint32_t)kCodeN) { lo = cdZ * 0x01010101u; hi = cdM | (cdP << 8); }             \
+      else { lo = cdP * 0x01010101u; hi = cdP | (cdP << 8); }                                         \
+      sm.btab[idx] = ((uint64_t)hi << 32) | lo;                                                       \
+    }                                                                                                 \
+    w.sync();                                                                                         \
   }
 
-    while (t < tile_end) {
-      // the warp's final step always takes the general path (it flushes the partial direction words)
-      const bool grouped = (t >= LG) && (t + S <= tile_end) && (t + S - 1 <= T_total - 2);
-      if (grouped) {
-        const bool masked = t + S - 1 > x_min - 1;
-        const bool capture = !(t + S - 1 < win_lo || t > win_hi);
-        if (!masked && !capture) GAMX_STEP_GROUP(false, false)
-        else if (!masked) GAMX_STEP_GROUP(true, false)
-        else GAMX_STEP_GROUP(true, true)
-        continue;
-      }
-
-      // ---- one general step: pipeline fill (first row), tile/tail remainders ---------------
-      {
-        const int i = t - gl;
-        const bool act = live && (i >= 0) && (i < X);
+  // ---- first row, banded_smith_waterman.cc:112-132 --------------------------------------------------
+  // h(0,j) = (pos > 0 && j > 0) ? max(S, h(0,j-1)) : S for filled cells (gap < every substitution
+  // score, so the gap terms of .cc:122/.cc:130 never win and force_start changes nothing here):
+  // a prefix maximum of S that restarts at the cell with pos == 0.  Never-written cells are 0.
+  GAMX_STAGE_TILE(0)
+  {
+    const uint16_t* pa = sm.asel + gl * (C - 1);
+    const uint64_t tb = sm.btab[LG - 1];  // row 0
+    const uint32_t tlo = (uint32_t)tb, thi = (uint32_t)(tb >> 32);
+    const int kNone = -(1 << 28);
+    int sc[C];
+    int run = kNone;  // running maximum inside the lane
 #pragma unroll
-        for (int sb = 0; sb < NB; sb++) A[sb * S + S - 1] = pa[t + sb * S + S - 1];
-        const uint64_t tb = pb[t];
-        const uint32_t tlo = (uint32_t)tb, thi = (uint32_t)(tb >> 32);
-        int left = w.shfl_up(H[C - 1], 1, LG);
-        if (gl == 0) left = kNegInf;
-        const bool row0 = act && i == 0;
-        if (row0) {
-          // first row, banded_smith_waterman.cc:112-132 (gap < every substitution score, so the
-          // gap terms of .cc:122/.cc:130 never win and force_start changes nothing here)
-          int lt = (left >> SH) - beta * (j0 - 1);  // true score of (0, j0-1)
-#pragma unroll
-          for (int k = 0; k < C; k++) {
-            const int j = j0 + k, pos = p0 + j;
-            int v;
-            if (pos < 0 || pos >= la || j >= Y) {
-              v = (beta * j) << SH;  // never-written cell: 0
-            } else {
-              const int cd = (int)prmt(tlo, thi, A[k]);
-              const int s = (cd >> SH) - alpha;
-              const int h = (pos > 0 && j > 0) ? imax(s, lt) : s;
-              v = ((h + beta * j) << SH) | ((DIRS && h == s) ? (cd & 3) : 0);
-              lt = h;
-            }
-            if (DIRS) { accV[k] = accV[k] * 4u + (uint32_t)v; accH[k] = accH[k] * 4u + (uint32_t)(v & ~3); H[k] = v & ~3; }
-            else H[k] = v;
-          }
-        } else {
-          const int cd = (int)prmt(tlo, thi, A[0]);
-          const int m = viaddmax(H[1 % C], U[0], left);
-          const int v = viaddmax(H[0], cd, m);
-          const int hc = DIRS ? (v & ~3) : v;
-          if (DIRS) { accV[0] = accV[0] * 4u + (uint32_t)v; accH[0] = accH[0] * 4u + (uint32_t)hc; }
-          if (act) H[0] = hc;
-        }
-        const int right = w.shfl_down(H[0], 1, LG);
-        if (!row0) {
-#pragma unroll
-          for (int k = 1; k < C; k++) {
-            const int up = (k == C - 1) ? right : H[(k + 1) % C];
-            const int cd = (int)prmt(tlo, thi, A[k]);
-            const int m = viaddmax(up, U[k], H[k - 1]);
-            const int v = viaddmax(H[k], cd, m);
-            const int hc = DIRS ? (v & ~3) : v;
-            if (DIRS) { accV[k] = accV[k] * 4u + (uint32_t)v; accH[k] = accH[k] * 4u + (uint32_t)hc; }
-            if (act) H[k] = hc;
-          }
-        }
-        // latch "last column" cells, .cc:197-212: slot k at step tcap0 - k
-        const int dc = tcap0 - t;
-#pragma unroll
-        for (int k = 0; k < C; k++)
-          if (dc == k) capv[k] = H[k];
-#pragma unroll
-        for (int k = 0; k < C; k++)
-          if (k % S != S - 1) A[k] = A[k + 1];
-        if (DIRS && ((t & 15) == 15 || t == T_total - 1)) {
-          const int sh = 2 * (15 - (t & 15));
-#pragma unroll
-          for (int k = 0; k < C; k++) fp[k * LG] = (accV[k] - accH[k]) << sh;
-          fp += C * LG;
-        }
-        t++;
-      }
+    for (int k = 0; k < C; k++) {
+      const int j = j0 + k, pos = p0 + j;
+      const uint32_t cd4 = prmt(tlo, thi, pa[gl + 4 * (k / 4)]);
+      const int cd = (int)((cd4 >> (8 * (k % 4))) & 0xffu);
+      const bool valid = live && pos >= 0 && pos < la && j < Y;
+      sc[k] = valid ? cd : -1;                        // Cd byte of the cell, -1: never written
+      const int s = (cd >> SH) - alpha;
+      if (valid) run = (pos > 0 && j > 0) ? imax(run, s) : s;
+      H[k] = run;                                      // local prefix maximum (provisional)
     }
-#undef GAMX_STEP_GROUP
+    // exclusive prefix maximum of the lanes' totals; a lane holding the pos == 0 cell restarts it
+    const bool restarts = live && (-p0 >= j0) && (-p0 < j0 + C);  // the cell with pos == 0 is mine
+    int incl = run;       // inclusive scan value
+    int cut = restarts;   // 1: nothing from lower lanes may pass through this lane
+#pragma unroll
+    for (int d = 1; d < LG; d <<= 1) {
+      const int o = w.shfl_up(incl, d, LG), oc = w.shfl_up(cut, d, LG);
+      if (gl >= d) { if (!cut) incl = imax(incl, o); cut |= oc; }
+    }
+    int in = w.shfl_up(incl, 1, LG);
+    if (gl == 0) in = kNone;
+    bool open = true;  // the incoming maximum applies until the lane's own restart cell
+#pragma unroll
+    for (int k = 0; k < C; k++) {
+      const int j = j0 + k, pos = p0 + j;
+      int v;
+      if (sc[k] < 0) {
+        v = (beta * j) << SH;  // never written: 0
+      } else {
+        if (!(pos > 0 && j > 0)) open = false;
+        const int s = (sc[k] >> SH) - alpha;
+        const int h = open ? imax(H[k], in) : H[k];
+        v = ((h + beta * j) << SH) | ((DIRS && h == s) ? (sc[k] & 3) : 0);
+      }
+      if (DIRS) { accV[k] = (uint32_t)(v & 3); accH[k] = 0; }
+      H[k] = DIRS ? (v & ~3) : v;
+      if (tcap0 - k == gl) sm.cap[k * LG + gl] = H[k];  // "last column" cell in row 0
+    }
+    if (DIRS && T_total == 1) {  // a single row on a single lane: no step will flush its directions
+#pragma unroll
+      for (int k = 0; k < C; k++) fp[k * LG] = accV[k] << 30;
+    }
   }
+
+  // UF unrolled steps starting at step t.  SLOW: lanes whose row is outside [1, X-1] keep their
+  // registers (direction words keep shifting once a lane has started), "last column" cells are
+  // latched, and steps at or beyond `stop` are skipped.
+#define GAMX_STEP_GROUP(SLOW)                                                                         \
+  {                                                                                                   \
+    const int dcap = tcap0 - t;                                                                       \
+    _Pragma("unroll") for (int u = 0; u < UF; u++) {                                                  \
+      const int tt = t + u;                                                                           \
+      if (!(SLOW) || tt < stop) {                                                                     \
+        const uint64_t tb = pb[tt];                                                                   \
+        const uint32_t tlo = (uint32_t)tb, thi = (uint32_t)(tb >> 32);                                \
+        uint32_t cd4[NQ];                                                                             \
+        _Pragma("unroll") for (int q = 0; q < NQ; q++) cd4[q] = prmt(tlo, thi, pa[tt + 4 * q]);       \
+        int left = w.shfl_up(H[C - 1], 1, LG);                                                        \
+        if (gl == 0) left = kNegInf;                                                                  \
+        const bool started = !(SLOW) || (tt - gl >= 1);                                               \
+        const bool act = !(SLOW) || (started && tt - gl < X);                                         \
+        int right = 0;                                                                                \
+        _Pragma("unroll") for (int k = 0; k < C; k++) {                                               \
+          const int up = (k == C - 1) ? right : H[(k + 1) % C];                                       \
+          const int d = add_byte(cd4[k / 4], k % 4, H[k]);                                            \
+          const int m = viaddmax(up, U[k], left);                                                     \
+          const int v = imax(d, m);                                                                   \
+          int hc = v;                                                                                 \
+          if (DIRS) {                                                                                 \
+            hc = v & ~3;                                                                              \
+            if (started) {                                                                            \
+              accV[k] = accV[k] * 4u + (uint32_t)v;                                                   \
+              accH[k] = accH[k] * 4u + (uint32_t)hc;                                                  \
+            }                                                                                         \
+          }                                                                                           \
+          if (act) H[k] = hc;                                                                         \
+          if (SLOW) { if (dcap == u + k) sm.cap[k * LG + gl] = H[k]; }                                \
+          left = H[k];                                                                                \
+          if (k == 0) right = w.shfl_down(H[0], 1, LG);                                               \
+        }                                                                                             \
+        if (DIRS && ((tt & 15) == 15 || ((SLOW) && tt == T_total - 1))) {                             \
+          const int sh = (SLOW) ? 2 * (15 - (tt & 15)) : 0;                                           \
+          _Pragma("unroll") for (int k = 0; k < C; k++) fp[k * LG] = (accV[k] - accH[k]) << sh;        \
+          fp += C * LG;                                                                               \
+        }                                                                                             \
+      }                                                                                               \
+    }                                                                                                 \
+    t += UF;                                                                                          \
+  }
+
+  int t = 1;  // row 0 is done; lane gl starts its row 1 at step gl + 1
+  int t0 = 0;
+  while (t < T_total) {
+    if (t >= t0 + kTileSteps) { t0 += kTileSteps; GAMX_STAGE_TILE(t0) }
+    const uint16_t* pa = sm.asel + (gl * (C - 1) - t0);    // pa[t + k]: window starting at slot k's base at step t
+    const uint64_t* pb = sm.btab + ((LG - 1) - gl - t0);   // pb[t]: table of row t - gl
+    const int stop = imin(t0 + kTileSteps, T_total);       // first step this tile does not cover
+    while (t < stop) {
+      const bool fast = (t >= LG) && (t + UF <= stop) && (t + UF - 1 <= x_min - 1) && (t + UF - 1 <= T_total - 2) &&
+                        (t + UF - 1 < win_lo || t > win_hi);
+      if (fast) GAMX_STEP_GROUP(false)
+      else GAMX_STEP_GROUP(true)
+    }
+    if (t > stop) t = stop;  // a SLOW group cut short by the tile end: the skipped steps belong to the next tile
+  }
+#undef GAMX_STEP_GROUP
+#undef GAMX_STAGE_TILE
 
   // ---- end-cell selection, .cc:174-212: last row (columns ascending) before last column ----
   EndBest best;
@@ -329,7 +313,7 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
       for (int k = 0; k < C; k++) {
         const int j = j0 + k, i = tcap0 - k - gl;  // the row this slot was on when it met pos == end_a
         if (i >= 0 && i < X && j <= 2 * B && i >= Jp->col_imin) {
-          const int val = Jp->col_zero ? 0 : ((capv[k] >> SH) - alpha * i - beta * j);
+          const int val = Jp->col_zero ? 0 : ((sm.cap[k * LG + gl] >> SH) - alpha * i - beta * j);
           best.consider(val, Y + i);
         }
       }

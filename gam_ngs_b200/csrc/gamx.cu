@@ -289,6 +289,15 @@ __global__ void __launch_bounds__(256) intpeak_kernel(int* out, int iters, int s
         a2 = (int)__byte_perm((unsigned)a2, (unsigned)b, (unsigned)c); a3 = (int)__byte_perm((unsigned)a3, (unsigned)b, (unsigned)c);
         a4 = (int)__byte_perm((unsigned)a4, (unsigned)b, (unsigned)c); a5 = (int)__byte_perm((unsigned)a5, (unsigned)b, (unsigned)c);
         a6 = (int)__byte_perm((unsigned)a6, (unsigned)b, (unsigned)c); a7 = (int)__byte_perm((unsigned)a7, (unsigned)b, (unsigned)c);
+      } else if (WHICH == 6) {
+        a0 = (int)__dp4a((unsigned)b, (unsigned)c, (unsigned)a0); a1 = (int)__dp4a((unsigned)b, (unsigned)c, (unsigned)a1);
+        a2 = (int)__dp4a((unsigned)b, (unsigned)c, (unsigned)a2); a3 = (int)__dp4a((unsigned)b, (unsigned)c, (unsigned)a3);
+        a4 = (int)__dp4a((unsigned)b, (unsigned)c, (unsigned)a4); a5 = (int)__dp4a((unsigned)b, (unsigned)c, (unsigned)a5);
+        a6 = (int)__dp4a((unsigned)b, (unsigned)c, (unsigned)a6); a7 = (int)__dp4a((unsigned)b, (unsigned)c, (unsigned)a7);
+      } else if (WHICH == 7) {  // mixed: 1 dp4a + 2 imad + 3 alu-pipe ops per "cell", the candidate loop mix
+        a0 = (int)__dp4a((unsigned)b, (unsigned)c, (unsigned)a0); a1 = a1 * b + a0; a2 = a2 * b + a1;
+        a3 = __viaddmax_s32(a3, b, a0); a4 = max(a4, a3); a5 = (a4 & b) ^ a5;
+        a6 = (int)__dp4a((unsigned)b, (unsigned)c, (unsigned)a6); a7 = a7 * b + a6;
       } else {
         a0 = a0 * b + c; a1 = a1 * b + c; a2 = a2 * b + c; a3 = a3 * b + c;
         a4 = a4 * b + c; a5 = a5 * b + c; a6 = a6 * b + c; a7 = a7 * b + c;
@@ -543,8 +552,8 @@ int occupancy_k1_t(int* blocks_per_sm) {
   return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k1_kernel<C, LG, DIRS>, kWarpsPerBlock * 32, 0);
 }
 
-#define GAMX_FOR_EACH_C(M, LG) M(2, LG) M(3, LG) M(4, LG) M(5, LG) M(6, LG) M(8, LG) M(9, LG) M(10, LG) \
-  M(12, LG) M(14, LG) M(16, LG) M(18, LG)
+#define GAMX_FOR_EACH_C(M, LG) M(2, LG) M(3, LG) M(4, LG) M(5, LG) M(6, LG) M(7, LG) M(8, LG) M(9, LG) M(10, LG) \
+  M(11, LG) M(12, LG) M(13, LG) M(14, LG) M(15, LG) M(16, LG) M(17, LG) M(18, LG)
 
 template <int LG>
 int k1_blocks_per_sm_lg(int c, bool dirs) {
@@ -647,7 +656,7 @@ template <int C, int LG, bool DIRS>
 int occupancy_k2_t(int* blocks_per_sm) {
   return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k2_kernel<C, LG, DIRS>, LG, 0);
 }
-#define GAMX_FOR_EACH_WIDE_C(M, LG) M(10, LG) M(12, LG) M(14, LG) M(16, LG) M(18, LG)
+#define GAMX_FOR_EACH_WIDE_C(M, LG) M(10, LG) M(11, LG) M(12, LG) M(13, LG) M(14, LG) M(15, LG) M(16, LG) M(17, LG) M(18, LG)
 
 int k2_blocks_per_sm(int c, int lg, bool dirs) {
   int b = 0;
@@ -1556,6 +1565,8 @@ double gamx_measure_int_peak(gamx_ctx* ctx, int dev_index, int which) {
       case 2: intpeak_kernel<2><<<blocks, threads, 0, d.stream>>>((int*)d.peak.p, iters, rep + 1); break;
       case 3: intpeak_kernel<3><<<blocks, threads, 0, d.stream>>>((int*)d.peak.p, iters, rep + 1); break;
       case 4: intpeak_kernel<4><<<blocks, threads, 0, d.stream>>>((int*)d.peak.p, iters, rep + 1); break;
+      case 6: intpeak_kernel<6><<<blocks, threads, 0, d.stream>>>((int*)d.peak.p, iters, rep + 1); break;
+      case 7: intpeak_kernel<7><<<blocks, threads, 0, d.stream>>>((int*)d.peak.p, iters, rep + 1); break;
       default: intpeak_kernel<5><<<blocks, threads, 0, d.stream>>>((int*)d.peak.p, iters, rep + 1); break;
     }
     cudaEventRecord(d.ev1, d.stream);

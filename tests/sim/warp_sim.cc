@@ -133,7 +133,8 @@ template <int LG>
 void run_warp_lg(WarpArgs& a, bool desc) {
   switch (a.c) {
 #define CASE(N) case N: dispatch<N, LG>(a, desc); break;
-    CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(8) CASE(9) CASE(10) CASE(12) CASE(14) CASE(16) CASE(18)
+    CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
+    CASE(14) CASE(15) CASE(16) CASE(17) CASE(18)
 #undef CASE
     default: break;
   }
