@@ -284,7 +284,7 @@ def main():
     if not args.no_e2e:
         def e2e_step():
             ctx.clear_contigs()
-            ctx.add_contigs(host.data_ptr(), lengths)   # H2D of the raw sequences + pack kernel
+            ctx.add_contigs(host.data_ptr(), lengths, async_upload=True)   # H2D of the raw sequences + pack kernel (async)
             return ctx.align_batch(jobs)                # H2D descriptors, kernels, D2H results
         for _ in range(2):
             e2e_step()

@@ -85,7 +85,7 @@ assert RESULT_DTYPE.itemsize == C.sizeof(GamxResult), (RESULT_DTYPE.itemsize, C.
 
 EXPORTS = [
     "gamx_abi_version", "gamx_create", "gamx_destroy", "gamx_device_count", "gamx_last_error",
-    "gamx_add_contig", "gamx_add_contig_ascii", "gamx_add_contigs", "gamx_contig_length", "gamx_clear_contigs",
+    "gamx_add_contig", "gamx_add_contig_ascii", "gamx_add_contigs", "gamx_add_contigs_async", "gamx_contig_length", "gamx_clear_contigs",
     "gamx_ops_capacity", "gamx_align_batch", "gamx_unpack_ops", "gamx_cigar_rle",
     "gamx_plan_create", "gamx_plan_run", "gamx_plan_sync", "gamx_plan_fetch", "gamx_plan_last_ms",
     "gamx_plan_cells", "gamx_plan_kernel_launches", "gamx_plan_destroy", "gamx_measure_int_peak",
@@ -126,6 +126,8 @@ def load_library(build_if_missing: bool = True):
     L.gamx_add_contig_ascii.restype = C.c_int64
     L.gamx_add_contigs.argtypes = [vp, vp, vp, u64]
     L.gamx_add_contigs.restype = C.c_int64
+    L.gamx_add_contigs_async.argtypes = [vp, vp, vp, u64]
+    L.gamx_add_contigs_async.restype = C.c_int64
     L.gamx_contig_length.argtypes = [vp, C.c_uint32]
     L.gamx_contig_length.restype = u64
     L.gamx_clear_contigs.argtypes = [vp]
@@ -265,12 +267,14 @@ class Context:
             self._check(int(cid))
         return int(cid)
 
-    def add_contigs(self, codes, lengths) -> int:
+    def add_contigs(self, codes, lengths, async_upload: bool = False) -> int:
         """Bulk upload: `codes` = concatenated base codes (numpy uint8 array or a raw pointer to
-        pinned host memory), `lengths` = bases per contig.  Returns the first contig id."""
+        pinned host memory), `lengths` = bases per contig.  Returns the first contig id.
+        async_upload=True (pinned pointer only) lets the copy overlap the planning of the next batch."""
         lengths = np.ascontiguousarray(lengths, dtype=np.uint64)
         ptr = codes if isinstance(codes, int) else np.ascontiguousarray(codes, dtype=np.uint8).ctypes.data
-        first = self.lib.gamx_add_contigs(self._h, ptr, lengths.ctypes.data, len(lengths))
+        fn = self.lib.gamx_add_contigs_async if (async_upload and isinstance(codes, int)) else self.lib.gamx_add_contigs
+        first = fn(self._h, ptr, lengths.ctypes.data, len(lengths))
         if first < 0:
             self._check(int(first))
         return int(first)
@@ -287,7 +291,7 @@ class Context:
         jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
         n = len(jobs)
         cap = self.ops_capacity(jobs) if (jobs["mode"] == MODE_FULL).any() else 0
-        results = np.zeros(n, dtype=RESULT_DTYPE)
+        results = np.empty(n, dtype=RESULT_DTYPE)  # every record is written by the library
         ops = np.zeros((cap + 3) // 4 + 8, dtype=np.uint8)
         self._check(self.lib.gamx_align_batch(self._h, jobs.ctypes.data, n, results.ctypes.data,
                                               ops.ctypes.data, cap))

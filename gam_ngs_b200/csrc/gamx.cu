@@ -435,7 +435,7 @@ int h2d_raw(gamx_ctx* ctx, Device& d, void* dst, const uint8_t* src, size_t byte
 
 // Stages contigs [first, first+n) - raw codes concatenated in `raw`, lengths in the index - to
 // every device: pinned async H2D of the raw bytes, then K0 packs them into the store on the device.
-int store_upload(gamx_ctx* ctx, const uint8_t* raw, size_t first, size_t n) {
+int store_upload(gamx_ctx* ctx, const uint8_t* raw, size_t first, size_t n, bool wait = true) {
   if (n == 0) return GAMX_OK;
   const StoreIndex& si = ctx->store;
   const uint64_t group0 = si.start[first] / 32;
@@ -453,6 +453,7 @@ int store_upload(gamx_ctx* ctx, const uint8_t* raw, size_t first, size_t n) {
     if (int rc = ensure_pin(ctx, d.h_meta, meta_bytes)) return rc;
     if (int rc = ensure_dev(ctx, d.meta, meta_bytes)) return rc;
     if (int rc = ensure_dev(ctx, d.raw, raw_bytes + 64)) return rc;
+    CU(cudaStreamSynchronize(d.stream));  // a previous asynchronous upload may still read h_meta
     uint64_t* roff = (uint64_t*)d.h_meta.p;
     uint64_t* len = roff + n;
     uint64_t* sg = len + n;
@@ -472,10 +473,11 @@ int store_upload(gamx_ctx* ctx, const uint8_t* raw, size_t first, size_t n) {
     d.store_groups = groups_end;
   }
   // the caller's raw buffer (and our pinned metadata) may be reused once the copies are done
-  for (Device& d : ctx->devs) {
-    CU(cudaSetDevice(d.id));
-    CU(cudaStreamSynchronize(d.stream));
-  }
+  if (wait)
+    for (Device& d : ctx->devs) {
+      CU(cudaSetDevice(d.id));
+      CU(cudaStreamSynchronize(d.stream));
+    }
   return GAMX_OK;
 }
 
@@ -773,7 +775,16 @@ int64_t gamx_add_contig_ascii(gamx_ctx* ctx, const char* seq, uint64_t len) {
   return gamx_add_contig(ctx, codes.data(), len);
 }
 
+static int64_t add_contigs_impl(gamx_ctx* ctx, const uint8_t* codes, const uint64_t* lengths, uint64_t n, bool wait);
+
 int64_t gamx_add_contigs(gamx_ctx* ctx, const uint8_t* codes, const uint64_t* lengths, uint64_t n) {
+  return add_contigs_impl(ctx, codes, lengths, n, true);
+}
+int64_t gamx_add_contigs_async(gamx_ctx* ctx, const uint8_t* codes, const uint64_t* lengths, uint64_t n) {
+  return add_contigs_impl(ctx, codes, lengths, n, false);
+}
+
+static int64_t add_contigs_impl(gamx_ctx* ctx, const uint8_t* codes, const uint64_t* lengths, uint64_t n, bool wait) {
   if (!ctx || !lengths || n == 0) return GAMX_ERR_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
   static const bool timing = getenv("GAMX_TIMING") != nullptr;
@@ -788,7 +799,7 @@ int64_t gamx_add_contigs(gamx_ctx* ctx, const uint8_t* codes, const uint64_t* le
   }
   ctx->pending_first = ctx->store.start.size();
   const auto t1 = std::chrono::steady_clock::now();
-  if (int rc = store_upload(ctx, codes, first, n)) return rc;
+  if (int rc = store_upload(ctx, codes, first, n, wait)) return rc;
   if (timing)
     fprintf(stderr, "[gamx] add_contigs n=%llu: index %.1f ms, upload+pack %.1f ms\n", (unsigned long long)n,
             std::chrono::duration<double, std::milli>(t1 - t0).count(),
@@ -885,12 +896,19 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
   // 2. cost-balanced sharding (longest-processing-time greedy on DP cells); no collective is needed,
   //    every job is independent.  The descending order is also the launch order, so
   //    the persistent warps of a kernel pick up the expensive jobs first.
-  sort_by_cost_desc(order, preps);
+  {
+    // near-uniform batches (max cost within 25 % of min) keep the caller's order: the descending order
+    // only matters for the tail of a launch, and sequential access to the job records is much faster
+    uint64_t cmin = ~0ull, cmax = 0;
+    for (uint32_t i : order) { cmin = std::min(cmin, preps[i].cells); cmax = std::max(cmax, preps[i].cells); }
+    if (!order.empty() && cmax > cmin + cmin / 4) sort_by_cost_desc(order, preps);
+  }
   std::vector<std::vector<uint32_t>> per_dev(nd);
   if (nd == 1) {
     per_dev[0].swap(order);
     for (uint32_t i : per_dev[0]) pl->job_dev[i] = 0;
   } else {
+    // (for an unsorted near-uniform batch LPT degenerates to round-robin, which is balanced too)
     lpt_assign(order, nd, [&](uint32_t i) { return preps[i].cells; }, pl->job_dev.data());
     for (uint32_t i : order) per_dev[pl->job_dev[i]].push_back(i);
   }

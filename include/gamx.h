@@ -150,6 +150,11 @@ GAMX_API int64_t gamx_add_contig_ascii(gamx_ctx* ctx, const char* seq, uint64_t 
  * staging otherwise) and packed there by a kernel; the call returns when `codes` may be reused.
  * Returns the id of the first contig (ids are consecutive) or a negative error. */
 GAMX_API int64_t gamx_add_contigs(gamx_ctx* ctx, const uint8_t* codes, const uint64_t* lengths, uint64_t n);
+/* Same, but only enqueues the copies and the pack kernel on the devices' streams and returns: the
+ * upload then overlaps the host-side planning of the next gamx_align_batch, which is stream-ordered
+ * behind it.  `codes` must be PINNED host memory and must stay valid and unchanged until that batch
+ * (or any other synchronising call of this context) has returned. */
+GAMX_API int64_t gamx_add_contigs_async(gamx_ctx* ctx, const uint8_t* codes, const uint64_t* lengths, uint64_t n);
 GAMX_API uint64_t gamx_contig_length(const gamx_ctx* ctx, uint32_t id);
 GAMX_API int gamx_clear_contigs(gamx_ctx* ctx);
 

@@ -19,7 +19,7 @@ jobs["end_a"] = al - 1; jobs["end_b"] = bl - 1; jobs["band"] = 64; jobs["mode"] 
 ctx = g.Context(devices=[0])
 for it in range(3):
     t0 = time.perf_counter(); ctx.clear_contigs()
-    t1 = time.perf_counter(); ctx.add_contigs(host.data_ptr(), lengths)
+    t1 = time.perf_counter(); ctx.add_contigs(host.data_ptr(), lengths, async_upload=True)
     t2 = time.perf_counter(); res, ops = ctx.align_batch(jobs)
     t3 = time.perf_counter()
     print(f"iter {it}: clear {1e3*(t1-t0):.1f} add_contigs {1e3*(t2-t1):.1f} align_batch {1e3*(t3-t2):.1f} total {1e3*(t3-t0):.1f} ms", flush=True)
