@@ -52,8 +52,14 @@ struct DevWarp {
   __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
 
+// Resident blocks per SM the compiler must allow for (register budget): more resident warps hide the
+// shuffle / dependent-chain latencies and the leader-only traceback.  Measured +4..16 % across bands
+// against an unconstrained build in the same run (profiles/r1c_geometry_probe.txt).
+#ifndef GAMX_K1_MIN_BLOCKS
+#define GAMX_K1_MIN_BLOCKS(C) ((C) <= 6 ? 8 : ((C) <= 10 ? 5 : ((C) <= 14 ? 4 : 3)))
+#endif
 template <int C, int LG, bool DIRS>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, GAMX_K1_MIN_BLOCKS(C))
 k1_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counter, SeqStore store,
           uint32_t* __restrict__ dirs, uint64_t group_stride, uint32_t* __restrict__ ops,
           DevResult* __restrict__ results) {
