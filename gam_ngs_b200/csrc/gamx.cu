@@ -601,9 +601,16 @@ int launch_k1(gamx_ctx* ctx, Device& d, const Group& g, const DevJob* jobs, int*
 // splits [0, n) over the host's cores; fn(begin, end) must be thread-safe
 template <class F>
 void parallel_for(uint64_t n, F fn) {
-  unsigned nt = std::thread::hardware_concurrency();
-  if (nt == 0) nt = 4;
-  if (nt > 32) nt = 32;
+  // host threads for batch preparation: all cores, divided by the number of ranks sharing the node
+  // when launched one process per GPU (torchrun sets LOCAL_WORLD_SIZE); GAMX_HOST_THREADS overrides
+  static const unsigned nt_cfg = [] {
+    unsigned n = std::thread::hardware_concurrency();
+    if (n == 0) n = 4;
+    if (const char* e = getenv("GAMX_HOST_THREADS")) { const int v = atoi(e); if (v > 0) return (unsigned)v; }
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) { const int v = atoi(e); if (v > 1) n = std::max(1u, n / (unsigned)v); }
+    return std::min(n, 32u);
+  }();
+  unsigned nt = nt_cfg;
   if (n < 20000 || nt == 1) { fn((uint64_t)0, n); return; }
   std::vector<std::thread> th;
   const uint64_t chunk = (n + nt - 1) / nt;
