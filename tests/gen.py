@@ -98,19 +98,25 @@ def fuzz_case(rng, max_len=80, max_band=40):
                 force_start=fs, force_end=fe)
 
 
-def bulk_pairs(rng, n, length, div=0.02, indel_share=0.5, len_lo=None, len_hi=None, chunk=32768):
+def bulk_pairs(rng, n, length, div=0.02, indel_share=0.5, len_lo=None, len_hi=None, chunk=32768, lengths=None):
     """Vectorised generator for large batches: n pairs (a_k, b_k), b_k = mutate(a_k).
     Lengths: fixed `length`, or uniform in [len_lo, len_hi].  Returns
     (a_codes, a_lens, b_codes, b_lens): concatenated uint8 codes and per-pair lengths."""
     a_parts, b_parts, a_lens_all, b_lens_all = [], [], [], []
-    if len_lo is not None:
+    if lengths is not None:
+        lengths = np.asarray(lengths, dtype=np.int64)
+        n = len(lengths)
+        per_chunk = max(1, int(chunk * 1000 // max(1, int(lengths.mean()))))
+    elif len_lo is not None:
         per_chunk = max(1, int(chunk * 1000 // max(1, (len_lo + len_hi) // 2)))
     else:
         per_chunk = max(1, int(chunk * 1000 // max(1, length)))
     done = 0
     while done < n:
         m = min(per_chunk, n - done)
-        if len_lo is None:
+        if lengths is not None:
+            la = lengths[done:done + m]
+        elif len_lo is None:
             la = np.full(m, length, dtype=np.int64)
         else:
             la = rng.integers(len_lo, len_hi + 1, size=m, dtype=np.int64)
