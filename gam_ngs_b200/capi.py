@@ -86,7 +86,7 @@ assert RESULT_DTYPE.itemsize == C.sizeof(GamxResult), (RESULT_DTYPE.itemsize, C.
 EXPORTS = [
     "gamx_abi_version", "gamx_create", "gamx_destroy", "gamx_device_count", "gamx_last_error",
     "gamx_add_contig", "gamx_add_contig_ascii", "gamx_add_contigs", "gamx_add_contigs_async", "gamx_contig_length", "gamx_clear_contigs",
-    "gamx_ops_capacity", "gamx_align_batch", "gamx_unpack_ops", "gamx_cigar_rle",
+    "gamx_ops_capacity", "gamx_set_pipeline_chunk", "gamx_align_batch", "gamx_unpack_ops", "gamx_cigar_rle",
     "gamx_plan_create", "gamx_plan_run", "gamx_plan_sync", "gamx_plan_fetch", "gamx_plan_last_ms",
     "gamx_plan_cells", "gamx_plan_kernel_launches", "gamx_plan_destroy", "gamx_measure_int_peak",
     "gamx_shard_by_cost", "gamx_find_hits_batch", "gamx_merge_align",
@@ -134,6 +134,8 @@ def load_library(build_if_missing: bool = True):
     L.gamx_clear_contigs.restype = C.c_int
     L.gamx_ops_capacity.argtypes = [vp, vp, u64]
     L.gamx_ops_capacity.restype = u64
+    L.gamx_set_pipeline_chunk.argtypes = [vp, u64]
+    L.gamx_set_pipeline_chunk.restype = C.c_int
     L.gamx_align_batch.argtypes = [vp, vp, u64, vp, vp, u64]
     L.gamx_align_batch.restype = C.c_int
     L.gamx_unpack_ops.argtypes = [vp, u64, u64, vp]
@@ -286,12 +288,19 @@ class Context:
         jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
         return int(self.lib.gamx_ops_capacity(self._h, jobs.ctypes.data, len(jobs)))
 
-    def align_batch(self, jobs: np.ndarray):
-        """Host buffers in, host buffers out (the end-to-end path): returns (results, ops)."""
+    def set_pipeline_chunk(self, jobs_per_chunk: int):
+        """Chunk size of the pipelined gamx_align_batch (0 disables pipelining)."""
+        self._check(self.lib.gamx_set_pipeline_chunk(self._h, int(jobs_per_chunk)))
+
+    def align_batch(self, jobs: np.ndarray, out: np.ndarray | None = None):
+        """Host buffers in, host buffers out (the end-to-end path): returns (results, ops).
+        out: optional caller-owned RESULT_DTYPE array of len(jobs) records to write into."""
         jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
         n = len(jobs)
         cap = self.ops_capacity(jobs) if (jobs["mode"] == MODE_FULL).any() else 0
-        results = np.empty(n, dtype=RESULT_DTYPE)  # every record is written by the library
+        if out is not None:
+            assert out.dtype == RESULT_DTYPE and len(out) == n and out.flags["C_CONTIGUOUS"]
+        results = out if out is not None else np.empty(n, dtype=RESULT_DTYPE)  # every record is written by the library
         ops = np.zeros((cap + 3) // 4 + 8, dtype=np.uint8)
         self._check(self.lib.gamx_align_batch(self._h, jobs.ctypes.data, n, results.ctypes.data,
                                               ops.ctypes.data, cap))

@@ -21,6 +21,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -141,29 +143,51 @@ generic_kernel(const GenJob* __restrict__ jobs, int n_jobs, SeqStore store, int6
 
 // K0: packs raw base codes (1 byte per base, values > 4 -> N) into the store format (2 bits per
 // base + N bitmask).  One thread produces one group of 32 bases = 2 packed words + 1 mask word.
-// Contig c of the upload occupies store groups [sgroup[c], sgroup[c+1]) (relative to group0) and
-// raw bytes [roff[c], roff[c] + len[c]).
-__global__ void __launch_bounds__(256)
-pack_kernel(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ roff, const uint64_t* __restrict__ len,
-            const uint64_t* __restrict__ sgroup, int n_contigs, uint64_t group0, uint64_t n_groups,
-            uint32_t* __restrict__ packed, uint32_t* __restrict__ nmask) {
-  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_groups) return;
+// Contig c of the piece occupies store groups [sgroup[c], sgroup[c+1]) (relative to group0) and
+// raw bytes [roff[c], roff[c] + len[c]); the launch covers groups [g_first, g_first + n_groups).
+// 64-thread blocks with at most 32 registers per thread: small enough to become resident next to the
+// persistent alignment blocks (which leave ~4 K registers per SM free), so the pack of upload piece
+// p+1 proceeds while the alignment kernel of an earlier chunk still owns every SM.
+constexpr int kPackThreads = 64;
+__global__ void __launch_bounds__(kPackThreads, 32)
+pack_kernel(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ roff, const uint64_t* __restrict__ sgroup,
+            int n_contigs, uint64_t group0, uint64_t g_first, uint64_t n_groups, uint32_t* __restrict__ packed,
+            uint32_t* __restrict__ nmask) {
+  const uint64_t gi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= n_groups) return;
+  const uint64_t g = g_first + gi;
   int lo = 0, hi = n_contigs;  // last c with sgroup[c] <= g
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
     if (sgroup[mid] <= g) lo = mid; else hi = mid;
   }
   const uint64_t local = (g - sgroup[lo]) * 32;
-  const uint64_t remain = len[lo] - local;
+  const uint64_t len = roff[lo + 1] - roff[lo];
+  const uint64_t remain = len - local;
   const int n = remain < 32 ? (int)remain : 32;
   const uint8_t* src = raw + roff[lo] + local;
   uint32_t w0 = 0, w1 = 0, m = 0;
-  for (int i = 0; i < n; i++) {
-    const uint32_t c = src[i];
-    if (c >= 4u) m |= 1u << i;
-    else if (i < 16) w0 |= c << (2 * i);
-    else w1 |= c << (2 * (i - 16));
+  if (n == 32 && ((uintptr_t)src & 3) == 0) {  // whole group, word-aligned source: eight 4-byte loads
+    const uint32_t* s4 = (const uint32_t*)src;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const uint32_t v = s4[q];
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const uint32_t c = (v >> (8 * b)) & 0xffu;
+        const int i = 4 * q + b;
+        if (c >= 4u) m |= 1u << i;
+        else if (i < 16) w0 |= c << (2 * i);
+        else w1 |= c << (2 * (i - 16));
+      }
+    }
+  } else {
+    for (int i = 0; i < n; i++) {
+      const uint32_t c = src[i];
+      if (c >= 4u) m |= 1u << i;
+      else if (i < 16) w0 |= c << (2 * i);
+      else w1 |= c << (2 * (i - 16));
+    }
   }
   const uint64_t G = group0 + g;
   packed[2 * G] = w0;
@@ -328,19 +352,35 @@ struct PinBuf {
   size_t cap = 0;
 };
 
+// Per-batch buffers.  Two slots per device, each with its own stream, so that the pipelined
+// gamx_align_batch can prepare / upload chunk c+1 and read back chunk c-1 while chunk c computes
+// (and the kernel of chunk c+1 fills the SMs chunk c's persistent warps leave).  Everything that is
+// not pipelined uses slot 0.
+struct Slot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DevBuf jobs, gjobs, results, dirs, ops, grows, gdirs, counters;
+  PinBuf h_jobs, h_gjobs, h_results, h_ops;
+};
+
 struct Device {
   int id = 0;
   int sm_count = 0;
   size_t total_mem = 0;
-  cudaStream_t stream = nullptr;
+  Slot s[2];
+  cudaStream_t stream = nullptr;  // == s[0].stream
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf packed, nmask;           // contig store replica (2 bits per base + N mask)
   uint64_t store_groups = 0;      // 32-base groups already packed on this device
   DevBuf raw, meta;               // staging for K0: raw base codes + per-contig offsets
-  DevBuf jobs, gjobs, results, dirs, ops, grows, gdirs, counters, peak;
+  DevBuf peak;
   DevBuf hjobs, hoffs, hkeys_a, hkeys_a2, hvals_a, hvals_a2, hkeys_b, hvotes, hout, htemp;  // findHits scratch
-  PinBuf h_jobs, h_gjobs, h_results, h_ops, h_stage, h_stage2, h_meta;
+  PinBuf h_stage, h_stage2;
   cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+  // contig uploads run on their own stream, piece by piece; a consumer stream waits for the event of
+  // the last piece it needs (pieces complete in order)
+  cudaStream_t up_stream = nullptr;
+  std::vector<cudaEvent_t> up_events;  // event pool, one per piece of the upload in flight (+ [0] = "all earlier uploads")
 };
 
 // Index of the contig store.  Sequence data itself lives only on the devices; contigs added one
@@ -351,11 +391,30 @@ struct StoreIndex {
   uint64_t n_bases = 0;
 };
 
+// An upload registered by gamx_add_contigs*: contigs [first, first + n) whose raw codes are copied
+// and packed piece by piece.  The synchronous entry point enqueues everything at once; the
+// asynchronous one leaves the pieces to be enqueued as batches need them (upload_advance), so that a
+// pipelined batch starts computing on the first contigs while later ones still cross PCIe.
+struct Upload {
+  bool active = false;
+  const uint8_t* raw = nullptr;
+  size_t first = 0, n = 0;
+  uint64_t group0 = 0;
+  std::vector<size_t> piece_end;      // exclusive end (contig index relative to first) of each piece
+  const uint64_t* roff = nullptr;     // per contig: raw byte offset (n+1 entries), in the context's pinned meta buffer
+  const uint64_t* sgroup = nullptr;   // per contig: first store group relative to group0 (n+1 entries)
+  size_t enqueued = 0;                // pieces already enqueued on every device
+};
+
 struct gamx_ctx {
   std::vector<Device> devs;
   StoreIndex store;
   std::vector<uint8_t> pending;   // raw codes of contigs [pending_first, store.start.size())
   size_t pending_first = 0;
+  Upload up;
+  PinBuf h_meta;                  // roff[n+1], sgroup[n+1] of the upload in flight (pinned, shared by the devices)
+  uint64_t pipeline_chunk = 65536;  // gamx_set_pipeline_chunk
+  uint64_t piece_bytes = 32u << 20;  // raw bytes per upload piece (GAMX_UPLOAD_PIECE_BYTES)
   std::mutex mu;
   std::string err;
 };
@@ -397,93 +456,162 @@ int ensure_pin(gamx_ctx* ctx, PinBuf& b, size_t bytes) {
   return GAMX_OK;
 }
 
-// grows a store array, keeping its contents
+// grows a store array, keeping its contents (rare: synchronises the whole device)
 int grow_keep(gamx_ctx* ctx, Device& d, DevBuf& b, size_t bytes, size_t used) {
   if (bytes <= b.cap) return GAMX_OK;
   void* np = nullptr;
   const size_t want = bytes + bytes / 2 + 4096;
+  CU(cudaDeviceSynchronize());
   CU(cudaMalloc(&np, want));
-  if (b.p && used) CU(cudaMemcpyAsync(np, b.p, used, cudaMemcpyDeviceToDevice, d.stream));
-  CU(cudaStreamSynchronize(d.stream));
+  if (b.p && used) CU(cudaMemcpy(np, b.p, used, cudaMemcpyDeviceToDevice));
   if (b.p) CU(cudaFree(b.p));
   b.p = np; b.cap = want;
   return GAMX_OK;
 }
 
-// host -> device copy of `bytes` raw codes: direct when the source is pinned, else through two
-// pinned staging buffers so the host memcpy of chunk n+1 overlaps the DMA of chunk n
-int h2d_raw(gamx_ctx* ctx, Device& d, void* dst, const uint8_t* src, size_t bytes) {
+// host -> device copy of `bytes` raw codes on the upload stream: direct when the source is pinned,
+// else through two pinned staging buffers so the host memcpy of chunk n+1 overlaps the DMA of chunk n
+int h2d_raw(gamx_ctx* ctx, Device& d, void* dst, const uint8_t* src, size_t bytes, bool pinned) {
   if (!bytes) return GAMX_OK;
-  cudaPointerAttributes at;
-  const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
-  if (!pinned) cudaGetLastError();
   if (pinned) {
-    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d.stream));
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d.up_stream));
     return GAMX_OK;
   }
   const size_t chunk = 16u << 20;
   if (int rc = ensure_pin(ctx, d.h_stage, chunk)) return rc;
   if (int rc = ensure_pin(ctx, d.h_stage2, chunk)) return rc;
   void* st[2] = {d.h_stage.p, d.h_stage2.p};
-  bool used[2] = {false, false};
   size_t off = 0;
   for (int i = 0; off < bytes; i ^= 1) {
     const size_t n = std::min(chunk, bytes - off);
-    if (used[i]) CU(cudaEventSynchronize(d.ev_stage[i]));
+    CU(cudaEventSynchronize(d.ev_stage[i]));  // (a never-recorded event is complete)
     memcpy(st[i], src + off, n);
-    CU(cudaMemcpyAsync((uint8_t*)dst + off, st[i], n, cudaMemcpyHostToDevice, d.stream));
-    CU(cudaEventRecord(d.ev_stage[i], d.stream));
-    used[i] = true;
+    CU(cudaMemcpyAsync((uint8_t*)dst + off, st[i], n, cudaMemcpyHostToDevice, d.up_stream));
+    CU(cudaEventRecord(d.ev_stage[i], d.up_stream));
     off += n;
   }
   return GAMX_OK;
 }
 
-// Stages contigs [first, first+n) - raw codes concatenated in `raw`, lengths in the index - to
-// every device: pinned async H2D of the raw bytes, then K0 packs them into the store on the device.
+bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  const bool pinned = cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  if (!pinned) cudaGetLastError();
+  return pinned;
+}
+
+
+// Enqueues upload pieces until the piece holding contig `upto` (absolute id; SIZE_MAX: all) is on its
+// way on every device.  Piece p: H2D of its raw bytes, K0 over its store groups, event p + 1.
+int upload_advance(gamx_ctx* ctx, size_t upto) {
+  Upload& u = ctx->up;
+  if (!u.active) return GAMX_OK;
+  const size_t np = u.piece_end.size();
+  size_t want = np;
+  if (upto != SIZE_MAX) {
+    if (upto < u.first) return GAMX_OK;
+    const size_t rel = std::min(upto - u.first, u.n - 1);
+    want = (size_t)(std::upper_bound(u.piece_end.begin(), u.piece_end.end(), rel) - u.piece_end.begin()) + 1;
+    want = std::min(want, np);
+  }
+  if (u.enqueued >= want) return GAMX_OK;
+  const bool pinned = is_pinned(u.raw);
+  for (size_t p = u.enqueued; p < want; p++) {
+    const size_t c0 = p ? u.piece_end[p - 1] : 0, c1 = u.piece_end[p];
+    const uint64_t g0 = u.sgroup[c0], g1 = u.sgroup[c1];
+    for (Device& d : ctx->devs) {
+      CU(cudaSetDevice(d.id));
+      if (int rc = h2d_raw(ctx, d, (uint8_t*)d.raw.p + u.roff[c0], u.raw + u.roff[c0], u.roff[c1] - u.roff[c0], pinned)) return rc;
+      if (g1 > g0) {
+        const uint64_t* dm = (const uint64_t*)d.meta.p;  // roff[n+1], sgroup[n+1]
+        const unsigned blocks = (unsigned)((g1 - g0 + kPackThreads - 1) / kPackThreads);
+        pack_kernel<<<blocks, kPackThreads, 0, d.up_stream>>>((const uint8_t*)d.raw.p, dm + c0, dm + (u.n + 1) + c0, (int)(c1 - c0),
+                                                    u.group0, g0, g1 - g0, (uint32_t*)d.packed.p, (uint32_t*)d.nmask.p);
+        CU(cudaGetLastError());
+      }
+      CU(cudaEventRecord(d.up_events[p + 1], d.up_stream));
+    }
+  }
+  u.enqueued = want;
+  if (want == np) {  // everything is enqueued: later consumers wait for event 0 ("all uploads so far")
+    for (Device& d : ctx->devs) {
+      CU(cudaSetDevice(d.id));
+      CU(cudaEventRecord(d.up_events[0], d.up_stream));
+    }
+    u.active = false;
+  }
+  return GAMX_OK;
+}
+
+// Makes `stream` of device d wait until contigs [0, upto] (SIZE_MAX: the whole store) are packed.
+int store_ready(gamx_ctx* ctx, Device& d, cudaStream_t stream, size_t upto) {
+  if (int rc = upload_advance(ctx, upto)) return rc;
+  const Upload& u = ctx->up;
+  if (d.up_events.empty()) return GAMX_OK;  // nothing was ever uploaded
+  CU(cudaSetDevice(d.id));
+  if (u.active && upto != SIZE_MAX && upto >= u.first) {
+    const size_t rel = std::min(upto - u.first, u.n - 1);
+    const size_t p = (size_t)(std::upper_bound(u.piece_end.begin(), u.piece_end.end(), rel) - u.piece_end.begin());
+    CU(cudaStreamWaitEvent(stream, d.up_events[std::min(p, u.piece_end.size() - 1) + 1], 0));
+  } else {
+    CU(cudaStreamWaitEvent(stream, d.up_events[0], 0));
+  }
+  return GAMX_OK;
+}
+
+// Registers the upload of contigs [first, first+n) - raw codes concatenated in `raw`, lengths in the
+// index - to every device.  wait: enqueue all pieces and return when `raw` may be reused.
 int store_upload(gamx_ctx* ctx, const uint8_t* raw, size_t first, size_t n, bool wait = true) {
   if (n == 0) return GAMX_OK;
+  if (int rc = upload_advance(ctx, SIZE_MAX)) return rc;  // finish enqueuing an earlier deferred upload
   const StoreIndex& si = ctx->store;
-  const uint64_t group0 = si.start[first] / 32;
+  Upload& u = ctx->up;
+  u.raw = raw; u.first = first; u.n = n; u.enqueued = 0;
+  u.group0 = si.start[first] / 32;
   const uint64_t groups_end = si.n_bases / 32;
-  const uint64_t n_groups = groups_end - group0;
-  uint64_t raw_bytes = 0;
-  for (size_t c = first; c < first + n; c++) raw_bytes += si.length[c];
+  const size_t meta_bytes = 2 * (n + 1) * sizeof(uint64_t);
+  for (Device& d : ctx->devs) {  // an earlier upload may still read the pinned meta buffer / raw
+    CU(cudaSetDevice(d.id));
+    CU(cudaStreamSynchronize(d.up_stream));
+  }
+  if (int rc = ensure_pin(ctx, ctx->h_meta, meta_bytes)) return rc;
+  uint64_t* roff = (uint64_t*)ctx->h_meta.p;
+  uint64_t* sgroup = roff + (n + 1);
+  u.roff = roff; u.sgroup = sgroup;
+  u.piece_end.clear();
+  uint64_t off = 0, piece_start = 0;
+  const uint64_t* st = si.start.data() + first;
+  const uint64_t* ln = si.length.data() + first;
+  const uint64_t g0 = u.group0, piece_bytes = ctx->piece_bytes;
+  for (size_t c = 0; c < n; c++) {
+    roff[c] = off; sgroup[c] = st[c] / 32 - g0;
+    off += ln[c];
+    if (off - piece_start >= piece_bytes) { u.piece_end.push_back(c + 1); piece_start = off; }
+  }
+  roff[n] = off; sgroup[n] = groups_end - u.group0;
+  if (u.piece_end.empty() || u.piece_end.back() != n) u.piece_end.push_back(n);
   for (Device& d : ctx->devs) {
     CU(cudaSetDevice(d.id));
     if (int rc = grow_keep(ctx, d, d.packed, groups_end * 8 + 64, d.store_groups * 8)) return rc;
     if (int rc = grow_keep(ctx, d, d.nmask, groups_end * 4 + 64, d.store_groups * 4)) return rc;
-    if (n_groups == 0) { d.store_groups = groups_end; continue; }
-    // per-contig metadata: roff[n], len[n], sgroup[n+1]
-    const size_t meta_bytes = (3 * n + 1) * sizeof(uint64_t);
-    if (int rc = ensure_pin(ctx, d.h_meta, meta_bytes)) return rc;
     if (int rc = ensure_dev(ctx, d.meta, meta_bytes)) return rc;
-    if (int rc = ensure_dev(ctx, d.raw, raw_bytes + 64)) return rc;
-    CU(cudaStreamSynchronize(d.stream));  // a previous asynchronous upload may still read h_meta
-    uint64_t* roff = (uint64_t*)d.h_meta.p;
-    uint64_t* len = roff + n;
-    uint64_t* sg = len + n;
-    uint64_t off = 0;
-    for (size_t c = 0; c < n; c++) {
-      roff[c] = off; len[c] = si.length[first + c]; sg[c] = si.start[first + c] / 32 - group0;
-      off += len[c];
+    if (int rc = ensure_dev(ctx, d.raw, off + 64)) return rc;
+    while (d.up_events.size() < u.piece_end.size() + 1) {
+      cudaEvent_t e;
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      d.up_events.push_back(e);
     }
-    sg[n] = n_groups;
-    CU(cudaMemcpyAsync(d.meta.p, d.h_meta.p, meta_bytes, cudaMemcpyHostToDevice, d.stream));
-    if (int rc = h2d_raw(ctx, d, d.raw.p, raw, raw_bytes)) return rc;
-    const uint64_t* dm = (const uint64_t*)d.meta.p;
-    const unsigned blocks = (unsigned)((n_groups + 255) / 256);
-    pack_kernel<<<blocks, 256, 0, d.stream>>>((const uint8_t*)d.raw.p, dm, dm + n, dm + 2 * n, (int)n, group0, n_groups,
-                                             (uint32_t*)d.packed.p, (uint32_t*)d.nmask.p);
-    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(d.meta.p, ctx->h_meta.p, meta_bytes, cudaMemcpyHostToDevice, d.up_stream));
     d.store_groups = groups_end;
   }
-  // the caller's raw buffer (and our pinned metadata) may be reused once the copies are done
-  if (wait)
+  u.active = true;
+  if (wait) {
+    if (int rc = upload_advance(ctx, SIZE_MAX)) return rc;
     for (Device& d : ctx->devs) {
       CU(cudaSetDevice(d.id));
-      CU(cudaStreamSynchronize(d.stream));
+      CU(cudaStreamSynchronize(d.up_stream));
     }
+  }
   return GAMX_OK;
 }
 
@@ -541,15 +669,18 @@ struct gamx_plan {
   uint64_t launches = 0;
   uint64_t ops_total = 0;  // ops capacity over all devices
   bool ran = false;
+  int slot = 0;            // which of the devices' buffer slots / streams the plan uses
+  size_t max_contig = 0;   // largest contig id a job refers to (upload dependency)
+  std::string err;         // plan_build reports here (it may run on a helper thread)
 };
 
 namespace {
 
 template <int C, int LG, bool DIRS>
-int launch_k1_t(gamx_ctx* ctx, Device& d, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
+int launch_k1_t(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
                 uint64_t stride, uint32_t* ops, DevResult* results) {
   SeqStore st{(const uint32_t*)d.packed.p, (const uint32_t*)d.nmask.p};
-  k1_kernel<C, LG, DIRS><<<g.grid, kWarpsPerBlock * 32, 0, d.stream>>>(jobs, (int)g.job_idx.size(), counter, st, dirs,
+  k1_kernel<C, LG, DIRS><<<g.grid, kWarpsPerBlock * 32, 0, stream>>>(jobs, (int)g.job_idx.size(), counter, st, dirs,
                                                                       stride, ops, results);
   CU(cudaGetLastError());
   return GAMX_OK;
@@ -581,45 +712,51 @@ int k1_blocks_per_sm(int c, int lg, bool dirs) {
 }
 
 template <int LG>
-int launch_k1_lg(gamx_ctx* ctx, Device& d, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
+int launch_k1_lg(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
                  uint64_t stride, uint32_t* ops, DevResult* results) {
   switch (g.c) {
-#define M(N, L) case N: return g.dirs ? launch_k1_t<N, L, true>(ctx, d, g, jobs, counter, dirs, stride, ops, results) \
-                                       : launch_k1_t<N, L, false>(ctx, d, g, jobs, counter, dirs, stride, ops, results);
+#define M(N, L) case N: return g.dirs ? launch_k1_t<N, L, true>(ctx, d, stream, g, jobs, counter, dirs, stride, ops, results) \
+                                       : launch_k1_t<N, L, false>(ctx, d, stream, g, jobs, counter, dirs, stride, ops, results);
     GAMX_FOR_EACH_C(M, LG)
 #undef M
     default: ctx->err = "internal: bad stripe width"; return GAMX_ERR_INVALID;
   }
 }
-int launch_k1(gamx_ctx* ctx, Device& d, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
+int launch_k1(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
               uint64_t stride, uint32_t* ops, DevResult* results) {
-  if (g.lg == 32) return launch_k1_lg<32>(ctx, d, g, jobs, counter, dirs, stride, ops, results);
-  if (g.lg == 16) return launch_k1_lg<16>(ctx, d, g, jobs, counter, dirs, stride, ops, results);
-  return launch_k1_lg<8>(ctx, d, g, jobs, counter, dirs, stride, ops, results);
+  if (g.lg == 32) return launch_k1_lg<32>(ctx, d, stream, g, jobs, counter, dirs, stride, ops, results);
+  if (g.lg == 16) return launch_k1_lg<16>(ctx, d, stream, g, jobs, counter, dirs, stride, ops, results);
+  return launch_k1_lg<8>(ctx, d, stream, g, jobs, counter, dirs, stride, ops, results);
 }
 
-// splits [0, n) over the host's cores; fn(begin, end) must be thread-safe
+// splits [0, n) over the host's cores; fn(slice, begin, end) must be thread-safe, slice < kMaxHostThreads
+constexpr unsigned kMaxHostThreads = 32;
 template <class F>
-void parallel_for(uint64_t n, F fn) {
+void parallel_slices(uint64_t n, F fn) {
   // host threads for batch preparation: all cores, divided by the number of ranks sharing the node
   // when launched one process per GPU (torchrun sets LOCAL_WORLD_SIZE); GAMX_HOST_THREADS overrides
   static const unsigned nt_cfg = [] {
     unsigned n = std::thread::hardware_concurrency();
     if (n == 0) n = 4;
-    if (const char* e = getenv("GAMX_HOST_THREADS")) { const int v = atoi(e); if (v > 0) return (unsigned)v; }
+    if (const char* e = getenv("GAMX_HOST_THREADS")) { const int v = atoi(e); if (v > 0) return std::min((unsigned)v, kMaxHostThreads); }
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) { const int v = atoi(e); if (v > 1) n = std::max(1u, n / (unsigned)v); }
-    return std::min(n, 32u);
+    return std::min(n, kMaxHostThreads);
   }();
   unsigned nt = nt_cfg;
-  if (n < 20000 || nt == 1) { fn((uint64_t)0, n); return; }
+  if (n < 20000 || nt == 1) { fn(0u, (uint64_t)0, n); return; }
   std::vector<std::thread> th;
   const uint64_t chunk = (n + nt - 1) / nt;
-  for (unsigned t = 0; t < nt; t++) {
+  for (unsigned t = 1; t < nt; t++) {
     const uint64_t b = t * chunk, e = std::min(n, b + chunk);
     if (b >= e) break;
-    th.emplace_back([=] { fn(b, e); });
+    th.emplace_back([=] { fn(t, b, e); });
   }
+  fn(0u, (uint64_t)0, std::min(n, chunk));  // the calling thread takes the first slice
   for (auto& t : th) t.join();
+}
+template <class F>
+void parallel_for(uint64_t n, F fn) {
+  parallel_slices(n, [&](unsigned, uint64_t b, uint64_t e) { fn(b, e); });
 }
 
 // stable LSD radix sort of job indices by descending cost
@@ -660,10 +797,10 @@ void lpt_assign(const std::vector<uint32_t>& order, int n_shards, CostOf cost_of
 
 // ---- K2 dispatch: LG = 64 takes every stripe width, LG = 128/256 only the wide ones -----------
 template <int C, int LG, bool DIRS>
-int launch_k2_t(gamx_ctx* ctx, Device& d, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
+int launch_k2_t(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
                 uint64_t stride, uint32_t* ops, DevResult* results) {
   SeqStore st{(const uint32_t*)d.packed.p, (const uint32_t*)d.nmask.p};
-  k2_kernel<C, LG, DIRS><<<g.grid, LG, 0, d.stream>>>(jobs, (int)g.job_idx.size(), counter, st, dirs, stride, ops, results);
+  k2_kernel<C, LG, DIRS><<<g.grid, LG, 0, stream>>>(jobs, (int)g.job_idx.size(), counter, st, dirs, stride, ops, results);
   CU(cudaGetLastError());
   return GAMX_OK;
 }
@@ -684,10 +821,10 @@ int k2_blocks_per_sm(int c, int lg, bool dirs) {
   if (e != cudaSuccess) { cudaGetLastError(); return 0; }
   return b;
 }
-int launch_k2(gamx_ctx* ctx, Device& d, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
+int launch_k2(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
               uint64_t stride, uint32_t* ops, DevResult* results) {
-#define M(N, L) if (g.c == N && g.lg == L) return g.dirs ? launch_k2_t<N, L, true>(ctx, d, g, jobs, counter, dirs, stride, ops, results) \
-                                                          : launch_k2_t<N, L, false>(ctx, d, g, jobs, counter, dirs, stride, ops, results);
+#define M(N, L) if (g.c == N && g.lg == L) return g.dirs ? launch_k2_t<N, L, true>(ctx, d, stream, g, jobs, counter, dirs, stride, ops, results) \
+                                                          : launch_k2_t<N, L, false>(ctx, d, stream, g, jobs, counter, dirs, stride, ops, results);
   GAMX_FOR_EACH_C(M, 64)
   GAMX_FOR_EACH_WIDE_C(M, 128)
   GAMX_FOR_EACH_WIDE_C(M, 256)
@@ -728,21 +865,30 @@ int gamx_create(gamx_ctx** out, const int* device_ids, int n_devices) {
     return GAMX_ERR_NO_DEVICE;
   }
   gamx_ctx* ctx = new gamx_ctx();
+  if (const char* e = getenv("GAMX_PIPELINE_CHUNK")) ctx->pipeline_chunk = (uint64_t)strtoull(e, nullptr, 10);
+  if (const char* e = getenv("GAMX_UPLOAD_PIECE_BYTES")) ctx->piece_bytes = std::max<uint64_t>(4096, strtoull(e, nullptr, 10));
   if (n_devices <= 0) n_devices = visible;
   for (int i = 0; i < n_devices; i++) {
     Device d;
     d.id = device_ids ? device_ids[i] : i;
     if (d.id < 0 || d.id >= visible) { delete ctx; return GAMX_ERR_INVALID; }
     cudaDeviceProp prop;
-    if (cudaSetDevice(d.id) != cudaSuccess || cudaGetDeviceProperties(&prop, d.id) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&d.ev0) != cudaSuccess || cudaEventCreate(&d.ev1) != cudaSuccess ||
-        cudaEventCreateWithFlags(&d.ev_stage[0], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&d.ev_stage[1], cudaEventDisableTiming) != cudaSuccess) {
+    bool ok = cudaSetDevice(d.id) == cudaSuccess && cudaGetDeviceProperties(&prop, d.id) == cudaSuccess;
+    for (int k = 0; ok && k < 2; k++)
+      ok = cudaStreamCreateWithFlags(&d.s[k].stream, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreate(&d.s[k].ev0) == cudaSuccess && cudaEventCreate(&d.s[k].ev1) == cudaSuccess;
+    int prio_lo = 0, prio_hi = 0;  // the upload stream's small pack blocks go first when an SM has room
+    ok = ok && cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithPriority(&d.up_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+         cudaEventCreate(&d.ev0) == cudaSuccess && cudaEventCreate(&d.ev1) == cudaSuccess &&
+         cudaEventCreateWithFlags(&d.ev_stage[0], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&d.ev_stage[1], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
       cudaGetLastError();
       delete ctx;
       return GAMX_ERR_CUDA;
     }
+    d.stream = d.s[0].stream;
     d.sm_count = prop.multiProcessorCount;
     d.total_mem = prop.totalGlobalMem;
     ctx->devs.push_back(d);
@@ -755,18 +901,29 @@ void gamx_destroy(gamx_ctx* ctx) {
   if (!ctx) return;
   for (Device& d : ctx->devs) {
     cudaSetDevice(d.id);
-    cudaStreamSynchronize(d.stream);
+    cudaDeviceSynchronize();
     DevBuf* dbs[] = {&d.packed, &d.nmask, &d.raw, &d.meta, &d.hjobs, &d.hoffs, &d.hkeys_a, &d.hkeys_a2, &d.hvals_a,
-                     &d.hvals_a2, &d.hkeys_b, &d.hvotes, &d.hout, &d.htemp, &d.jobs, &d.gjobs, &d.results, &d.dirs, &d.ops, &d.grows, &d.gdirs, &d.counters, &d.peak};
+                     &d.hvals_a2, &d.hkeys_b, &d.hvotes, &d.hout, &d.htemp, &d.peak};
     for (DevBuf* b : dbs) if (b->p) cudaFree(b->p);
-    PinBuf* pbs[] = {&d.h_jobs, &d.h_gjobs, &d.h_results, &d.h_ops, &d.h_stage, &d.h_stage2, &d.h_meta};
+    PinBuf* pbs[] = {&d.h_stage, &d.h_stage2};
     for (PinBuf* b : pbs) if (b->p) cudaFreeHost(b->p);
+    for (Slot& sl : d.s) {
+      DevBuf* sd[] = {&sl.jobs, &sl.gjobs, &sl.results, &sl.dirs, &sl.ops, &sl.grows, &sl.gdirs, &sl.counters};
+      for (DevBuf* b : sd) if (b->p) cudaFree(b->p);
+      PinBuf* sp[] = {&sl.h_jobs, &sl.h_gjobs, &sl.h_results, &sl.h_ops};
+      for (PinBuf* b : sp) if (b->p) cudaFreeHost(b->p);
+      cudaEventDestroy(sl.ev0);
+      cudaEventDestroy(sl.ev1);
+      cudaStreamDestroy(sl.stream);
+    }
+    for (cudaEvent_t e : d.up_events) cudaEventDestroy(e);
     cudaEventDestroy(d.ev0);
     cudaEventDestroy(d.ev1);
     cudaEventDestroy(d.ev_stage[0]);
     cudaEventDestroy(d.ev_stage[1]);
-    cudaStreamDestroy(d.stream);
+    cudaStreamDestroy(d.up_stream);
   }
+  if (ctx->h_meta.p) cudaFreeHost(ctx->h_meta.p);
   delete ctx;
 }
 
@@ -804,11 +961,25 @@ static int64_t add_contigs_impl(gamx_ctx* ctx, const uint8_t* codes, const uint6
   const auto t0 = std::chrono::steady_clock::now();
   if (int rc = flush_pending(ctx)) return rc;
   const size_t first = ctx->store.start.size();
-  ctx->store.start.reserve(first + n);
-  ctx->store.length.reserve(first + n);
-  for (uint64_t c = 0; c < n; c++) {
-    if (lengths[c] >= (1ull << 31)) { ctx->err = "contig longer than 2^31 bases"; return GAMX_ERR_INVALID; }
-    index_add(ctx, lengths[c]);
+  {
+    StoreIndex& si = ctx->store;
+    si.start.resize(first + n);
+    si.length.resize(first + n);
+    uint64_t* st = si.start.data() + first;
+    uint64_t* ln = si.length.data() + first;
+    uint64_t nb = si.n_bases, too_long = 0;
+    for (uint64_t c = 0; c < n; c++) {
+      const uint64_t len = lengths[c];
+      too_long |= len >> 31;
+      st[c] = nb; ln[c] = len;
+      nb += (len + 31) & ~uint64_t(31);
+    }
+    if (too_long) {
+      si.start.resize(first); si.length.resize(first);
+      ctx->err = "contig longer than 2^31 bases";
+      return GAMX_ERR_INVALID;
+    }
+    si.n_bases = nb;
   }
   ctx->pending_first = ctx->store.start.size();
   const auto t1 = std::chrono::steady_clock::now();
@@ -827,10 +998,24 @@ uint64_t gamx_contig_length(const gamx_ctx* ctx, uint32_t id) {
 int gamx_clear_contigs(gamx_ctx* ctx) {
   if (!ctx) return GAMX_ERR_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
-  ctx->store = StoreIndex();
+  if (int rc = upload_advance(ctx, SIZE_MAX)) return rc;
+  for (Device& d : ctx->devs) {  // kernels in flight may still read the store that is about to be overwritten
+    CU(cudaSetDevice(d.id));
+    CU(cudaDeviceSynchronize());
+    d.store_groups = 0;
+  }
+  ctx->store.start.clear();   // (capacity is kept: a caller that re-uploads per batch pays no page faults)
+  ctx->store.length.clear();
+  ctx->store.n_bases = 0;
   ctx->pending.clear();
   ctx->pending_first = 0;
-  for (Device& d : ctx->devs) d.store_groups = 0;
+  return GAMX_OK;
+}
+
+int gamx_set_pipeline_chunk(gamx_ctx* ctx, uint64_t jobs_per_chunk) {
+  if (!ctx) return GAMX_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->pipeline_chunk = jobs_per_chunk;
   return GAMX_OK;
 }
 
@@ -865,9 +1050,19 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
   for (int d = 0; d < nd; d++) pl->dps[d].dev = d;
   Prepared* preps = pl->preps.get();
 
-  // 1. guards, sizes and classification of every job (banded_smith_waterman.cc:90-97), in parallel
+  // 1. guards, sizes and classification of every job (banded_smith_waterman.cc:90-97), in parallel;
+  //    every slice also summarises its jobs so that the common batch - one kernel family, near-uniform
+  //    cost, one device, no edit strings - needs no further pass over the jobs
+  struct Summary {
+    uint64_t cells = 0, cmin = ~0ull, cmax = 0, max_dir_words = 0, n_special = 0;
+    size_t max_contig = 0;
+    int c = -1, lg = 0, dirs = 0;  // kernel family of the slice's first job
+    bool mixed = false;
+  };
+  Summary sums[kMaxHostThreads];
   std::atomic<int64_t> bad(-1);
-  parallel_for(n, [&](uint64_t b, uint64_t e) {
+  parallel_slices(n, [&](unsigned t, uint64_t b, uint64_t e) {
+    Summary S;
     for (uint64_t i = b; i < e; i++) {
       const gamx_job& j = jobs[i];
       SeqView va, vb;
@@ -878,18 +1073,66 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
         continue;
       }
       pl->modes[i] = j.mode;
-      prepare_job(preps[i], nullptr, va, la, vb, lb, j.begin_a, j.end_a, j.begin_b, j.end_b, j.band, j.gap,
+      Prepared& P = preps[i];
+      prepare_job(P, nullptr, va, la, vb, lb, j.begin_a, j.end_a, j.begin_b, j.end_b, j.band, j.gap,
                   j.force_start != 0, j.force_end != 0, j.mode);
+      S.cells += P.cells;
+      S.max_contig = std::max(S.max_contig, (size_t)std::max(j.a_id, j.b_id));
+      if ((P.cls != kClassWarp && P.cls != kClassCta) || P.ops_cap) { S.n_special++; continue; }
+      S.cmin = std::min(S.cmin, P.cells); S.cmax = std::max(S.cmax, P.cells);
+      S.max_dir_words = std::max(S.max_dir_words, P.dir_words);
+      const int dirs = j.mode != GAMX_MODE_SCORE;
+      if (S.c < 0) { S.c = P.c; S.lg = P.lg; S.dirs = dirs; }
+      else if (S.c != P.c || S.lg != P.lg || S.dirs != dirs) S.mixed = true;
     }
+    sums[t] = S;
   });
   if (bad.load() >= 0) {
-    ctx->err = "job " + std::to_string(bad.load()) + ": unknown contig id, view outside the contig, or bad mode";
-    delete pl;
+    pl->err = "job " + std::to_string(bad.load()) + ": unknown contig id, view outside the contig, or bad mode";
+    *out = pl;
     return GAMX_ERR_INVALID;
+  }
+  {
+    Summary A;
+    for (const Summary& S : sums) {
+      if (S.c < 0 && S.n_special == 0 && S.cells == 0) continue;  // unused slice
+      A.cells += S.cells; A.n_special += S.n_special;
+      A.cmin = std::min(A.cmin, S.cmin); A.cmax = std::max(A.cmax, S.cmax);
+      A.max_dir_words = std::max(A.max_dir_words, S.max_dir_words);
+      A.max_contig = std::max(A.max_contig, S.max_contig);
+      if (S.c >= 0) {
+        if (A.c < 0) { A.c = S.c; A.lg = S.lg; A.dirs = S.dirs; }
+        else if (A.c != S.c || A.lg != S.lg || A.dirs != S.dirs) A.mixed = true;
+      }
+      A.mixed = A.mixed || S.mixed;
+    }
+    pl->cells = A.cells;
+    pl->max_contig = A.max_contig;
+    const bool latency_candidate = A.lg == 32 && n < (uint64_t)2 * ctx->devs[0].sm_count;  // see "Latency mode" below
+    if (nd == 1 && n > 0 && A.n_special == 0 && !A.mixed && A.c >= 0 && A.cmax <= A.cmin + A.cmin / 4 && !latency_candidate) {
+      // fast path: the whole batch is one launch in the caller's order
+      DevPlan& dp = pl->dps[0];
+      Group g; g.c = A.c; g.lg = A.lg; g.dirs = A.dirs != 0;
+      g.job_idx.resize(n);
+      g.max_dir_words = A.max_dir_words;
+      uint32_t* idx = g.job_idx.data();
+      uint32_t* jr = pl->job_res.data();
+      int* jd = pl->job_dev.data();
+      parallel_for(n, [&](uint64_t b, uint64_t e) {
+        for (uint64_t i = b; i < e; i++) { idx[i] = (uint32_t)i; jr[i] = (uint32_t)i; jd[i] = 0; }
+      });
+      dp.n_jobs = dp.n_dev_jobs = (uint32_t)n;
+      dp.groups.push_back(std::move(g));
+      *out = pl;
+      return GAMX_OK;
+    }
+    pl->cells = 0;  // the general path below sums again
+    pl->max_contig = 0;
   }
   std::vector<uint32_t> order;
   order.reserve(n);
   for (uint64_t i = 0; i < n; i++) {
+    pl->max_contig = std::max(pl->max_contig, (size_t)std::max(jobs[i].a_id, jobs[i].b_id));
     pl->cells += preps[i].cells;
     if (preps[i].cls == kClassEarly) continue;
     order.push_back((uint32_t)i);
@@ -1003,50 +1246,93 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
   return GAMX_OK;
 }
 
-// uploads descriptors and sizes the scratch of every device
+// resident blocks per SM of a kernel family (the occupancy query is cached: it is asked per chunk)
+static int blocks_per_sm_cached(int c, int lg, bool dirs) {
+  static std::mutex mu;
+  static int cache[kMaxC + 1][5][2];  // [c][lg index][dirs], 0 = not asked yet, -1 = does not fit
+  const int li = lg == 8 ? 0 : lg == 16 ? 1 : lg == 32 ? 2 : lg == 64 ? 3 : 4;
+  if (c < 0 || c > kMaxC || (lg > 64 && lg != 128 && lg != 256)) return 0;
+  std::lock_guard<std::mutex> lk(mu);
+  int& v = (lg == 256 ? cache[c][4][dirs] : lg == 128 ? cache[c][4][dirs] : cache[c][li][dirs]);
+  if (lg >= 128) {  // 128 and 256 share no slot: ask every time (rare, wide bands only)
+    return k2_blocks_per_sm(c, lg, dirs);
+  }
+  if (v == 0) {
+    const int b = lg > 32 ? k2_blocks_per_sm(c, lg, dirs) : k1_blocks_per_sm(c, lg, dirs);
+    v = b > 0 ? b : -1;
+  }
+  return v > 0 ? v : 0;
+}
+
+// uploads descriptors and sizes the scratch of every device (on the plan's slot)
 static int plan_upload(gamx_plan* pl) {
   gamx_ctx* ctx = pl->ctx;
   if (int rc = flush_pending(ctx)) return rc;
+  static const bool timing = getenv("GAMX_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto tp = now();
+  double tm[6] = {0, 0, 0, 0, 0, 0};
+  auto lap = [&](int k) { const auto t = now(); tm[k] += std::chrono::duration<double, std::milli>(t - tp).count(); tp = t; };
   for (DevPlan& dp : pl->dps) {
     Device& d = ctx->devs[dp.dev];
+    Slot& sl = d.s[pl->slot];
     if (dp.n_jobs == 0) continue;
     CU(cudaSetDevice(d.id));
-    if (int rc = ensure_pin(ctx, d.h_jobs, (size_t)dp.n_dev_jobs * sizeof(DevJob))) return rc;
-    if (int rc = ensure_pin(ctx, d.h_gjobs, (size_t)dp.n_gen_jobs * sizeof(GenJob))) return rc;
-    if (int rc = ensure_dev(ctx, d.jobs, (size_t)dp.n_dev_jobs * sizeof(DevJob))) return rc;
-    if (int rc = ensure_dev(ctx, d.gjobs, (size_t)dp.n_gen_jobs * sizeof(GenJob))) return rc;
-    if (int rc = ensure_dev(ctx, d.results, (size_t)dp.n_jobs * sizeof(DevResult))) return rc;
-    if (int rc = ensure_pin(ctx, d.h_results, (size_t)dp.n_jobs * sizeof(DevResult))) return rc;
-    if (int rc = ensure_dev(ctx, d.counters, sizeof(int) * (dp.groups.size() + 1))) return rc;
-    if (int rc = ensure_dev(ctx, d.ops, dp.ops_words * 4 + 64)) return rc;
-    if (int rc = ensure_dev(ctx, d.grows, dp.grows * 8 + 64)) return rc;
-    if (int rc = ensure_dev(ctx, d.gdirs, dp.gdirs * 4 + 64)) return rc;
+    lap(5);
+    // the kernels read the contig store: stream-ordered behind the upload pieces they need
+    if (int rc = store_ready(ctx, d, sl.stream, pl->max_contig)) return rc;
+    lap(0);
+    if (int rc = ensure_pin(ctx, sl.h_jobs, (size_t)dp.n_dev_jobs * sizeof(DevJob))) return rc;
+    if (int rc = ensure_pin(ctx, sl.h_gjobs, (size_t)dp.n_gen_jobs * sizeof(GenJob))) return rc;
+    if (int rc = ensure_dev(ctx, sl.jobs, (size_t)dp.n_dev_jobs * sizeof(DevJob))) return rc;
+    if (int rc = ensure_dev(ctx, sl.gjobs, (size_t)dp.n_gen_jobs * sizeof(GenJob))) return rc;
+    if (int rc = ensure_dev(ctx, sl.results, (size_t)dp.n_jobs * sizeof(DevResult))) return rc;
+    if (int rc = ensure_pin(ctx, sl.h_results, (size_t)dp.n_jobs * sizeof(DevResult))) return rc;
+    if (int rc = ensure_dev(ctx, sl.counters, sizeof(int) * (dp.groups.size() + 1))) return rc;
+    if (int rc = ensure_dev(ctx, sl.ops, dp.ops_words * 4 + 64)) return rc;
+    if (int rc = ensure_dev(ctx, sl.grows, dp.grows * 8 + 64)) return rc;
+    if (int rc = ensure_dev(ctx, sl.gdirs, dp.gdirs * 4 + 64)) return rc;
+    lap(1);
     // direction scratch: one region per resident warp ("slot"), reused from job to job
+    // (cudaMemGetInfo stalls for milliseconds while kernels are running, so it is only asked when the
+    //  scratch this slot already owns is not enough for full occupancy)
     uint64_t dirs_words = 0;
-    size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
-    const uint64_t budget_words = (uint64_t)((free_b + d.dirs.cap) * 0.8) / 4;
-    for (Group& g : dp.groups) {
-      if (!g.c) { g.grid = (int)((g.job_idx.size() + 63) / 64); continue; }
-      const bool cta = g.lg > 32;
-      int bps = cta ? k2_blocks_per_sm(g.c, g.lg, g.dirs) : k1_blocks_per_sm(g.c, g.lg, g.dirs);
-      if (bps <= 0) { ctx->err = "alignment kernel does not fit on the device"; return GAMX_ERR_CUDA; }
-      uint64_t grid = (uint64_t)d.sm_count * bps;
-      const uint64_t pairs_per_block = cta ? 1 : (uint64_t)kWarpsPerBlock * (32 / g.lg);
-      const uint64_t need = (g.job_idx.size() + pairs_per_block - 1) / pairs_per_block;
-      if (need < grid) grid = need;
-      if (g.dirs && g.max_dir_words) {
-        const uint64_t per_block = g.max_dir_words * pairs_per_block;
-        if (per_block > budget_words) { ctx->err = "direction scratch of one job exceeds device memory"; return GAMX_ERR_NOMEM; }
-        if (grid * per_block > budget_words) grid = budget_words / per_block;
-        dirs_words = std::max(dirs_words, grid * per_block);
+    uint64_t budget_words = sl.dirs.cap / 4;
+    for (int pass = 0; pass < 2; pass++) {
+      bool short_of_memory = false;
+      dirs_words = 0;
+      for (Group& g : dp.groups) {
+        if (!g.c) { g.grid = (int)((g.job_idx.size() + 63) / 64); continue; }
+        const bool cta = g.lg > 32;
+        const int bps = blocks_per_sm_cached(g.c, g.lg, g.dirs);
+        if (bps <= 0) { ctx->err = "alignment kernel does not fit on the device"; return GAMX_ERR_CUDA; }
+        uint64_t grid = (uint64_t)d.sm_count * bps;
+        const uint64_t pairs_per_block = cta ? 1 : (uint64_t)kWarpsPerBlock * (32 / g.lg);
+        const uint64_t need = (g.job_idx.size() + pairs_per_block - 1) / pairs_per_block;
+        if (need < grid) grid = need;
+        if (g.dirs && g.max_dir_words) {
+          const uint64_t per_block = g.max_dir_words * pairs_per_block;
+          if (grid * per_block > budget_words) {
+            short_of_memory = true;
+            if (pass == 1) {
+              if (per_block > budget_words) { ctx->err = "direction scratch of one job exceeds device memory"; return GAMX_ERR_NOMEM; }
+              grid = budget_words / per_block;
+            }
+          }
+          dirs_words = std::max(dirs_words, grid * per_block);
+        }
+        g.grid = (int)std::max<uint64_t>(grid, 1);
       }
-      g.grid = (int)std::max<uint64_t>(grid, 1);
+      if (!short_of_memory || pass == 1) break;
+      size_t free_b = 0, total_b = 0;
+      CU(cudaMemGetInfo(&free_b, &total_b));
+      budget_words = (uint64_t)((free_b + sl.dirs.cap) * 0.8) / 4;
     }
     dp.dirs_words = dirs_words;
-    if (int rc = ensure_dev(ctx, d.dirs, dirs_words * 4 + 64)) return rc;
-    DevJob* hj = (DevJob*)d.h_jobs.p;
-    GenJob* hg = (GenJob*)d.h_gjobs.p;
+    if (int rc = ensure_dev(ctx, sl.dirs, dirs_words * 4 + 64)) return rc;
+    lap(2);
+    DevJob* hj = (DevJob*)sl.h_jobs.p;
+    GenJob* hg = (GenJob*)sl.h_gjobs.p;
     for (const Group& g : dp.groups) {
       const Prepared* preps = pl->preps.get();
       parallel_for(g.job_idx.size(), [&](uint64_t b, uint64_t e) {
@@ -1056,11 +1342,27 @@ static int plan_upload(gamx_plan* pl) {
         }
       });
     }
+    lap(3);
     if (dp.n_dev_jobs)
-      CU(cudaMemcpyAsync(d.jobs.p, hj, (size_t)dp.n_dev_jobs * sizeof(DevJob), cudaMemcpyHostToDevice, d.stream));
+      CU(cudaMemcpyAsync(sl.jobs.p, hj, (size_t)dp.n_dev_jobs * sizeof(DevJob), cudaMemcpyHostToDevice, sl.stream));
     if (dp.n_gen_jobs)
-      CU(cudaMemcpyAsync(d.gjobs.p, hg, (size_t)dp.n_gen_jobs * sizeof(GenJob), cudaMemcpyHostToDevice, d.stream));
+      CU(cudaMemcpyAsync(sl.gjobs.p, hg, (size_t)dp.n_gen_jobs * sizeof(GenJob), cudaMemcpyHostToDevice, sl.stream));
+    lap(4);
   }
+  if (timing)
+    fprintf(stderr, "[gamx] plan_upload: store_ready %.2f, buffers %.2f, geometry+dirs %.2f, fill %.2f, h2d %.2f, other %.2f ms\n",
+            tm[0], tm[1], tm[2], tm[3], tm[4], tm[5]);
+  return GAMX_OK;
+}
+
+static int plan_build_checked(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan** out) {
+  gamx_plan* pl = nullptr;
+  const int rc = plan_build(ctx, jobs, n, &pl);
+  if (rc) {
+    if (pl) { ctx->err = pl->err; delete pl; }
+    return rc;
+  }
+  *out = pl;
   return GAMX_OK;
 }
 
@@ -1069,7 +1371,7 @@ int gamx_plan_create(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan*
   std::lock_guard<std::mutex> lk(ctx->mu);
   *out = nullptr;
   gamx_plan* pl = nullptr;
-  if (int rc = plan_build(ctx, jobs, n, &pl)) return rc;
+  if (int rc = plan_build_checked(ctx, jobs, n, &pl)) return rc;
   if (int rc = plan_upload(pl)) { delete pl; return rc; }
   *out = pl;
   return GAMX_OK;
@@ -1081,28 +1383,29 @@ static int plan_run_locked(gamx_plan* pl) {
   for (DevPlan& dp : pl->dps) {
     if (dp.n_jobs == 0) continue;
     Device& d = ctx->devs[dp.dev];
+    Slot& sl = d.s[pl->slot];
     CU(cudaSetDevice(d.id));
-    CU(cudaEventRecord(d.ev0, d.stream));
-    CU(cudaMemsetAsync(d.counters.p, 0, sizeof(int) * (dp.groups.size() + 1), d.stream));
+    CU(cudaEventRecord(sl.ev0, sl.stream));
+    CU(cudaMemsetAsync(sl.counters.p, 0, sizeof(int) * (dp.groups.size() + 1), sl.stream));
     for (size_t gi = 0; gi < dp.groups.size(); gi++) {
       const Group& g = dp.groups[gi];
-      DevResult* res = (DevResult*)d.results.p + g.res_off;
+      DevResult* res = (DevResult*)sl.results.p + g.res_off;
       if (g.c) {
-        const DevJob* dj = (const DevJob*)d.jobs.p + g.job_off;
-        const int rc = g.lg > 32 ? launch_k2(ctx, d, g, dj, (int*)d.counters.p + gi, (uint32_t*)d.dirs.p,
-                                             g.max_dir_words, (uint32_t*)d.ops.p, res)
-                                 : launch_k1(ctx, d, g, dj, (int*)d.counters.p + gi, (uint32_t*)d.dirs.p,
-                                             g.max_dir_words, (uint32_t*)d.ops.p, res);
+        const DevJob* dj = (const DevJob*)sl.jobs.p + g.job_off;
+        const int rc = g.lg > 32 ? launch_k2(ctx, d, sl.stream, g, dj, (int*)sl.counters.p + gi, (uint32_t*)sl.dirs.p,
+                                             g.max_dir_words, (uint32_t*)sl.ops.p, res)
+                                 : launch_k1(ctx, d, sl.stream, g, dj, (int*)sl.counters.p + gi, (uint32_t*)sl.dirs.p,
+                                             g.max_dir_words, (uint32_t*)sl.ops.p, res);
         if (rc) return rc;
       } else {
         SeqStore st{(const uint32_t*)d.packed.p, (const uint32_t*)d.nmask.p};
-        generic_kernel<<<g.grid, 64, 0, d.stream>>>((const GenJob*)d.gjobs.p + g.job_off, (int)g.job_idx.size(), st,
-                                                    (int64_t*)d.grows.p, (uint32_t*)d.gdirs.p, (uint32_t*)d.ops.p, res);
+        generic_kernel<<<g.grid, 64, 0, sl.stream>>>((const GenJob*)sl.gjobs.p + g.job_off, (int)g.job_idx.size(), st,
+                                                     (int64_t*)sl.grows.p, (uint32_t*)sl.gdirs.p, (uint32_t*)sl.ops.p, res);
         CU(cudaGetLastError());
       }
       pl->launches++;
     }
-    CU(cudaEventRecord(d.ev1, d.stream));
+    CU(cudaEventRecord(sl.ev1, sl.stream));
   }
   pl->ran = true;
   return GAMX_OK;
@@ -1119,9 +1422,10 @@ static int plan_sync_locked(gamx_plan* pl) {
   for (DevPlan& dp : pl->dps) {
     if (dp.n_jobs == 0) continue;
     Device& d = ctx->devs[dp.dev];
+    Slot& sl = d.s[pl->slot];
     CU(cudaSetDevice(d.id));
-    CU(cudaStreamSynchronize(d.stream));
-    if (pl->ran) CU(cudaEventElapsedTime(&dp.last_ms, d.ev0, d.ev1));
+    CU(cudaStreamSynchronize(sl.stream));
+    if (pl->ran) CU(cudaEventElapsedTime(&dp.last_ms, sl.ev0, sl.ev1));
   }
   return GAMX_OK;
 }
@@ -1132,29 +1436,33 @@ int gamx_plan_sync(gamx_plan* pl) {
   return plan_sync_locked(pl);
 }
 
-static int plan_fetch_locked(gamx_plan* pl, gamx_result* results, uint8_t* ops_buf, uint64_t ops_cap) {
+// enqueues the device -> host copies of a plan's results (and ops) on its slot's stream
+static int plan_fetch_enqueue(gamx_plan* pl) {
   gamx_ctx* ctx = pl->ctx;
-  if (!results && pl->n) return GAMX_ERR_INVALID;
-  if (pl->ops_total > 0 && (!ops_buf || ops_cap < pl->ops_total)) {
-    ctx->err = "ops buffer too small: need " + std::to_string(pl->ops_total) + " ops";
-    return GAMX_ERR_OPS_CAPACITY;
-  }
   for (DevPlan& dp : pl->dps) {
     if (dp.n_jobs == 0) continue;
     Device& d = ctx->devs[dp.dev];
+    Slot& sl = d.s[pl->slot];
     CU(cudaSetDevice(d.id));
-    CU(cudaMemcpyAsync(d.h_results.p, d.results.p, (size_t)dp.n_jobs * sizeof(DevResult), cudaMemcpyDeviceToHost, d.stream));
+    CU(cudaMemcpyAsync(sl.h_results.p, sl.results.p, (size_t)dp.n_jobs * sizeof(DevResult), cudaMemcpyDeviceToHost, sl.stream));
     if (dp.ops_words) {
-      if (int rc = ensure_pin(ctx, d.h_ops, dp.ops_words * 4)) return rc;
-      CU(cudaMemcpyAsync(d.h_ops.p, d.ops.p, dp.ops_words * 4, cudaMemcpyDeviceToHost, d.stream));
+      if (int rc = ensure_pin(ctx, sl.h_ops, dp.ops_words * 4)) return rc;
+      CU(cudaMemcpyAsync(sl.h_ops.p, sl.ops.p, dp.ops_words * 4, cudaMemcpyDeviceToHost, sl.stream));
     }
   }
+  return GAMX_OK;
+}
+
+// waits for the copies and converts the device records into the caller's gamx_result array
+static int plan_fetch_finish(gamx_plan* pl, gamx_result* results, uint8_t* ops_buf) {
+  gamx_ctx* ctx = pl->ctx;
   for (DevPlan& dp : pl->dps) {
     if (dp.n_jobs == 0) continue;
     Device& d = ctx->devs[dp.dev];
+    Slot& sl = d.s[pl->slot];
     CU(cudaSetDevice(d.id));
-    CU(cudaStreamSynchronize(d.stream));
-    if (dp.ops_words) memcpy(ops_buf + dp.ops_base / 4, d.h_ops.p, dp.ops_words * 4);
+    CU(cudaStreamSynchronize(sl.stream));
+    if (dp.ops_words) memcpy(ops_buf + dp.ops_base / 4, sl.h_ops.p, dp.ops_words * 4);
   }
   parallel_for(pl->n, [&](uint64_t b, uint64_t e) {
     for (uint64_t i = b; i < e; i++) {
@@ -1163,7 +1471,7 @@ static int plan_fetch_locked(gamx_plan* pl, gamx_result* results, uint8_t* ops_b
       uint64_t base = 0;
       if (pl->job_dev[i] >= 0) {
         const DevPlan& dp = pl->dps[pl->job_dev[i]];
-        dr = (const DevResult*)ctx->devs[dp.dev].h_results.p + pl->job_res[i];
+        dr = (const DevResult*)ctx->devs[dp.dev].s[pl->slot].h_results.p + pl->job_res[i];
         base = dp.ops_base;
       }
       finalize_result(P, dr, pl->modes[i], &results[i]);
@@ -1171,6 +1479,17 @@ static int plan_fetch_locked(gamx_plan* pl, gamx_result* results, uint8_t* ops_b
     }
   });
   return GAMX_OK;
+}
+
+static int plan_fetch_locked(gamx_plan* pl, gamx_result* results, uint8_t* ops_buf, uint64_t ops_cap) {
+  gamx_ctx* ctx = pl->ctx;
+  if (!results && pl->n) return GAMX_ERR_INVALID;
+  if (pl->ops_total > 0 && (!ops_buf || ops_cap < pl->ops_total)) {
+    ctx->err = "ops buffer too small: need " + std::to_string(pl->ops_total) + " ops";
+    return GAMX_ERR_OPS_CAPACITY;
+  }
+  if (int rc = plan_fetch_enqueue(pl)) return rc;
+  return plan_fetch_finish(pl, results, ops_buf);
 }
 
 int gamx_plan_fetch(gamx_plan* pl, gamx_result* results, uint8_t* ops_buf, uint64_t ops_cap) {
@@ -1190,6 +1509,109 @@ uint64_t gamx_plan_cells(const gamx_plan* pl) { return pl ? pl->cells : 0; }
 uint64_t gamx_plan_kernel_launches(const gamx_plan* pl) { return pl ? pl->launches : 0; }
 void gamx_plan_destroy(gamx_plan* pl) { delete pl; }
 
+// Pipelined form of gamx_align_batch for large batches without edit strings: the batch is cut into
+// chunks in the caller's order; a helper thread prepares chunk c+1 (guards, classification,
+// descriptors) while the main thread uploads and launches chunk c on slot c & 1 and converts the
+// results of chunk c-2.  Each chunk's kernel is stream-ordered behind the contig upload pieces it
+// needs only, so with gamx_add_contigs_async the sequence upload, the alignment kernels, the result
+// copies and the host work all overlap.
+static int align_batch_pipelined(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_result* results, uint64_t chunk) {
+  // chunk boundaries: two short chunks first, so that the device starts early
+  std::vector<uint64_t> lo_of;
+  for (uint64_t at = 0, k = 0; at < n; k++) {
+    lo_of.push_back(at);
+    at += k == 0 ? std::max<uint64_t>(chunk / 4, 1) : k == 1 ? std::max<uint64_t>(chunk / 2, 1) : chunk;
+  }
+  const uint64_t nchunks = lo_of.size();
+  lo_of.push_back(n);
+  struct Built { gamx_plan* pl = nullptr; int rc = 0; };
+  static const bool timing = getenv("GAMX_TIMING") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
+  // producer: prepares the chunks in order, at most kAhead chunks ahead of the consumer
+  constexpr size_t kAhead = 3;
+  std::mutex qm;
+  std::condition_variable qcv;
+  std::deque<Built> queue;
+  bool stop = false;
+  double t_build = 0;
+  std::thread producer([&] {
+    for (uint64_t c = 0; c < nchunks; c++) {
+      {
+        std::unique_lock<std::mutex> lk(qm);
+        qcv.wait(lk, [&] { return queue.size() < kAhead || stop; });
+        if (stop) return;
+      }
+      const auto t0 = now();
+      Built b;
+      const uint64_t lo = lo_of[c], hi = lo_of[c + 1];
+      b.rc = plan_build(ctx, jobs + lo, hi - lo, &b.pl);
+      t_build += ms(t0, now());
+      std::lock_guard<std::mutex> lk(qm);
+      queue.push_back(b);
+      qcv.notify_all();
+    }
+  });
+  std::vector<gamx_plan*> live(nchunks, nullptr);
+  int rc = GAMX_OK;
+  auto finish = [&](uint64_t c) {
+    if (!live[c]) return;
+    if (!rc) rc = plan_fetch_finish(live[c], results + lo_of[c], nullptr);
+    delete live[c];
+    live[c] = nullptr;
+  };
+  double t_fin = 0, t_up = 0, t_run = 0, t_wait = 0;
+  size_t prev_max = 0;
+  for (uint64_t c = 0; c < nchunks && !rc; c++) {
+    const auto t0 = now();
+    Built cur;
+    {
+      std::unique_lock<std::mutex> lk(qm);
+      qcv.wait(lk, [&] { return !queue.empty(); });
+      cur = queue.front();
+      queue.pop_front();
+      qcv.notify_all();
+    }
+    const auto t1 = now();
+    if (c >= 2) finish(c - 2);  // frees slot c & 1
+    const auto t2 = now();
+    if (!rc && cur.rc) { rc = cur.rc; if (cur.pl) ctx->err = cur.pl->err; }
+    auto t3 = t2;
+    if (!rc) {
+      cur.pl->slot = (int)(c & 1);
+      rc = plan_upload(cur.pl);
+      t3 = now();
+      if (!rc) rc = plan_run_locked(cur.pl);
+      if (!rc) rc = plan_fetch_enqueue(cur.pl);
+      live[c] = cur.pl;
+      // keep the copy engine busy: the upload pieces the next chunk will probably need (contig ids
+      // usually grow with the job index) start crossing PCIe now
+      const size_t mx = cur.pl->max_contig;
+      if (!rc && mx > prev_max) rc = upload_advance(ctx, mx + (mx - prev_max));
+      prev_max = std::max(prev_max, mx);
+    } else {
+      delete cur.pl;
+    }
+    const auto t4 = now();
+    t_wait += ms(t0, t1); t_fin += ms(t1, t2); t_up += ms(t2, t3); t_run += ms(t3, t4);
+  }
+  {
+    std::lock_guard<std::mutex> lk(qm);
+    stop = true;
+    qcv.notify_all();
+  }
+  producer.join();
+  for (Built& b : queue) delete b.pl;
+  for (uint64_t c = 0; c < nchunks; c++) finish(c);
+  if (!rc) rc = upload_advance(ctx, SIZE_MAX);  // contigs no job referred to still have to arrive
+  if (timing)
+    fprintf(stderr, "[gamx] pipelined: build %.1f ms (producer thread), waiting for it %.1f, finish %.1f, upload %.1f, run+enqueue %.1f\n",
+            t_build, t_wait, t_fin, t_up, t_run);
+  return rc;
+}
+
 int gamx_align_batch(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_result* results, uint8_t* ops_buf,
                      uint64_t ops_cap) {
   if (!ctx || (!jobs && n) || (!results && n)) return GAMX_ERR_INVALID;
@@ -1200,8 +1622,22 @@ int gamx_align_batch(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_resul
     return std::chrono::duration<double, std::milli>(b - a).count();
   };
   const auto t0 = now();
+  // large batches that return no edit strings are pipelined in chunks (GAMX_PIPELINE_CHUNK jobs,
+  // 0 disables); FULL-mode batches need one ops buffer per device and take the single-plan path
+  const uint64_t chunk_cfg = ctx->pipeline_chunk;
+  if (chunk_cfg && n >= 2 * chunk_cfg) {
+    bool any_full = false;
+    for (uint64_t i = 0; i < n && !any_full; i++) any_full = jobs[i].mode == GAMX_MODE_FULL;
+    if (!any_full) {
+      if (int rc = flush_pending(ctx)) return rc;
+      const int rc = align_batch_pipelined(ctx, jobs, n, results, chunk_cfg);
+      if (timing) fprintf(stderr, "[gamx] align_batch n=%llu pipelined in chunks of %llu: %.1f ms\n", (unsigned long long)n,
+                          (unsigned long long)chunk_cfg, ms(t0, now()));
+      return rc;
+    }
+  }
   gamx_plan* pl = nullptr;
-  int rc = plan_build(ctx, jobs, n, &pl);
+  int rc = plan_build_checked(ctx, jobs, n, &pl);
   if (rc) return rc;
   if (pl->ops_total > 0 && (!ops_buf || ops_cap < pl->ops_total)) {
     ctx->err = "ops buffer too small: need " + std::to_string(pl->ops_total) + " ops";
@@ -1249,6 +1685,7 @@ int gamx_find_hits_batch(gamx_ctx* ctx, const gamx_hits_job* jobs, uint64_t n, g
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (n >= (1ull << 22)) { ctx->err = "at most 2^22 findHits jobs per batch"; return GAMX_ERR_INVALID; }
   if (int rc = flush_pending(ctx)) return rc;
+  if (int rc = store_ready(ctx, ctx->devs[0], ctx->devs[0].stream, SIZE_MAX)) return rc;
   // guards of ablast.cc:47-53 on the host; surviving jobs go to the first device
   std::vector<HitsJob> hj;
   std::vector<uint32_t> idx;

@@ -152,8 +152,10 @@ GAMX_API int64_t gamx_add_contig_ascii(gamx_ctx* ctx, const char* seq, uint64_t 
 GAMX_API int64_t gamx_add_contigs(gamx_ctx* ctx, const uint8_t* codes, const uint64_t* lengths, uint64_t n);
 /* Same, but only enqueues the copies and the pack kernel on the devices' streams and returns: the
  * upload then overlaps the host-side planning of the next gamx_align_batch, which is stream-ordered
- * behind it.  `codes` must be PINNED host memory and must stay valid and unchanged until that batch
- * (or any other synchronising call of this context) has returned. */
+ * behind it.  The copy proceeds in pieces of ~32 MB that are enqueued as the batches need them, so a
+ * pipelined gamx_align_batch starts computing on the first contigs while later ones still cross PCIe.
+ * `codes` must be PINNED host memory and must stay valid and unchanged until that batch (or any
+ * other synchronising call of this context) has returned. */
 GAMX_API int64_t gamx_add_contigs_async(gamx_ctx* ctx, const uint8_t* codes, const uint64_t* lengths, uint64_t n);
 GAMX_API uint64_t gamx_contig_length(const gamx_ctx* ctx, uint32_t id);
 GAMX_API int gamx_clear_contigs(gamx_ctx* ctx);
@@ -177,6 +179,14 @@ GAMX_API void gamx_unpack_ops(const uint8_t* ops_buf, uint64_t ops_offset, uint6
  * (op in the low 2 bits, length in the upper 30 of each uint32), returns the number of runs. */
 GAMX_API uint64_t gamx_cigar_rle(const uint8_t* ops_buf, uint64_t ops_offset, uint64_t n_ops,
                         uint32_t* runs, uint64_t cap);
+
+/* gamx_align_batch pipelines large batches that return no edit strings (no FULL-mode job): the batch is
+ * cut into chunks of `jobs_per_chunk` jobs in the caller's order; while chunk c computes, chunk c+1 is
+ * prepared and uploaded and chunk c-1 is read back, and every chunk waits only for the contig upload
+ * pieces (gamx_add_contigs_async) its own jobs refer to.  Batches shorter than two chunks take the
+ * single-launch path.  0 disables pipelining.  Default 65536 (environment GAMX_PIPELINE_CHUNK); the
+ * first two chunks are a quarter and a half of that so that the device starts early. */
+GAMX_API int gamx_set_pipeline_chunk(gamx_ctx* ctx, uint64_t jobs_per_chunk);
 
 /* ---- device-resident (pre-staged) batches: the kernel-only timing path -------------- */
 

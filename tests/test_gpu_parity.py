@@ -326,3 +326,61 @@ def test_find_hits_matches_oracle(ctx):
     r = ctx.find_hits_batch(j)[0]
     want, mc = rst.find_hits(a, w[0], w[1], b, w[2], w[3])
     assert (r["n_hits"], r["first_hit"], r["last_hit"]) == (len(want), want[0], want[-1])
+
+
+def test_pipelined_batch_matches_single_launch_and_oracle():
+    """The chunked, pipelined gamx_align_batch (asynchronous piece-wise contig upload from pinned
+    memory, two slots/streams, helper-thread planning) returns exactly what the single-launch path
+    returns, and both agree with the oracle; includes early-exit and generic-kernel jobs."""
+    import torch
+    rng = np.random.default_rng(11)
+    n = 3000
+    a, al, b, bl = gen.bulk_pairs(rng, n, 0, div=0.03, len_lo=150, len_hi=700)
+    # chunk-interleaved contig order [A chunk][B chunk]... as bench.py's end-to-end leg uploads it
+    m = 256
+    ao = np.concatenate([[0], np.cumsum(al)]).astype(np.int64)
+    bo = np.concatenate([[0], np.cumsum(bl)]).astype(np.int64)
+    host = torch.empty(int(ao[-1] + bo[-1]), dtype=torch.uint8, pin_memory=True)
+    hv = host.numpy()
+    lengths, a_id, b_id = [], np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+    pos = cid = 0
+    for lo in range(0, n, m):
+        hi = min(n, lo + m)
+        for src, off, ln, ids in ((a, ao, al, a_id), (b, bo, bl, b_id)):
+            seg = src[off[lo]:off[hi]]
+            hv[pos:pos + len(seg)] = seg
+            pos += len(seg)
+            lengths.extend(ln[lo:hi].tolist())
+            ids[lo:hi] = np.arange(cid, cid + hi - lo)
+            cid += hi - lo
+    jobs = g.make_jobs(n)
+    jobs["a_id"], jobs["b_id"] = a_id, b_id
+    jobs["end_a"], jobs["end_b"] = al - 1, bl - 1
+    jobs["band"] = rng.choice([16, 64, 150], size=n)
+    jobs["force_end"] = rng.integers(0, 8, size=n) == 0
+    jobs["mode"] = np.where(rng.integers(0, 4, size=n) == 0, capi.MODE_SCORE, capi.MODE_ENDPOINTS)
+    jobs["end_b"][5] = 0; jobs["begin_b"][5] = 3     # empty (end_b < begin_b)
+    jobs["gap"][9] = -3                               # generic kernel
+    import os
+    os.environ["GAMX_UPLOAD_PIECE_BYTES"] = "200000"  # several upload pieces even at this size (read by gamx_create)
+    c = g.Context(devices=[0])
+    del os.environ["GAMX_UPLOAD_PIECE_BYTES"]
+    try:
+        c.set_pipeline_chunk(0)
+        c.add_contigs(host.data_ptr(), np.array(lengths, dtype=np.uint64))
+        ref, _ = c.align_batch(jobs)
+        for chunk in (128, 1000):
+            c.clear_contigs()
+            c.set_pipeline_chunk(chunk)
+            c.add_contigs(host.data_ptr(), np.array(lengths, dtype=np.uint64), async_upload=True)
+            got, _ = c.align_batch(jobs)
+            assert got.tobytes() == ref.tobytes(), chunk
+    finally:
+        c.close()
+    assert int(ref["status"][5]) == capi.JOB_EMPTY
+    for k in list(range(0, n, 97)) + [9]:
+        A, B = a[ao[k]:ao[k + 1]], b[bo[k]:bo[k + 1]]
+        case = dict(a=A, b=B, begin_a=0, end_a=len(A) - 1, begin_b=int(jobs["begin_b"][k]), end_b=int(jobs["end_b"][k]),
+                    band=int(jobs["band"][k]), gap=int(jobs["gap"][k]), force_start=False, force_end=bool(jobs["force_end"][k]))
+        mode = int(jobs["mode"][k])
+        assert result_to_expect(None, ref[k], None, mode) == project(oracle_expect(case), mode), k

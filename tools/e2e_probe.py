@@ -11,10 +11,17 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 rng = np.random.default_rng(1)
 a, al, b, bl = gen.bulk_pairs(rng, n, 1000)
 host = torch.empty(len(a) + len(b), dtype=torch.uint8, pin_memory=True)
-hv = host.numpy(); hv[:len(a)] = a; hv[len(a):] = b
-lengths = np.concatenate([al, bl]).astype(np.uint64)
+hv = host.numpy()
+ao = np.concatenate([[0], np.cumsum(al)]).astype(np.int64); bo = np.concatenate([[0], np.cumsum(bl)]).astype(np.int64)
+lengths = np.empty(2 * n, dtype=np.uint64); a_id = np.empty(n, np.uint32); b_id = np.empty(n, np.uint32)
+pos = cid = 0
+for lo in range(0, n, 16384):  # blocks of pairs: [a-contigs][b-contigs], like bench.py
+    hi = min(n, lo + 16384)
+    for src, off, ln, ids in ((a, ao, al, a_id), (b, bo, bl, b_id)):
+        seg = src[off[lo]:off[hi]]; hv[pos:pos + len(seg)] = seg; pos += len(seg)
+        lengths[cid:cid + hi - lo] = ln[lo:hi]; ids[lo:hi] = np.arange(cid, cid + hi - lo); cid += hi - lo
 jobs = g.make_jobs(n)
-jobs["a_id"] = np.arange(n); jobs["b_id"] = np.arange(n, 2 * n)
+jobs["a_id"] = a_id; jobs["b_id"] = b_id
 jobs["end_a"] = al - 1; jobs["end_b"] = bl - 1; jobs["band"] = 64; jobs["mode"] = 1
 ctx = g.Context(devices=[0])
 for it in range(3):
