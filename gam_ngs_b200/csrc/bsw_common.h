@@ -66,6 +66,64 @@ GAMX_HD uint32_t load_code(const SeqStore& s, const SeqView& v, int64_t p) {
   return n ? (uint32_t)kCodeN : c;
 }
 
+// 64-bit funnel shift right: the low 32 bits of ((hi:lo) >> s), 0 <= s < 32
+GAMX_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(lo, hi, s);
+#else
+  return (uint32_t)((((uint64_t)hi << 32) | lo) >> (s & 31u));
+#endif
+}
+
+// Bulk form of load_code for tile staging: the 16 view positions p .. p+15 with four word loads
+// instead of 32.  *codes: 2-bit field q = base code of position p+q (NOT yet complemented; garbage
+// where the position is N or outside [0, len)), *nflags: bit q set when position p+q is N.  Only words
+// that hold a position of [0, len) are touched (len >= 1), so nothing is read outside the contig.
+GAMX_HD void load_codes16(const SeqStore& s, const SeqView& v, int64_t p, int64_t len, uint32_t* codes, uint32_t* nflags) {
+  const bool fwd = v.dir > 0;
+  const int64_t idx0 = fwd ? v.origin + p : v.origin - p - 15;               // lowest store index of the run
+  const int64_t imin = fwd ? v.origin : v.origin - (len - 1);
+  const int64_t imax = fwd ? v.origin + (len - 1) : v.origin;
+  const int64_t wmin = imin >> 4, wmax = imax >> 4, mmin = imin >> 5, mmax = imax >> 5;
+  int64_t w0 = idx0 >> 4, w1 = w0 + 1, m0 = idx0 >> 5, m1 = m0 + 1;
+  w0 = w0 < wmin ? wmin : (w0 > wmax ? wmax : w0);
+  w1 = w1 < wmin ? wmin : (w1 > wmax ? wmax : w1);
+  m0 = m0 < mmin ? mmin : (m0 > mmax ? mmax : m0);
+  m1 = m1 < mmin ? mmin : (m1 > mmax ? mmax : m1);
+  const uint32_t pa = s.packed[w0], pb = s.packed[w1], na = s.nmask[m0], nb = s.nmask[m1];
+  uint32_t c = funnel_r(pa, pb, 2u * (uint32_t)(idx0 & 15));
+  uint32_t n = funnel_r(na, nb, (uint32_t)(idx0 & 31)) & 0xffffu;
+  if (!fwd) {  // the run was fetched in ascending store order = descending view order
+#if defined(__CUDA_ARCH__)
+    const uint32_t b = __brev(c);
+    n = __brev(n) >> 16;
+#else
+    uint32_t b = c;
+    b = ((b >> 1) & 0x55555555u) | ((b & 0x55555555u) << 1);
+    b = ((b >> 2) & 0x33333333u) | ((b & 0x33333333u) << 2);
+    b = ((b >> 4) & 0x0f0f0f0fu) | ((b & 0x0f0f0f0fu) << 4);
+    b = ((b >> 8) & 0x00ff00ffu) | ((b & 0x00ff00ffu) << 8);
+    b = (b >> 16) | (b << 16);
+    uint32_t m = n;
+    m = ((m >> 1) & 0x5555u) | ((m & 0x5555u) << 1);
+    m = ((m >> 2) & 0x3333u) | ((m & 0x3333u) << 2);
+    m = ((m >> 4) & 0x0f0fu) | ((m & 0x0f0fu) << 4);
+    n = ((m >> 8) & 0x00ffu) | ((m & 0x00ffu) << 8);
+#endif
+    c = ((b >> 1) & 0x55555555u) | ((b & 0x55555555u) << 1);  // bit-reversed pairs back in bit order
+  }
+  *codes = c;
+  *nflags = n;
+}
+
+// spreads eight 2-bit fields (16 bits) to eight nibbles (32 bits)
+GAMX_HD uint32_t spread2to4(uint32_t x) {
+  x = (x | (x << 8)) & 0x00ff00ffu;
+  x = (x | (x << 4)) & 0x0f0f0f0fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  return x;
+}
+
 // Substitution score of the reference's 5x5 matrix extended with the pad symbol.
 GAMX_HD int subst_score(uint32_t a, uint32_t b) {
   if (a == (uint32_t)kCodePad || b == (uint32_t)kCodePad) return 0;

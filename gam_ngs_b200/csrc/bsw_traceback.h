@@ -8,7 +8,7 @@
 //
 // Two walkers:
 //   traceback_walk     one cell per iteration, any direction layout (generic kernel).
-//   k1_traceback<C>    K1 layout: a direction word holds 16 consecutive rows of one band
+//   k1_traceback       K1 layout: a direction word holds 16 consecutive rows of one band
 //                      column, so a run of DIAG moves (the common case: ~98% of the path at
 //                      2% divergence) is consumed 16 cells per iteration with bit tricks and
 //                      its ops are emitted as one bulk insert.
@@ -128,9 +128,24 @@ GAMX_HD void traceback_walk(const DirAt& dir_at, int end_i, int end_j, int64_t p
 
 // K1 layout: word ((t>>4)*C + k)*LG + l holds the tags of band column j = l*C+k for the 16
 // steps t = x + l of one step block, the tag of step offset o = t&15 at bits [2*(15-o), +2).
-template <int C, int LG>
-GAMX_HD void k1_traceback(const uint32_t* dirs, int end_i, int end_j, int p0, bool want_ops,
-                          uint32_t* ops_words, uint32_t ops_cap, DevResult& R) {
+// C (stripe width) and LG (lanes per pair) are the geometry of the kernel that stored the words.
+// The walk is a chain of dependent loads, so it is run one job per THREAD by the traceback kernel
+// (thousands of independent walks in flight) rather than by a lane of the warp that filled the band.
+//
+// Fetch: uint32_t operator()(int blk, int k, int l) -> the word of step block blk of band column
+// (lane l, slot k).  DirectFetch loads it; the warp-per-job traceback kernel passes a fetcher whose
+// lanes load 32 consecutive step blocks of the column at once (one round trip per 512 rows).
+struct DirectFetch {
+  const uint32_t* dirs;
+  int C, LG;
+  GAMX_HD uint32_t operator()(int blk, int k, int l) const {
+    return dirs[((uint32_t)blk * (uint32_t)C + (uint32_t)k) * (uint32_t)LG + (uint32_t)l];
+  }
+};
+
+template <class Fetch>
+GAMX_HD void k1_traceback_t(Fetch& fetch, int C, int end_i, int end_j, int p0, bool want_ops,
+                            uint32_t* ops_words, uint32_t ops_cap, DevResult& R) {
   OpsWriter ow;
   ow.init(ops_words, ops_cap, want_ops);
   WalkStats s;
@@ -139,7 +154,7 @@ GAMX_HD void k1_traceback(const uint32_t* dirs, int end_i, int end_j, int p0, bo
   int l = y / C, k = y - l * C;
   while (x >= 0 && y >= 0 && pos >= 0) {
     const int t = x + l, o = t & 15;
-    const uint32_t w = dirs[((uint32_t)(t >> 4) * C + k) * LG + l];
+    const uint32_t w = fetch(t >> 4, k, l);
     const uint32_t ws = w >> (2 * (15 - o));  // pair p = tag of row x-p (p <= o)
     const uint32_t tag = ws & 3u;
     if (tag >= (uint32_t)kTagDiagMis) {
@@ -174,6 +189,12 @@ GAMX_HD void k1_traceback(const uint32_t* dirs, int end_i, int end_j, int p0, bo
   }
   ow.finish();
   s.store(R, (int64_t)pos, x);
+}
+
+GAMX_HD void k1_traceback(const uint32_t* dirs, int C, int LG, int end_i, int end_j, int p0, bool want_ops,
+                          uint32_t* ops_words, uint32_t ops_cap, DevResult& R) {
+  DirectFetch f{dirs, C, LG};
+  k1_traceback_t(f, C, end_i, end_j, p0, want_ops, ops_words, ops_cap, R);
 }
 
 }  // namespace gamx

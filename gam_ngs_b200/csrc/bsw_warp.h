@@ -26,22 +26,24 @@
 //
 // Instruction mix per cell (the ALU pipe is the binding resource):
 //   ALU pipe : VIADDMNMX  m = max(up + U, left)          FMA pipe : IDP.4A  d = diag + Cd
-//              VIMNMX     v = max(d, m)                             IMAD    accV = 4*accV + v
-//              LOP3       h = v & ~3                                IMAD    accH = 4*accH + h
+//              VIMNMX     v = max(d, m)                             IMAD    acc = 4*acc + v
+//              LOP3       h = v & ~3                                IMAD    acc = acc + (-1)*h
 //              1/4 PRMT   four Cd bytes at once
 // Cd comes from an 8-byte per-row table (indexed by the a-base; N and padding need no branch):
 // the a-bases of the tile sit in shared memory as overlapping 4-nibble windows, so one LDS.U16 is
 // the PRMT selector of four consecutive slots and one PRMT yields their four Cd bytes; IDP.4A with
-// a one-hot multiplier adds byte k to the diagonal.  accV - accH is the lane's direction word (16
-// tags).  Score-only (DIRS=false) keeps VIADDMNMX + VIMNMX + 1/4 PRMT on the ALU pipe.
+// a one-hot multiplier adds byte k to the diagonal.  acc is the lane's direction word (16 tags, the
+// oldest in the top bit pair).  Score-only (DIRS=false) keeps VIADDMNMX + VIMNMX + 1/4 PRMT on the ALU pipe.
 //
 // The first row (.cc:112-132: a running maximum that takes its left neighbour without the gap
 // penalty) is computed for all lanes at once by a prefix-max scan before the step loop.  Steps
-// then run in unrolled groups of UF in two variants (a small code footprint matters: the kernel is
-// issue-bound and the instruction cache is shared by warps in different phases):
-//   FAST  steady state: every lane on a row in [1, X-1], nothing to latch
-//   SLOW  pipeline fill / drain, tile and job tails: lanes outside their row range keep their
-//         registers; also latches the "last column" cells (pos == end_a, .cc:197-212)
+// then run in two variants (a small code footprint matters: the kernel is issue-bound and the
+// instruction cache is shared by warps in different phases):
+//   FAST  steady state, unrolled groups of UF steps starting at multiples of UF: every lane on a row
+//         in [1, X-1], nothing to latch; the only per-group overhead is two shared-memory pointer
+//         bumps, the group counter and the flush test
+//   SLOW  one step at a time: pipeline fill / drain, tile and job tails: lanes outside their row range
+//         keep their registers; also latches the "last column" cells (pos == end_a, .cc:197-212)
 #pragma once
 #include "bsw_common.h"
 #include "bsw_traceback.h"
@@ -52,11 +54,17 @@ constexpr int kTileSteps = 128;  // steps per shared-memory sequence tile
 constexpr int kMaxC = 18;        // widest lane stripe: band <= (32*18-1)/2 = 287
 
 GAMX_HD constexpr bool stripe_supported(int c) { return c >= 2 && c <= kMaxC; }
-// steps per unrolled group: keeps the steady-state loop body around 150-350 instructions
-GAMX_HD constexpr int unroll_of(int c) { return c <= 6 ? 4 : (c <= 12 ? 3 : 2); }
+// steps per unrolled steady-state group (divides 16, so that a direction flush falls on a group end):
+// keeps the loop body around 150-350 instructions
+#ifndef GAMX_UF4_MAX_C
+#define GAMX_UF4_MAX_C 12
+#endif
+GAMX_HD constexpr int unroll_of(int c) { return c <= GAMX_UF4_MAX_C ? 4 : 2; }
+
+struct alignas(16) Quad { uint32_t v[4]; };
 
 template <int C, int LG>
-struct GroupSmem {
+struct alignas(16) GroupSmem {
   uint64_t btab[kTileSteps + LG];            // b-rows of the tile as 8-byte Cd tables
   uint16_t asel[kTileSteps + LG * C + 8];    // a-bases as 4-nibble windows: codes of positions p..p+3
   int cap[C * LG];                           // latched "last column" cells, [slot][lane]
@@ -84,7 +92,9 @@ struct EndBest {
 // One warp: 32/LG jobs.  Jp / out are per-lane arguments, uniform within a group of LG lanes:
 // the group's job (null: idle group) and its result slot.  dirs: the warp's direction scratch,
 // group g uses dirs + g*group_stride.
-template <int C, int LG, bool DIRS, class W>
+// TB: walk the stored directions right here (group leader lane).  The product kernels pass false: they
+// only record the end cell, and the traceback kernel (one job per thread) finishes the results.
+template <int C, int LG, bool DIRS, bool TB = true, class W>
 GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<C, LG>& wsm, uint32_t* dirs,
                         uint64_t group_stride, uint32_t* ops_buf, DevResult* out) {
   static_assert(stripe_supported(C), "lane stripe width");
@@ -133,44 +143,79 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
   const uint32_t cdZ = ((uint32_t)alpha << SH) | tagM;  // N against anything: score 0, MATCH op
   const uint32_t cdP = ((uint32_t)alpha << SH) | tagX;  // padding: score 0
 
-  // Direction words are accumulated as the difference of two multiply-add chains (both on the
-  // FMA pipe, leaving the ALU pipe to the DP): accV = 4*accV + v, accH = 4*accH + (v & ~3);
-  // accV - accH (mod 2^32) = the last 16 tags, oldest in the top bit pair.
+  // Direction words are accumulated with two multiply-adds (both on the FMA pipe, leaving the ALU
+  // pipe to the DP): acc = 4*acc + v, acc += neg1 * (v & ~3), i.e. acc = 4*acc + tag (mod 2^32): the
+  // last 16 tags, oldest in the top bit pair.  neg1 is -1 in a register the compiler cannot see
+  // through, so the second one stays a multiply-add instead of becoming an ALU-pipe subtraction.
   int H[C];
-  uint32_t accV[C], accH[C];
+  uint32_t acc[C];
   int U[C];
+  const uint32_t neg1 = (uint32_t)(gap >> 31);  // gap < 0 for every job of this kernel
 #pragma unroll
   for (int k = 0; k < C; k++) {
-    H[k] = 0; accV[k] = 0; accH[k] = 0;
+    H[k] = 0; acc[k] = 0;
     U[k] = (gl == ld && k == kd) ? kBlock : (DIRS ? 1 : 0);
   }
+  const int lneg = gl == 0 ? kNegInf : 0;  // OR-ed into the shuffled left neighbour: band column 0 has none
   const int tcap0 = kc - gl * (C - 1);  // step at which slot 0 holds a "last column" cell (slot k: tcap0 - k)
 
-  // Stages the sequence tile for steps [t0, t0 + kTileSteps): a-bases as 4-nibble windows (every
-  // lane decodes runs of 8 positions + 3 look-ahead), b-rows as 8-byte Cd tables.
+  // Stages the sequence tile for steps [t0, t0 + kTileSteps): a-bases as 4-nibble windows, b-rows as
+  // 8-byte Cd tables.  A lane fetches runs of 16 view positions with four word loads (load_codes16)
+  // and expands them with bit operations; N and out-of-range positions (pad symbol) are patched in a
+  // rare slow path.  Eight windows = one 16-byte store.
 #define GAMX_STAGE_TILE(T0)                                                                           \
   {                                                                                                   \
     w.sync();                                                                                         \
     const int na = kTileSteps + LG * C - (LG - 1) + 3;                                                \
     const int pa0 = p0 + (T0);                                                                        \
     for (int c0 = gl * 8; c0 < na; c0 += LG * 8) {                                                    \
-      uint32_t win = 0;                                                                               \
-      _Pragma("unroll") for (int q = 0; q < 11; q++) {                                                \
-        const int pos = pa0 + c0 + q;                                                                 \
-        const uint32_t code = (live && pos >= 0 && pos < la) ? load_code(store, va, pos) : (uint32_t)kCodePad; \
-        win = (win >> 4) | (code << 12);                                                              \
-        if (q >= 3) sm.asel[c0 + q - 3] = (uint16_t)win;                                              \
+      const int pos0 = pa0 + c0;           /* windows c0..c0+7 need positions pos0 .. pos0+10 */      \
+      uint32_t codes = 0, nfl = 0, valid = 0;                                                         \
+      if (live && pos0 + 10 >= 0 && pos0 < la) {                                                      \
+        load_codes16(store, va, pos0, la, &codes, &nfl);                                              \
+        const int vlo = pos0 < 0 ? -pos0 : 0, vhi = imin(11, la - pos0);                              \
+        valid = ((1u << vhi) - 1u) & ~((1u << vlo) - 1u);                                             \
       }                                                                                               \
+      const uint32_t cx = va.comp * 0x11111111u;                                                      \
+      uint32_t nlo = spread2to4(codes & 0xffffu) ^ cx;                                                \
+      uint32_t nhi = (spread2to4((codes >> 16) & 0x3fu) ^ cx) & 0xfffu;                               \
+      const uint32_t special = (nfl | ~valid) & 0x7ffu;                                               \
+      if (special) {                                                                                  \
+        uint64_t nib = ((uint64_t)nhi << 32) | nlo;                                                   \
+        _Pragma("unroll") for (int q = 0; q < 11; q++) {                                              \
+          if ((special >> q) & 1u) {                                                                  \
+            const uint64_t code = ((valid >> q) & 1u) ? (uint64_t)kCodeN : (uint64_t)kCodePad;        \
+            nib = (nib & ~((uint64_t)0xf << (4 * q))) | (code << (4 * q));                            \
+          }                                                                                           \
+        }                                                                                             \
+        nlo = (uint32_t)nib; nhi = (uint32_t)(nib >> 32);                                             \
+      }                                                                                               \
+      uint32_t ow[4];                                                                                 \
+      _Pragma("unroll") for (int j = 0; j < 4; j++) {                                                 \
+        const uint32_t x = j == 0 ? nlo : funnel_r(nlo, nhi, 8u * j);   /* nibbles 2j .. 2j+7 */      \
+        ow[j] = (x & 0xffffu) | ((x << 12) & 0xffff0000u);               /* windows 2j, 2j+1 */        \
+      }                                                                                               \
+      Quad qv;                                                                                        \
+      qv.v[0] = ow[0]; qv.v[1] = ow[1]; qv.v[2] = ow[2]; qv.v[3] = ow[3];                             \
+      *reinterpret_cast<Quad*>(sm.asel + c0) = qv;    /* c0 % 8 == 0: 16-byte aligned */              \
     }                                                                                                 \
     const int nb = kTileSteps + LG - 1;                                                               \
-    for (int idx = gl; idx < nb; idx += LG) {                                                         \
-      const int i = (T0) - (LG - 1) + idx;                                                            \
-      const uint32_t bc = (live && i >= 0 && i < X) ? load_code(store, vb, i) : (uint32_t)kCodePad;   \
-      uint32_t lo, hi;                                                                                \
-      if (bc < 4u) { lo = (cdX * 0x01010101u) ^ ((cdX ^ cdM) << (8 * bc)); hi = cdZ | (cdP << 8); }   \
-      else if (bc == (uint32_t)kCodeN) { lo = cdZ * 0x01010101u; hi = cdM | (cdP << 8); }             \
-      else { lo = cdP * 0x01010101u; hi = cdP | (cdP << 8); }                                         \
-      sm.btab[idx] = ((uint64_t)hi << 32) | lo;                                                       \
+    for (int r0 = gl * 8; r0 < nb; r0 += LG * 8) {                                                    \
+      const int i0 = (T0) - (LG - 1) + r0;  /* table r0+q is row i0+q */                              \
+      uint32_t codes = 0, nfl = 0, valid = 0;                                                         \
+      if (live && i0 + 7 >= 0 && i0 < X) {                                                            \
+        load_codes16(store, vb, i0, X, &codes, &nfl);                                                 \
+        const int vlo = i0 < 0 ? -i0 : 0, vhi = imin(8, X - i0);                                      \
+        valid = ((1u << vhi) - 1u) & ~((1u << vlo) - 1u);                                             \
+      }                                                                                               \
+      codes ^= vb.comp * 0x5555u;                                                                     \
+      _Pragma("unroll") for (int q = 0; q < 8; q++) {                                                 \
+        const uint32_t bc = (codes >> (2 * q)) & 3u;                                                  \
+        uint32_t lo = (cdX * 0x01010101u) ^ ((cdX ^ cdM) << (8 * bc)), hi = cdZ | (cdP << 8);         \
+        if (!((valid >> q) & 1u)) { lo = cdP * 0x01010101u; hi = cdP | (cdP << 8); }                  \
+        else if ((nfl >> q) & 1u) { lo = cdZ * 0x01010101u; hi = cdM | (cdP << 8); }                  \
+        sm.btab[r0 + q] = ((uint64_t)hi << 32) | lo;                                                  \
+      }                                                                                               \
     }                                                                                                 \
     w.sync();                                                                                         \
   }
@@ -222,60 +267,56 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
         const int h = open ? imax(H[k], in) : H[k];
         v = ((h + beta * j) << SH) | ((DIRS && h == s) ? (sc[k] & 3) : 0);
       }
-      if (DIRS) { accV[k] = (uint32_t)(v & 3); accH[k] = 0; }
+      if (DIRS) acc[k] = (uint32_t)(v & 3);
       H[k] = DIRS ? (v & ~3) : v;
       if (tcap0 - k == gl) sm.cap[k * LG + gl] = H[k];  // "last column" cell in row 0
     }
     if (DIRS && T_total == 1) {  // a single row on a single lane: no step will flush its directions
 #pragma unroll
-      for (int k = 0; k < C; k++) fp[k * LG] = accV[k] << 30;
+      for (int k = 0; k < C; k++) fp[k * LG] = acc[k] << 30;
     }
   }
 
-  // UF unrolled steps starting at step t.  SLOW: lanes whose row is outside [1, X-1] keep their
-  // registers (direction words keep shifting once a lane has started), "last column" cells are
-  // latched, and steps at or beyond `stop` are skipped.
-#define GAMX_STEP_GROUP(SLOW)                                                                         \
+  // The Cd bytes of one step: PA / PB point at the selector windows / row table of that step.
+#define GAMX_LOAD_CD(CD, PA, PB)                                                                      \
   {                                                                                                   \
-    const int dcap = tcap0 - t;                                                                       \
-    _Pragma("unroll") for (int u = 0; u < UF; u++) {                                                  \
-      const int tt = t + u;                                                                           \
-      if (!(SLOW) || tt < stop) {                                                                     \
-        const uint64_t tb = pb[tt];                                                                   \
-        const uint32_t tlo = (uint32_t)tb, thi = (uint32_t)(tb >> 32);                                \
-        uint32_t cd4[NQ];                                                                             \
-        _Pragma("unroll") for (int q = 0; q < NQ; q++) cd4[q] = prmt(tlo, thi, pa[tt + 4 * q]);       \
-        int left = w.shfl_up(H[C - 1], 1, LG);                                                        \
-        if (gl == 0) left = kNegInf;                                                                  \
-        const bool started = !(SLOW) || (tt - gl >= 1);                                               \
-        const bool act = !(SLOW) || (started && tt - gl < X);                                         \
-        int right = 0;                                                                                \
-        _Pragma("unroll") for (int k = 0; k < C; k++) {                                               \
-          const int up = (k == C - 1) ? right : H[(k + 1) % C];                                       \
-          const int d = add_byte(cd4[k / 4], k % 4, H[k]);                                            \
-          const int m = viaddmax(up, U[k], left);                                                     \
-          const int v = imax(d, m);                                                                   \
-          int hc = v;                                                                                 \
-          if (DIRS) {                                                                                 \
-            hc = v & ~3;                                                                              \
-            if (started) {                                                                            \
-              accV[k] = accV[k] * 4u + (uint32_t)v;                                                   \
-              accH[k] = accH[k] * 4u + (uint32_t)hc;                                                  \
-            }                                                                                         \
-          }                                                                                           \
-          if (act) H[k] = hc;                                                                         \
-          if (SLOW) { if (dcap == u + k) sm.cap[k * LG + gl] = H[k]; }                                \
-          left = H[k];                                                                                \
-          if (k == 0) right = w.shfl_down(H[0], 1, LG);                                               \
-        }                                                                                             \
-        if (DIRS && ((tt & 15) == 15 || ((SLOW) && tt == T_total - 1))) {                             \
-          const int sh = (SLOW) ? 2 * (15 - (tt & 15)) : 0;                                           \
-          _Pragma("unroll") for (int k = 0; k < C; k++) fp[k * LG] = (accV[k] - accH[k]) << sh;        \
-          fp += C * LG;                                                                               \
-        }                                                                                             \
+    const uint64_t tb = *(PB);                                                                        \
+    const uint32_t tlo = (uint32_t)tb, thi = (uint32_t)(tb >> 32);                                    \
+    _Pragma("unroll") for (int q = 0; q < NQ; q++) (CD)[q] = prmt(tlo, thi, (PA)[4 * q]);             \
+  }
+  // One step tt with its Cd bytes in CD.  SLOW: lanes whose row is outside [1, X-1] keep their
+  // registers (direction words keep shifting once a lane has started), "last column" cells are
+  // latched and the direction flush is decided per step; the FAST variant leaves the flush to its caller.
+#define GAMX_STEP(SLOW, TT, CD)                                                                       \
+  {                                                                                                   \
+    const int tt = (TT);                                                                              \
+    int left = w.shfl_up(H[C - 1], 1, LG) | lneg;                                                     \
+    const bool started = !(SLOW) || (tt - gl >= 1);                                                   \
+    const bool act = !(SLOW) || (started && tt - gl < X);                                             \
+    const int dcap = tcap0 - tt;  /* the slot that is on a "last column" cell in this step */         \
+    int capv = 0;                                                                                     \
+    int right = 0;                                                                                    \
+    _Pragma("unroll") for (int k = 0; k < C; k++) {                                                   \
+      const int up = (k == C - 1) ? right : H[(k + 1) % C];                                           \
+      const int d = add_byte((CD)[k / 4], k % 4, H[k]);                                               \
+      const int m = viaddmax(up, U[k], left);                                                         \
+      const int v = imax(d, m);                                                                       \
+      int hc = v;                                                                                     \
+      if (DIRS) {                                                                                     \
+        hc = v & ~3;                                                                                  \
+        if (started) acc[k] = (acc[k] * 4u + (uint32_t)v) + neg1 * (uint32_t)hc;                      \
       }                                                                                               \
+      if (act) H[k] = hc;                                                                             \
+      if (SLOW) capv = (dcap == k) ? H[k] : capv;                                                     \
+      left = H[k];                                                                                    \
+      if (k == 0) right = w.shfl_down(H[0], 1, LG);                                                   \
     }                                                                                                 \
-    t += UF;                                                                                          \
+    if ((SLOW) && (unsigned)dcap < (unsigned)C) sm.cap[dcap * LG + gl] = capv;                         \
+    if ((SLOW) && DIRS && ((tt & 15) == 15 || tt == T_total - 1)) {                                   \
+      const int sh = 2 * (15 - (tt & 15));                                                            \
+      _Pragma("unroll") for (int k = 0; k < C; k++) fp[k * LG] = acc[k] << sh;                         \
+      fp += C * LG;                                                                                   \
+    }                                                                                                 \
   }
 
   int t = 1;  // row 0 is done; lane gl starts its row 1 at step gl + 1
@@ -286,14 +327,49 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
     const uint64_t* pb = sm.btab + ((LG - 1) - gl - t0);   // pb[t]: table of row t - gl
     const int stop = imin(t0 + kTileSteps, T_total);       // first step this tile does not cover
     while (t < stop) {
-      const bool fast = (t >= LG) && (t + UF <= stop) && (t + UF - 1 <= x_min - 1) && (t + UF - 1 <= T_total - 2) &&
-                        (t + UF - 1 < win_lo || t > win_hi);
-      if (fast) GAMX_STEP_GROUP(false)
-      else GAMX_STEP_GROUP(true)
+      // steps [t, fast_hi) are steady state: every lane has started (t >= LG) and is on a row < X,
+      // the job's last step (partial flush) is excluded, no lane meets its "last column" cells
+      int fast_hi = imin(stop, imin(x_min, T_total - 1));
+      if (t <= win_hi) fast_hi = imin(fast_hi, win_lo);
+      int nf = (t >= LG && (t & (UF - 1)) == 0) ? (fast_hi - t) / UF : 0;
+      if (nf > 0) {
+        // software pipeline: the shared-memory loads and byte permutes of step t+1 are issued before
+        // the cells of step t, so their latency never sits in front of a step's dependent chain
+        // (the look-ahead of a group's last step reads one entry past the group: inside the arrays,
+        // and overwritten before use when it belongs to the next tile)
+        const uint16_t* pa_t = pa + t;
+        const uint64_t* pb_t = pb + t;
+        uint32_t cdn[NQ];
+        GAMX_LOAD_CD(cdn, pa_t, pb_t)
+        do {
+#pragma unroll
+          for (int u = 0; u < UF; u++) {
+            uint32_t cd4[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; q++) cd4[q] = cdn[q];
+            GAMX_LOAD_CD(cdn, pa_t + u + 1, pb_t + u + 1)
+            GAMX_STEP(false, t + u, cd4)
+          }
+          t += UF; pa_t += UF; pb_t += UF;
+          if (DIRS && (t & 15) == 0) {
+#pragma unroll
+            for (int k = 0; k < C; k++) fp[k * LG] = acc[k];
+            fp += C * LG;
+          }
+        } while (--nf > 0);
+      } else {
+        const int slow_stop = imin(stop, (t & ~(UF - 1)) + UF);  // up to the next group boundary
+        do {
+          uint32_t cd4[NQ];
+          GAMX_LOAD_CD(cd4, pa + t, pb + t)
+          GAMX_STEP(true, t, cd4)
+          t++;
+        } while (t < slow_stop);
+      }
     }
-    if (t > stop) t = stop;  // a SLOW group cut short by the tile end: the skipped steps belong to the next tile
   }
-#undef GAMX_STEP_GROUP
+#undef GAMX_STEP
+#undef GAMX_LOAD_CD
 #undef GAMX_STAGE_TILE
 
   // ---- end-cell selection, .cc:174-212: last row (columns ascending) before last column ----
@@ -342,8 +418,8 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
       R.score = best.val; R.end_i = ei; R.end_j = ej;
       if (p0 + ei + ej >= la) {
         R.status = kStatusOutOfRange;  // first traceback step reads a.at(pos), .cc:231/:265
-      } else if (DIRS && !(Jp->mode & 0x100)) {  // 0x100: debug knob GAMX_DEBUG_SKIP_TRACEBACK
-        k1_traceback<C, LG>(gdirs, ei, ej, p0, (Jp->mode & 0xff) == kModeFull, ops_buf + Jp->ops_word, Jp->ops_cap, R);
+      } else if (DIRS && TB && !(Jp->mode & 0x100)) {  // 0x100: debug knob GAMX_DEBUG_SKIP_TRACEBACK
+        k1_traceback(gdirs, C, LG, ei, ej, p0, (Jp->mode & 0xff) == kModeFull, ops_buf + Jp->ops_word, Jp->ops_cap, R);
         R.ops_start = Jp->ops_word * 16 + Jp->ops_cap - R.n_ops;
       }
     }

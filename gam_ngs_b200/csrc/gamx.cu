@@ -69,8 +69,6 @@ k1_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counter
   __shared__ WarpSmem<C, LG> sm[kWarpsPerBlock];
   DevWarp w;
   const int warp = (int)(threadIdx.x >> 5);
-  const uint64_t slot = (uint64_t)blockIdx.x * kWarpsPerBlock + warp;
-  uint32_t* my_dirs = DIRS ? dirs + slot * (group_stride * G) : nullptr;
   const int grp = w.lane() / LG;
   for (;;) {
     int j = 0;
@@ -79,7 +77,9 @@ k1_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counter
     if (j >= n_jobs) break;
     const int mine = j + grp;  // jobs are sorted by cost: the groups of a warp get similar work
     const DevJob* Jp = mine < n_jobs ? jobs + mine : nullptr;
-    warp_align<C, LG, DIRS>(w, Jp, store, sm[warp], my_dirs, group_stride, ops, results + (mine < n_jobs ? mine : 0));
+    // direction words of job `mine` of this launch: dirs + mine * group_stride (read back by tb_kernel)
+    uint32_t* my_dirs = DIRS ? dirs + (uint64_t)j * group_stride : nullptr;
+    warp_align<C, LG, DIRS, false>(w, Jp, store, sm[warp], my_dirs, group_stride, ops, results + (mine < n_jobs ? mine : 0));
   }
 }
 
@@ -119,14 +119,75 @@ k2_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counter
   __shared__ int xch[2 * LG];
   __shared__ int next_job;
   CtaPolicy<LG> w{xch, 0};
-  uint32_t* my_dirs = DIRS ? dirs + (uint64_t)blockIdx.x * group_stride : nullptr;
   for (;;) {
     if (threadIdx.x == 0) next_job = atomicAdd(counter, 1);
     __syncthreads();
     const int j = next_job;
     __syncthreads();
     if (j >= n_jobs) break;
-    warp_align<C, LG, DIRS>(w, jobs + j, store, sm, my_dirs, group_stride, ops, results + j);
+    uint32_t* my_dirs = DIRS ? dirs + (uint64_t)j * group_stride : nullptr;
+    warp_align<C, LG, DIRS, false>(w, jobs + j, store, sm, my_dirs, group_stride, ops, results + j);
+  }
+}
+
+// Traceback kernel: one job per thread.  The fill kernels (K1/K2 with the direction store) leave the
+// selected end cell in the job's result record and the 2-bit directions of job j of the launch at
+// dirs + j * stride; this kernel walks them (bsw_traceback.h) and completes the record: coordinates,
+// op counts, first/last match and - FULL mode - the edit string.  The walk is a chain of dependent
+// loads, so it wants many independent walks in flight, not a lane of a busy fill warp; its small
+// blocks (64 threads, <= 48 registers) fit beside the resident fill blocks of the next wave.
+constexpr int kTbThreads = 64;
+constexpr int kTbWarpRows = 4096;  // jobs with at least this many rows are walked by a whole warp (tbw_kernel)
+__global__ void __launch_bounds__(kTbThreads, 20)
+tb_kernel(const DevJob* __restrict__ jobs, int n_jobs, const uint32_t* __restrict__ dirs, uint64_t stride, int c, int lg,
+          uint32_t* __restrict__ ops, DevResult* __restrict__ results) {
+  const int j = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (j >= n_jobs) return;
+  const DevJob* Jp = jobs + j;
+  if (Jp->x >= kTbWarpRows) return;  // tbw_kernel's
+  DevResult R = results[j];
+  if (R.status != kStatusOk || (Jp->mode & 0x100)) return;  // empty / out of range: nothing to walk
+  k1_traceback(dirs + (uint64_t)j * stride, c, lg, R.end_i, R.end_j, Jp->p0, (Jp->mode & 0xff) == kModeFull,
+               ops + Jp->ops_word, Jp->ops_cap, R);
+  R.ops_start = Jp->ops_word * 16 + Jp->ops_cap - R.n_ops;
+  results[j] = R;
+}
+
+// Long jobs: one job per WARP.  Every lane runs the same walk (no divergence, no state exchange);
+// what the lanes share is the fetch: when the walk needs a word that is not cached, lane i loads the
+// word of step block blk - i of the current band column, so one round trip covers 32 step blocks
+// (512 rows of a DIAG run) instead of one, and the words then come from a shuffle.
+struct WarpFetch {
+  const uint32_t* dirs;
+  int C, LG;
+  int cb, ck, cl;   // cached: step blocks cb .. cb-31 of column (ck, cl); cb < 0: nothing
+  uint32_t mine;    // this lane's word: step block cb - lane
+  __device__ __forceinline__ uint32_t operator()(int blk, int k, int l) {
+    if (k != ck || l != cl || blk > cb || blk < cb - 31) {  // (uniform: all lanes walk the same path)
+      cb = blk; ck = k; cl = l;
+      const int b = blk - (int)(threadIdx.x & 31);
+      mine = b >= 0 ? dirs[((uint32_t)b * (uint32_t)C + (uint32_t)k) * (uint32_t)LG + (uint32_t)l] : 0u;
+    }
+    return __shfl_sync(0xffffffffu, mine, cb - blk);
+  }
+};
+
+constexpr int kTbwThreads = 128;
+__global__ void __launch_bounds__(kTbwThreads, 8)
+tbw_kernel(const DevJob* __restrict__ jobs, int n_jobs, const uint32_t* __restrict__ dirs, uint64_t stride, int c, int lg,
+           uint32_t* __restrict__ ops, DevResult* __restrict__ results) {
+  const int j = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (j >= n_jobs) return;
+  const DevJob* Jp = jobs + j;
+  if (Jp->x < kTbWarpRows) return;  // tb_kernel's
+  DevResult R = results[j];
+  if (R.status != kStatusOk || (Jp->mode & 0x100)) return;
+  const bool leader = (threadIdx.x & 31) == 0;
+  WarpFetch f{dirs + (uint64_t)j * stride, c, lg, -1, -1, -1, 0u};
+  k1_traceback_t(f, c, R.end_i, R.end_j, Jp->p0, leader && (Jp->mode & 0xff) == kModeFull, ops + Jp->ops_word, Jp->ops_cap, R);
+  if (leader) {
+    R.ops_start = Jp->ops_word * 16 + Jp->ops_cap - R.n_ops;
+    results[j] = R;
   }
 }
 
@@ -359,6 +420,14 @@ struct PinBuf {
 struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // the traceback kernel of a wave runs on tb_stream while the next wave fills the other half of the
+  // direction scratch: ev_fill[h] = half h is filled, ev_tb[h] = half h has been walked
+  cudaStream_t tb_stream = nullptr;
+  cudaEvent_t ev_fill[2] = {nullptr, nullptr}, ev_tb[2] = {nullptr, nullptr};
+  // odd waves are launched on stream2, so that their blocks move in while the persistent blocks of the
+  // previous wave drain (no idle tail at a wave boundary); ev_ready = inputs of the run are on the device
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_ready = nullptr;
   DevBuf jobs, gjobs, results, dirs, ops, grows, gdirs, counters;
   PinBuf h_jobs, h_gjobs, h_results, h_ops;
 };
@@ -642,6 +711,8 @@ struct Group {
   uint32_t res_off = 0;  // offset of this group's results in the device result array
   uint32_t job_off = 0;  // offset into the device job array (DevJob or GenJob)
   int grid = 0;
+  uint64_t min_x = ~0ull, max_x = 0;  // rows of the shortest / longest job (which traceback kernels are needed)
+  uint64_t wave_jobs = 0;  // dirs groups: jobs per launch (their direction words fill one scratch half)
 };
 
 struct DevPlan {
@@ -650,7 +721,8 @@ struct DevPlan {
   uint32_t n_jobs = 0, n_dev_jobs = 0, n_gen_jobs = 0;
   uint64_t ops_words = 0;  // device ops buffer size
   uint64_t ops_base = 0;   // position (in ops) of this device's buffer in the caller's ops_buf
-  uint64_t dirs_words = 0, grows = 0, gdirs = 0;
+  uint64_t dirs_words = 0, grows = 0, gdirs = 0;  // dirs_words: one scratch half
+  uint32_t n_launches = 0;
   float last_ms = 0.f;
 };
 
@@ -677,10 +749,10 @@ struct gamx_plan {
 namespace {
 
 template <int C, int LG, bool DIRS>
-int launch_k1_t(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
+int launch_k1_t(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, int n_jobs, const DevJob* jobs, int* counter, uint32_t* dirs,
                 uint64_t stride, uint32_t* ops, DevResult* results) {
   SeqStore st{(const uint32_t*)d.packed.p, (const uint32_t*)d.nmask.p};
-  k1_kernel<C, LG, DIRS><<<g.grid, kWarpsPerBlock * 32, 0, stream>>>(jobs, (int)g.job_idx.size(), counter, st, dirs,
+  k1_kernel<C, LG, DIRS><<<g.grid, kWarpsPerBlock * 32, 0, stream>>>(jobs, n_jobs, counter, st, dirs,
                                                                       stride, ops, results);
   CU(cudaGetLastError());
   return GAMX_OK;
@@ -712,21 +784,21 @@ int k1_blocks_per_sm(int c, int lg, bool dirs) {
 }
 
 template <int LG>
-int launch_k1_lg(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
+int launch_k1_lg(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, int n_jobs, const DevJob* jobs, int* counter, uint32_t* dirs,
                  uint64_t stride, uint32_t* ops, DevResult* results) {
   switch (g.c) {
-#define M(N, L) case N: return g.dirs ? launch_k1_t<N, L, true>(ctx, d, stream, g, jobs, counter, dirs, stride, ops, results) \
-                                       : launch_k1_t<N, L, false>(ctx, d, stream, g, jobs, counter, dirs, stride, ops, results);
+#define M(N, L) case N: return g.dirs ? launch_k1_t<N, L, true>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results) \
+                                       : launch_k1_t<N, L, false>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results);
     GAMX_FOR_EACH_C(M, LG)
 #undef M
     default: ctx->err = "internal: bad stripe width"; return GAMX_ERR_INVALID;
   }
 }
-int launch_k1(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
+int launch_k1(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, int n_jobs, const DevJob* jobs, int* counter, uint32_t* dirs,
               uint64_t stride, uint32_t* ops, DevResult* results) {
-  if (g.lg == 32) return launch_k1_lg<32>(ctx, d, stream, g, jobs, counter, dirs, stride, ops, results);
-  if (g.lg == 16) return launch_k1_lg<16>(ctx, d, stream, g, jobs, counter, dirs, stride, ops, results);
-  return launch_k1_lg<8>(ctx, d, stream, g, jobs, counter, dirs, stride, ops, results);
+  if (g.lg == 32) return launch_k1_lg<32>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results);
+  if (g.lg == 16) return launch_k1_lg<16>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results);
+  return launch_k1_lg<8>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results);
 }
 
 // splits [0, n) over the host's cores; fn(slice, begin, end) must be thread-safe, slice < kMaxHostThreads
@@ -797,10 +869,10 @@ void lpt_assign(const std::vector<uint32_t>& order, int n_shards, CostOf cost_of
 
 // ---- K2 dispatch: LG = 64 takes every stripe width, LG = 128/256 only the wide ones -----------
 template <int C, int LG, bool DIRS>
-int launch_k2_t(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
+int launch_k2_t(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, int n_jobs, const DevJob* jobs, int* counter, uint32_t* dirs,
                 uint64_t stride, uint32_t* ops, DevResult* results) {
   SeqStore st{(const uint32_t*)d.packed.p, (const uint32_t*)d.nmask.p};
-  k2_kernel<C, LG, DIRS><<<g.grid, LG, 0, stream>>>(jobs, (int)g.job_idx.size(), counter, st, dirs, stride, ops, results);
+  k2_kernel<C, LG, DIRS><<<g.grid, LG, 0, stream>>>(jobs, n_jobs, counter, st, dirs, stride, ops, results);
   CU(cudaGetLastError());
   return GAMX_OK;
 }
@@ -821,10 +893,10 @@ int k2_blocks_per_sm(int c, int lg, bool dirs) {
   if (e != cudaSuccess) { cudaGetLastError(); return 0; }
   return b;
 }
-int launch_k2(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, const DevJob* jobs, int* counter, uint32_t* dirs,
+int launch_k2(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, int n_jobs, const DevJob* jobs, int* counter, uint32_t* dirs,
               uint64_t stride, uint32_t* ops, DevResult* results) {
-#define M(N, L) if (g.c == N && g.lg == L) return g.dirs ? launch_k2_t<N, L, true>(ctx, d, stream, g, jobs, counter, dirs, stride, ops, results) \
-                                                          : launch_k2_t<N, L, false>(ctx, d, stream, g, jobs, counter, dirs, stride, ops, results);
+#define M(N, L) if (g.c == N && g.lg == L) return g.dirs ? launch_k2_t<N, L, true>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results) \
+                                                          : launch_k2_t<N, L, false>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results);
   GAMX_FOR_EACH_C(M, 64)
   GAMX_FOR_EACH_WIDE_C(M, 128)
   GAMX_FOR_EACH_WIDE_C(M, 256)
@@ -876,6 +948,13 @@ int gamx_create(gamx_ctx** out, const int* device_ids, int n_devices) {
     bool ok = cudaSetDevice(d.id) == cudaSuccess && cudaGetDeviceProperties(&prop, d.id) == cudaSuccess;
     for (int k = 0; ok && k < 2; k++)
       ok = cudaStreamCreateWithFlags(&d.s[k].stream, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaStreamCreateWithFlags(&d.s[k].tb_stream, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaStreamCreateWithFlags(&d.s[k].stream2, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&d.s[k].ev_ready, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&d.s[k].ev_fill[0], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&d.s[k].ev_fill[1], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&d.s[k].ev_tb[0], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&d.s[k].ev_tb[1], cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreate(&d.s[k].ev0) == cudaSuccess && cudaEventCreate(&d.s[k].ev1) == cudaSuccess;
     int prio_lo = 0, prio_hi = 0;  // the upload stream's small pack blocks go first when an SM has room
     ok = ok && cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) == cudaSuccess;
@@ -914,6 +993,10 @@ void gamx_destroy(gamx_ctx* ctx) {
       for (PinBuf* b : sp) if (b->p) cudaFreeHost(b->p);
       cudaEventDestroy(sl.ev0);
       cudaEventDestroy(sl.ev1);
+      for (int h = 0; h < 2; h++) { cudaEventDestroy(sl.ev_fill[h]); cudaEventDestroy(sl.ev_tb[h]); }
+      cudaEventDestroy(sl.ev_ready);
+      cudaStreamDestroy(sl.tb_stream);
+      cudaStreamDestroy(sl.stream2);
       cudaStreamDestroy(sl.stream);
     }
     for (cudaEvent_t e : d.up_events) cudaEventDestroy(e);
@@ -1054,7 +1137,7 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
   //    every slice also summarises its jobs so that the common batch - one kernel family, near-uniform
   //    cost, one device, no edit strings - needs no further pass over the jobs
   struct Summary {
-    uint64_t cells = 0, cmin = ~0ull, cmax = 0, max_dir_words = 0, n_special = 0;
+    uint64_t cells = 0, cmin = ~0ull, cmax = 0, max_dir_words = 0, n_special = 0, xmin = ~0ull, xmax = 0;
     size_t max_contig = 0;
     int c = -1, lg = 0, dirs = 0;  // kernel family of the slice's first job
     bool mixed = false;
@@ -1081,6 +1164,7 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
       if ((P.cls != kClassWarp && P.cls != kClassCta) || P.ops_cap) { S.n_special++; continue; }
       S.cmin = std::min(S.cmin, P.cells); S.cmax = std::max(S.cmax, P.cells);
       S.max_dir_words = std::max(S.max_dir_words, P.dir_words);
+      S.xmin = std::min(S.xmin, P.x_size); S.xmax = std::max(S.xmax, P.x_size);
       const int dirs = j.mode != GAMX_MODE_SCORE;
       if (S.c < 0) { S.c = P.c; S.lg = P.lg; S.dirs = dirs; }
       else if (S.c != P.c || S.lg != P.lg || S.dirs != dirs) S.mixed = true;
@@ -1099,6 +1183,7 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
       A.cells += S.cells; A.n_special += S.n_special;
       A.cmin = std::min(A.cmin, S.cmin); A.cmax = std::max(A.cmax, S.cmax);
       A.max_dir_words = std::max(A.max_dir_words, S.max_dir_words);
+      A.xmin = std::min(A.xmin, S.xmin); A.xmax = std::max(A.xmax, S.xmax);
       A.max_contig = std::max(A.max_contig, S.max_contig);
       if (S.c >= 0) {
         if (A.c < 0) { A.c = S.c; A.lg = S.lg; A.dirs = S.dirs; }
@@ -1115,6 +1200,7 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
       Group g; g.c = A.c; g.lg = A.lg; g.dirs = A.dirs != 0;
       g.job_idx.resize(n);
       g.max_dir_words = A.max_dir_words;
+      g.min_x = A.xmin; g.max_x = A.xmax;
       uint32_t* idx = g.job_idx.data();
       uint32_t* jr = pl->job_res.data();
       int* jd = pl->job_dev.data();
@@ -1187,6 +1273,7 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
         Group& g = groups[find_group(P.c, P.lg, pl->modes[i] != GAMX_MODE_SCORE)];
         g.job_idx.push_back(i);
         g.max_dir_words = std::max(g.max_dir_words, P.dir_words);
+        g.min_x = std::min(g.min_x, P.x_size); g.max_x = std::max(g.max_x, P.x_size);
       } else {
         groups[find_group(0, 32, true)].job_idx.push_back(i);
       }
@@ -1288,48 +1375,57 @@ static int plan_upload(gamx_plan* pl) {
     if (int rc = ensure_dev(ctx, sl.gjobs, (size_t)dp.n_gen_jobs * sizeof(GenJob))) return rc;
     if (int rc = ensure_dev(ctx, sl.results, (size_t)dp.n_jobs * sizeof(DevResult))) return rc;
     if (int rc = ensure_pin(ctx, sl.h_results, (size_t)dp.n_jobs * sizeof(DevResult))) return rc;
-    if (int rc = ensure_dev(ctx, sl.counters, sizeof(int) * (dp.groups.size() + 1))) return rc;
     if (int rc = ensure_dev(ctx, sl.ops, dp.ops_words * 4 + 64)) return rc;
     if (int rc = ensure_dev(ctx, sl.grows, dp.grows * 8 + 64)) return rc;
     if (int rc = ensure_dev(ctx, sl.gdirs, dp.gdirs * 4 + 64)) return rc;
     lap(1);
-    // direction scratch: one region per resident warp ("slot"), reused from job to job
+    // Launch geometry, and the direction scratch: two halves; a launch ("wave") of a dirs group covers
+    // as many jobs as fit one half (job j of the wave owns words [j * max_dir_words, +max_dir_words)),
+    // and the traceback kernel walks half h while the next wave fills the other one.
     // (cudaMemGetInfo stalls for milliseconds while kernels are running, so it is only asked when the
-    //  scratch this slot already owns is not enough for full occupancy)
-    uint64_t dirs_words = 0;
-    uint64_t budget_words = sl.dirs.cap / 4;
-    for (int pass = 0; pass < 2; pass++) {
-      bool short_of_memory = false;
-      dirs_words = 0;
-      for (Group& g : dp.groups) {
-        if (!g.c) { g.grid = (int)((g.job_idx.size() + 63) / 64); continue; }
-        const bool cta = g.lg > 32;
-        const int bps = blocks_per_sm_cached(g.c, g.lg, g.dirs);
-        if (bps <= 0) { ctx->err = "alignment kernel does not fit on the device"; return GAMX_ERR_CUDA; }
-        uint64_t grid = (uint64_t)d.sm_count * bps;
-        const uint64_t pairs_per_block = cta ? 1 : (uint64_t)kWarpsPerBlock * (32 / g.lg);
-        const uint64_t need = (g.job_idx.size() + pairs_per_block - 1) / pairs_per_block;
-        if (need < grid) grid = need;
-        if (g.dirs && g.max_dir_words) {
-          const uint64_t per_block = g.max_dir_words * pairs_per_block;
-          if (grid * per_block > budget_words) {
-            short_of_memory = true;
-            if (pass == 1) {
-              if (per_block > budget_words) { ctx->err = "direction scratch of one job exceeds device memory"; return GAMX_ERR_NOMEM; }
-              grid = budget_words / per_block;
-            }
-          }
-          dirs_words = std::max(dirs_words, grid * per_block);
-        }
-        g.grid = (int)std::max<uint64_t>(grid, 1);
+    //  scratch this slot already owns is too small to hold a whole group)
+    uint64_t want_words = 0, min_words = 0;
+    dp.n_launches = 0;
+    for (Group& g : dp.groups) {
+      if (!g.c) { g.grid = (int)((g.job_idx.size() + 63) / 64); dp.n_launches++; continue; }
+      const bool cta = g.lg > 32;
+      const int bps = blocks_per_sm_cached(g.c, g.lg, g.dirs);
+      if (bps <= 0) { ctx->err = "alignment kernel does not fit on the device"; return GAMX_ERR_CUDA; }
+      uint64_t grid = (uint64_t)d.sm_count * bps;
+      const uint64_t pairs_per_block = cta ? 1 : (uint64_t)kWarpsPerBlock * (32 / g.lg);
+      const uint64_t need = (g.job_idx.size() + pairs_per_block - 1) / pairs_per_block;
+      if (need < grid) grid = need;
+      g.grid = (int)std::max<uint64_t>(grid, 1);
+      if (g.dirs && g.max_dir_words) {
+        want_words = std::max(want_words, g.max_dir_words * (uint64_t)g.job_idx.size());
+        min_words = std::max(min_words, g.max_dir_words);
       }
-      if (!short_of_memory || pass == 1) break;
+    }
+    uint64_t half_words = sl.dirs.cap > 64 ? (sl.dirs.cap - 64) / 8 : 0;  // what the slot owns already (two halves of 4-byte words)
+    if (want_words > half_words) {
+      // Few large waves beat many small ones (every wave boundary costs a partly idle tail, and a
+      // wave should hold many times the jobs that are resident at once): a half may take up to 15 % of
+      // the free memory, and at least 4 GiB when the device has it.
       size_t free_b = 0, total_b = 0;
       CU(cudaMemGetInfo(&free_b, &total_b));
-      budget_words = (uint64_t)((free_b + sl.dirs.cap) * 0.8) / 4;
+      const uint64_t avail = (uint64_t)free_b + sl.dirs.cap;
+      const uint64_t budget = std::max<uint64_t>((uint64_t)(avail * 0.15), std::min<uint64_t>((uint64_t)4 << 30, avail / 4)) / 4;
+      half_words = std::max(half_words, std::min(want_words, budget));
+      if (half_words < min_words) { ctx->err = "direction scratch of one job exceeds device memory"; return GAMX_ERR_NOMEM; }
     }
-    dp.dirs_words = dirs_words;
-    if (int rc = ensure_dev(ctx, sl.dirs, dirs_words * 4 + 64)) return rc;
+    for (Group& g : dp.groups) {
+      if (!g.c) continue;
+      if (g.dirs && g.max_dir_words) {
+        g.wave_jobs = std::min<uint64_t>(half_words / g.max_dir_words, g.job_idx.size());
+        dp.n_launches += (uint32_t)((g.job_idx.size() + g.wave_jobs - 1) / g.wave_jobs);
+      } else {
+        g.wave_jobs = g.job_idx.size();
+        dp.n_launches++;
+      }
+    }
+    dp.dirs_words = want_words ? half_words : 0;
+    if (int rc = ensure_dev(ctx, sl.dirs, dp.dirs_words * 8 + 64)) return rc;
+    if (int rc = ensure_dev(ctx, sl.counters, sizeof(int) * (dp.n_launches + 1))) return rc;
     lap(2);
     DevJob* hj = (DevJob*)sl.h_jobs.p;
     GenJob* hg = (GenJob*)sl.h_gjobs.p;
@@ -1386,25 +1482,65 @@ static int plan_run_locked(gamx_plan* pl) {
     Slot& sl = d.s[pl->slot];
     CU(cudaSetDevice(d.id));
     CU(cudaEventRecord(sl.ev0, sl.stream));
-    CU(cudaMemsetAsync(sl.counters.p, 0, sizeof(int) * (dp.groups.size() + 1), sl.stream));
+    CU(cudaMemsetAsync(sl.counters.p, 0, sizeof(int) * (dp.n_launches + 1), sl.stream));
+    CU(cudaEventRecord(sl.ev_ready, sl.stream));
+    CU(cudaStreamWaitEvent(sl.stream2, sl.ev_ready, 0));
+    uint32_t launch = 0, wave = 0;
+    bool half_used[2] = {false, false};
     for (size_t gi = 0; gi < dp.groups.size(); gi++) {
       const Group& g = dp.groups[gi];
       DevResult* res = (DevResult*)sl.results.p + g.res_off;
-      if (g.c) {
-        const DevJob* dj = (const DevJob*)sl.jobs.p + g.job_off;
-        const int rc = g.lg > 32 ? launch_k2(ctx, d, sl.stream, g, dj, (int*)sl.counters.p + gi, (uint32_t*)sl.dirs.p,
-                                             g.max_dir_words, (uint32_t*)sl.ops.p, res)
-                                 : launch_k1(ctx, d, sl.stream, g, dj, (int*)sl.counters.p + gi, (uint32_t*)sl.dirs.p,
-                                             g.max_dir_words, (uint32_t*)sl.ops.p, res);
-        if (rc) return rc;
-      } else {
+      if (!g.c) {
         SeqStore st{(const uint32_t*)d.packed.p, (const uint32_t*)d.nmask.p};
         generic_kernel<<<g.grid, 64, 0, sl.stream>>>((const GenJob*)sl.gjobs.p + g.job_off, (int)g.job_idx.size(), st,
                                                      (int64_t*)sl.grows.p, (uint32_t*)sl.gdirs.p, (uint32_t*)sl.ops.p, res);
         CU(cudaGetLastError());
+        pl->launches++; launch++;
+        continue;
       }
-      pl->launches++;
+      const DevJob* dj = (const DevJob*)sl.jobs.p + g.job_off;
+      const uint64_t n = g.job_idx.size();
+      const bool walk = g.dirs && g.max_dir_words;
+      for (uint64_t w0 = 0; w0 < n; w0 += g.wave_jobs) {
+        const uint64_t nw = std::min(g.wave_jobs, n - w0);
+        const int h = walk ? (int)(wave & 1) : 0;
+        cudaStream_t fs = h ? sl.stream2 : sl.stream;  // fill stream of this wave
+        uint32_t* half = (uint32_t*)sl.dirs.p + (uint64_t)h * dp.dirs_words;
+        if (walk && half_used[h]) CU(cudaStreamWaitEvent(fs, sl.ev_tb[h], 0));  // half h is free again
+        Group gw;  // launch view of the wave (no job list needed)
+        gw.c = g.c; gw.lg = g.lg; gw.dirs = g.dirs;
+        const uint64_t pairs_per_block = g.lg > 32 ? 1 : (uint64_t)kWarpsPerBlock * (32 / g.lg);
+        gw.grid = (int)std::min<uint64_t>((uint64_t)g.grid, (nw + pairs_per_block - 1) / pairs_per_block);
+        const int rc = g.lg > 32 ? launch_k2(ctx, d, fs, gw, (int)nw, dj + w0, (int*)sl.counters.p + launch, half,
+                                             g.max_dir_words, (uint32_t*)sl.ops.p, res + w0)
+                                 : launch_k1(ctx, d, fs, gw, (int)nw, dj + w0, (int*)sl.counters.p + launch, half,
+                                             g.max_dir_words, (uint32_t*)sl.ops.p, res + w0);
+        if (rc) return rc;
+        pl->launches++; launch++;
+        if (walk) {
+          CU(cudaEventRecord(sl.ev_fill[h], fs));
+          CU(cudaStreamWaitEvent(sl.tb_stream, sl.ev_fill[h], 0));
+          if (g.min_x < (uint64_t)kTbWarpRows) {  // short jobs: one per thread
+            tb_kernel<<<(unsigned)((nw + kTbThreads - 1) / kTbThreads), kTbThreads, 0, sl.tb_stream>>>(
+                dj + w0, (int)nw, half, g.max_dir_words, g.c, g.lg, (uint32_t*)sl.ops.p, res + w0);
+            CU(cudaGetLastError());
+            pl->launches++;
+          }
+          if (g.max_x >= (uint64_t)kTbWarpRows) {  // long jobs: one per warp
+            const uint64_t warps_per_block = kTbwThreads / 32;
+            tbw_kernel<<<(unsigned)((nw + warps_per_block - 1) / warps_per_block), kTbwThreads, 0, sl.tb_stream>>>(
+                dj + w0, (int)nw, half, g.max_dir_words, g.c, g.lg, (uint32_t*)sl.ops.p, res + w0);
+            CU(cudaGetLastError());
+            pl->launches++;
+          }
+          CU(cudaEventRecord(sl.ev_tb[h], sl.tb_stream));
+          half_used[h] = true;
+          wave++;
+        }
+      }
     }
+    for (int h = 0; h < 2; h++)
+      if (half_used[h]) CU(cudaStreamWaitEvent(sl.stream, sl.ev_tb[h], 0));
     CU(cudaEventRecord(sl.ev1, sl.stream));
   }
   pl->ran = true;
