@@ -11,12 +11,14 @@ x_size * (2*band+1) per job (banded_smith_waterman.cc:93-97,135-137).
 
   value   whole-job GCUPS with inputs (packed contigs + job descriptors) resident in HBM,
           device time by CUDA events on the launching stream, max over ranks.
-  e2e     the same metric through the C-ABI call a user makes, host buffers in and out:
-          every step re-uploads the raw sequences from pinned host memory (gamx_add_contigs:
-          H2D + pack kernel), the job descriptors, runs the kernels and reads the results back.
+  e2e     the same metric through the C-ABI calls a user makes, host buffers in and out:
+          every step re-uploads the raw sequences from pinned host memory (gamx_add_contigs_async:
+          H2D in pieces + pack kernel) and calls gamx_align_batch, which pipelines chunks of jobs
+          (descriptor H2D, fill kernel, traceback kernel, result D2H) behind the pieces they need.
   roofline  score+endpoints is integer-ALU/DPX bound, not HBM bound: achieved =
           cells/s * 4 lane-ops against the VIADDMNMX issue peak measured live by a
-          register-only microbenchmark; the HBM view of the same kernel is reported beside it.
+          register-only microbenchmark; the HBM view of the same kernels (2 direction bits per cell
+          written once, sequences and records) is reported beside it with the ncu DRAM traffic.
   cpu_baseline  the reference's own aligner (oracle/_ref, compiled from the unmodified sources)
           on all host cores, on a bounded seeded sample of the same workload.
 """
@@ -46,6 +48,9 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "cfg2_1M_1kb_band64_endpoints"
 ALGO_LANE_OPS_PER_CELL = 4      # select + add + max + fused add-max in 32-bit
 DIR_BYTES_PER_CELL = 0.25       # 2 direction bits per cell
+# dram__bytes_read.sum + dram__bytes_write.sum of the fill kernel + traceback kernel per DP cell, from the
+# `ncu --set full` capture of 100k config-2 pairs in profiles/ (r1d_k1_c9_lg16_fill_100k.csv)
+NCU_DRAM_BYTES_PER_CELL = 0.31
 
 
 def env_int(name, default):
@@ -322,7 +327,6 @@ def main():
                "ms_per_step": e2e_s / args.steps * 1e3,
                "includes": "raw sequence H2D from pinned memory + device 2-bit pack, job descriptor H2D, kernels, result D2H",
                "pipeline": "chunks of 65536 jobs on two streams; upload pieces of 32 MB on a third"}
-        launches_e2e = 2  # pack kernel + k1 per step
     # ---- roofline --------------------------------------------------------------------------------
     peaks, peak_src = load_peaks()
     kernel_s = dev_s / args.steps
@@ -330,15 +334,18 @@ def main():
     ach_int = cells_rank / (dev_ms * 1e-3 / args.steps) * ALGO_LANE_OPS_PER_CELL / 1e12
     roofline = {"bound": "int_alu", "achieved": ach_int, "peak": int_peak / 1e12, "unit": "Tlaneop/s",
                 "frac": ach_int / (int_peak / 1e12) if int_peak else None, "traffic": None,
-                "kernel": "k1_kernel<9,16,true>" if spec["mode"] else "k1_kernel<9,16,false>",
+                "kernel": "k1_kernel<9,16,true> (+ tb_kernel)" if spec["mode"] else "k1_kernel<9,16,false>",
                 "algorithmic": f"{ALGO_LANE_OPS_PER_CELL} int32 lane-ops per cell (SURVEY 8d) x {int(cells_rank)} cells per launch",
                 "peak_source": "VIADDMNMX issue rate measured live by gamx_measure_int_peak (register-only kernel)"}
     seq_bytes = total_bases * 3 / 8
     algo_bytes = (cells_rank * DIR_BYTES_PER_CELL if spec["mode"] else 0.0) + seq_bytes + n * (96 + 104)
     ach_hbm = algo_bytes / (dev_ms * 1e-3 / args.steps) / 1e9
     roofline_hbm = {"bound": "hbm", "achieved": ach_hbm, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach_hbm / peaks["hbm_gbs"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
-                    "note": "direction bits (0.25 B/cell) live in a per-warp scratch that stays in L2; not the binding resource"}
+                    "frac": ach_hbm / peaks["hbm_gbs"], "peak_source": f"MEASURED_PEAKS.json ({peak_src})",
+                    "traffic": NCU_DRAM_BYTES_PER_CELL * cells_rank,
+                    "note": "direction bits (0.25 B/cell) are written once to a per-wave scratch in HBM and read back sparsely by "
+                            "the traceback kernel; traffic = ncu dram bytes per cell (profiles/, 100k-pair capture) x cells; "
+                            "not the binding resource"}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

@@ -454,9 +454,33 @@ struct Device {
 
 // Index of the contig store.  Sequence data itself lives only on the devices; contigs added one
 // at a time wait as raw bytes in `pending` until the next upload.
+// growable array of uint64 that does not value-initialise on resize (bulk uploads fill it in parallel)
+struct U64Vec {
+  uint64_t* p = nullptr;
+  size_t n = 0, cap = 0;
+  U64Vec() = default;
+  U64Vec(const U64Vec&) = delete;
+  U64Vec& operator=(const U64Vec&) = delete;
+  ~U64Vec() { free(p); }
+  size_t size() const { return n; }
+  uint64_t* data() { return p; }
+  const uint64_t* data() const { return p; }
+  uint64_t& operator[](size_t i) { return p[i]; }
+  const uint64_t& operator[](size_t i) const { return p[i]; }
+  void reserve(size_t want) {
+    if (want <= cap) return;
+    size_t c = std::max(want, cap + cap / 2 + 16);
+    p = (uint64_t*)realloc(p, c * sizeof(uint64_t));
+    cap = c;
+  }
+  void resize(size_t want) { reserve(want); n = want; }  // new elements are NOT initialised
+  void push_back(uint64_t v) { reserve(n + 1); p[n++] = v; }
+  void clear() { n = 0; }
+};
+
 struct StoreIndex {
-  std::vector<uint64_t> start;   // first base index (multiple of 32)
-  std::vector<uint64_t> length;
+  U64Vec start;   // first base index (multiple of 32)
+  U64Vec length;
   uint64_t n_bases = 0;
 };
 
@@ -523,6 +547,36 @@ int ensure_pin(gamx_ctx* ctx, PinBuf& b, size_t bytes) {
   CU(cudaHostAlloc(&b.p, want, cudaHostAllocPortable));
   b.cap = want;
   return GAMX_OK;
+}
+
+// splits [0, n) over the host's cores; fn(slice, begin, end) must be thread-safe, slice < kMaxHostThreads
+constexpr unsigned kMaxHostThreads = 32;
+template <class F>
+void parallel_slices(uint64_t n, F fn) {
+  // host threads for batch preparation: all cores, divided by the number of ranks sharing the node
+  // when launched one process per GPU (torchrun sets LOCAL_WORLD_SIZE); GAMX_HOST_THREADS overrides
+  static const unsigned nt_cfg = [] {
+    unsigned n = std::thread::hardware_concurrency();
+    if (n == 0) n = 4;
+    if (const char* e = getenv("GAMX_HOST_THREADS")) { const int v = atoi(e); if (v > 0) return std::min((unsigned)v, kMaxHostThreads); }
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) { const int v = atoi(e); if (v > 1) n = std::max(1u, n / (unsigned)v); }
+    return std::min(n, kMaxHostThreads);
+  }();
+  unsigned nt = nt_cfg;
+  if (n < 20000 || nt == 1) { fn(0u, (uint64_t)0, n); return; }
+  std::vector<std::thread> th;
+  const uint64_t chunk = (n + nt - 1) / nt;
+  for (unsigned t = 1; t < nt; t++) {
+    const uint64_t b = t * chunk, e = std::min(n, b + chunk);
+    if (b >= e) break;
+    th.emplace_back([=] { fn(t, b, e); });
+  }
+  fn(0u, (uint64_t)0, std::min(n, chunk));  // the calling thread takes the first slice
+  for (auto& t : th) t.join();
+}
+template <class F>
+void parallel_for(uint64_t n, F fn) {
+  parallel_slices(n, [&](unsigned, uint64_t b, uint64_t e) { fn(b, e); });
 }
 
 // grows a store array, keeping its contents (rare: synchronises the whole device)
@@ -647,16 +701,31 @@ int store_upload(gamx_ctx* ctx, const uint8_t* raw, size_t first, size_t n, bool
   uint64_t* roff = (uint64_t*)ctx->h_meta.p;
   uint64_t* sgroup = roff + (n + 1);
   u.roff = roff; u.sgroup = sgroup;
-  u.piece_end.clear();
-  uint64_t off = 0, piece_start = 0;
+  // raw offsets (exclusive prefix of the lengths), store groups and piece boundaries, in two parallel
+  // passes; a piece ends with the contig whose end crosses a multiple of piece_bytes
   const uint64_t* st = si.start.data() + first;
   const uint64_t* ln = si.length.data() + first;
   const uint64_t g0 = u.group0, piece_bytes = ctx->piece_bytes;
-  for (size_t c = 0; c < n; c++) {
-    roff[c] = off; sgroup[c] = st[c] / 32 - g0;
-    off += ln[c];
-    if (off - piece_start >= piece_bytes) { u.piece_end.push_back(c + 1); piece_start = off; }
-  }
+  uint64_t slice_raw[kMaxHostThreads + 1] = {0};
+  std::vector<size_t> slice_pieces[kMaxHostThreads];
+  parallel_slices(n, [&](unsigned t, uint64_t b, uint64_t e) {
+    uint64_t sum = 0;
+    for (uint64_t c = b; c < e; c++) sum += ln[c];
+    slice_raw[t + 1] = sum;
+  });
+  for (unsigned t = 0; t < kMaxHostThreads; t++) slice_raw[t + 1] += slice_raw[t];
+  parallel_slices(n, [&](unsigned t, uint64_t b, uint64_t e) {
+    uint64_t off = slice_raw[t];
+    for (uint64_t c = b; c < e; c++) {
+      roff[c] = off; sgroup[c] = st[c] / 32 - g0;
+      const uint64_t end = off + ln[c];
+      if (end / piece_bytes != off / piece_bytes) slice_pieces[t].push_back(c + 1);
+      off = end;
+    }
+  });
+  const uint64_t off = slice_raw[kMaxHostThreads];
+  u.piece_end.clear();
+  for (unsigned t = 0; t < kMaxHostThreads; t++) u.piece_end.insert(u.piece_end.end(), slice_pieces[t].begin(), slice_pieces[t].end());
   roff[n] = off; sgroup[n] = groups_end - u.group0;
   if (u.piece_end.empty() || u.piece_end.back() != n) u.piece_end.push_back(n);
   for (Device& d : ctx->devs) {
@@ -799,36 +868,6 @@ int launch_k1(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, int
   if (g.lg == 32) return launch_k1_lg<32>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results);
   if (g.lg == 16) return launch_k1_lg<16>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results);
   return launch_k1_lg<8>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results);
-}
-
-// splits [0, n) over the host's cores; fn(slice, begin, end) must be thread-safe, slice < kMaxHostThreads
-constexpr unsigned kMaxHostThreads = 32;
-template <class F>
-void parallel_slices(uint64_t n, F fn) {
-  // host threads for batch preparation: all cores, divided by the number of ranks sharing the node
-  // when launched one process per GPU (torchrun sets LOCAL_WORLD_SIZE); GAMX_HOST_THREADS overrides
-  static const unsigned nt_cfg = [] {
-    unsigned n = std::thread::hardware_concurrency();
-    if (n == 0) n = 4;
-    if (const char* e = getenv("GAMX_HOST_THREADS")) { const int v = atoi(e); if (v > 0) return std::min((unsigned)v, kMaxHostThreads); }
-    if (const char* e = getenv("LOCAL_WORLD_SIZE")) { const int v = atoi(e); if (v > 1) n = std::max(1u, n / (unsigned)v); }
-    return std::min(n, kMaxHostThreads);
-  }();
-  unsigned nt = nt_cfg;
-  if (n < 20000 || nt == 1) { fn(0u, (uint64_t)0, n); return; }
-  std::vector<std::thread> th;
-  const uint64_t chunk = (n + nt - 1) / nt;
-  for (unsigned t = 1; t < nt; t++) {
-    const uint64_t b = t * chunk, e = std::min(n, b + chunk);
-    if (b >= e) break;
-    th.emplace_back([=] { fn(t, b, e); });
-  }
-  fn(0u, (uint64_t)0, std::min(n, chunk));  // the calling thread takes the first slice
-  for (auto& t : th) t.join();
-}
-template <class F>
-void parallel_for(uint64_t n, F fn) {
-  parallel_slices(n, [&](unsigned, uint64_t b, uint64_t e) { fn(b, e); });
 }
 
 // stable LSD radix sort of job indices by descending cost
@@ -1050,13 +1089,26 @@ static int64_t add_contigs_impl(gamx_ctx* ctx, const uint8_t* codes, const uint6
     si.length.resize(first + n);
     uint64_t* st = si.start.data() + first;
     uint64_t* ln = si.length.data() + first;
-    uint64_t nb = si.n_bases, too_long = 0;
-    for (uint64_t c = 0; c < n; c++) {
-      const uint64_t len = lengths[c];
-      too_long |= len >> 31;
-      st[c] = nb; ln[c] = len;
-      nb += (len + 31) & ~uint64_t(31);
-    }
+    // two passes over slices: padded sizes per slice, then the exclusive prefix and the fill
+    uint64_t slice_bases[kMaxHostThreads + 1] = {0}, slice_long[kMaxHostThreads] = {0};
+    parallel_slices(n, [&](unsigned t, uint64_t b, uint64_t e) {
+      uint64_t sum = 0, tl = 0;
+      for (uint64_t c = b; c < e; c++) { sum += (lengths[c] + 31) & ~uint64_t(31); tl |= lengths[c] >> 31; }
+      slice_bases[t + 1] = sum; slice_long[t] = tl;
+    });
+    uint64_t too_long = 0;
+    for (unsigned t = 0; t < kMaxHostThreads; t++) too_long |= slice_long[t];
+    slice_bases[0] = si.n_bases;
+    for (unsigned t = 0; t < kMaxHostThreads; t++) slice_bases[t + 1] += slice_bases[t];
+    parallel_slices(n, [&](unsigned t, uint64_t b, uint64_t e) {
+      uint64_t nb = slice_bases[t];
+      for (uint64_t c = b; c < e; c++) {
+        const uint64_t len = lengths[c];
+        st[c] = nb; ln[c] = len;
+        nb += (len + 31) & ~uint64_t(31);
+      }
+    });
+    const uint64_t nb = slice_bases[kMaxHostThreads];
     if (too_long) {
       si.start.resize(first); si.length.resize(first);
       ctx->err = "contig longer than 2^31 bases";

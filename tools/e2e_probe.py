@@ -30,3 +30,7 @@ for it in range(3):
     t2 = time.perf_counter(); res, ops = ctx.align_batch(jobs)
     t3 = time.perf_counter()
     print(f"iter {it}: clear {1e3*(t1-t0):.1f} add_contigs {1e3*(t2-t1):.1f} align_batch {1e3*(t3-t2):.1f} total {1e3*(t3-t0):.1f} ms", flush=True)
+for it in range(2):  # contigs stay resident: the pipelined batch alone
+    t2 = time.perf_counter(); res, ops = ctx.align_batch(jobs)
+    t3 = time.perf_counter()
+    print(f"resident store, iter {it}: align_batch {1e3*(t3-t2):.1f} ms", flush=True)
