@@ -319,14 +319,16 @@ def main():
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         barrier()
         if r2.tobytes() != res.tobytes():
-            raise SystemExit("PARITY FAILURE: the end-to-end (pipelined) results differ from the resident-plan results")
+            bad = [k for k in range(n) if r2[k].tobytes() != res[k].tobytes()]
+            raise SystemExit(f"PARITY FAILURE: the end-to-end (pipelined) results differ from the resident-plan results "
+                             f"in {len(bad)} jobs, first {bad[:6]}: {r2[bad[0]]} vs {res[bad[0]]}")
         h2d = total_bases + lengths.nbytes * 3 + n * 96  # raw codes + pack metadata + DevJob descriptors (96 B each)
         d2h = n * 104                                     # DevResult records
         e2e = {"value": total_cells * args.steps / e2e_s / 1e9, "unit": "GCUPS",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": e2e_s / args.steps * 1e3,
                "includes": "raw sequence H2D from pinned memory + device 2-bit pack, job descriptor H2D, kernels, result D2H",
-               "pipeline": "chunks of 65536 jobs on two streams; upload pieces of 32 MB on a third"}
+               "pipeline": "chunks of 65536 jobs over 4 buffer slots/streams; upload pieces of 64 MB on their own stream"}
     # ---- roofline --------------------------------------------------------------------------------
     peaks, peak_src = load_peaks()
     kernel_s = dev_s / args.steps

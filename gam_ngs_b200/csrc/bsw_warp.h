@@ -273,7 +273,7 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
     }
     if (DIRS && T_total == 1) {  // a single row on a single lane: no step will flush its directions
 #pragma unroll
-      for (int k = 0; k < C; k++) fp[k * LG] = acc[k] << 30;
+      for (int k = 0; k < C; k++) if (live) fp[k * LG] = acc[k] << 30;
     }
   }
 
@@ -314,7 +314,7 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
     if ((SLOW) && (unsigned)dcap < (unsigned)C) sm.cap[dcap * LG + gl] = capv;                         \
     if ((SLOW) && DIRS && ((tt & 15) == 15 || tt == T_total - 1)) {                                   \
       const int sh = 2 * (15 - (tt & 15));                                                            \
-      _Pragma("unroll") for (int k = 0; k < C; k++) fp[k * LG] = acc[k] << sh;                         \
+      _Pragma("unroll") for (int k = 0; k < C; k++) if (live) fp[k * LG] = acc[k] << sh;               \
       fp += C * LG;                                                                                   \
     }                                                                                                 \
   }
@@ -353,7 +353,7 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
           t += UF; pa_t += UF; pb_t += UF;
           if (DIRS && (t & 15) == 0) {
 #pragma unroll
-            for (int k = 0; k < C; k++) fp[k * LG] = acc[k];
+            for (int k = 0; k < C; k++) if (live) fp[k * LG] = acc[k];  // (an idle group owns no scratch)
             fp += C * LG;
           }
         } while (--nf > 0);

@@ -210,50 +210,57 @@ generic_kernel(const GenJob* __restrict__ jobs, int n_jobs, SeqStore store, int6
 // persistent alignment blocks (which leave ~4 K registers per SM free), so the pack of upload piece
 // p+1 proceeds while the alignment kernel of an earlier chunk still owns every SM.
 constexpr int kPackThreads = 64;
+constexpr int kPackPerThread = 4;                           // 32-base groups per thread (more loads in flight)
+constexpr int kPackGroups = kPackThreads * kPackPerThread;  // groups per block
 __global__ void __launch_bounds__(kPackThreads, 32)
 pack_kernel(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ roff, const uint64_t* __restrict__ sgroup,
             int n_contigs, uint64_t group0, uint64_t g_first, uint64_t n_groups, uint32_t* __restrict__ packed,
             uint32_t* __restrict__ nmask) {
-  const uint64_t gi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gi >= n_groups) return;
-  const uint64_t g = g_first + gi;
-  int lo = 0, hi = n_contigs;  // last c with sgroup[c] <= g
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (sgroup[mid] <= g) lo = mid; else hi = mid;
-  }
-  const uint64_t local = (g - sgroup[lo]) * 32;
-  const uint64_t len = roff[lo + 1] - roff[lo];
-  const uint64_t remain = len - local;
-  const int n = remain < 32 ? (int)remain : 32;
-  const uint8_t* src = raw + roff[lo] + local;
-  uint32_t w0 = 0, w1 = 0, m = 0;
-  if (n == 32 && ((uintptr_t)src & 3) == 0) {  // whole group, word-aligned source: eight 4-byte loads
-    const uint32_t* s4 = (const uint32_t*)src;
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-      const uint32_t v = s4[q];
+  for (int r = 0; r < kPackPerThread; r++) {
+    const uint64_t gi = (uint64_t)blockIdx.x * kPackGroups + (uint64_t)r * kPackThreads + threadIdx.x;
+    if (gi >= n_groups) return;
+    const uint64_t g = g_first + gi;
+    int lo = 0, hi = n_contigs;  // last c with sgroup[c] <= g
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (sgroup[mid] <= g) lo = mid; else hi = mid;
+    }
+    const uint64_t local = (g - sgroup[lo]) * 32;
+    const uint64_t len = roff[lo + 1] - roff[lo];
+    const uint64_t remain = len - local;
+    const int n = remain < 32 ? (int)remain : 32;
+    const uint8_t* src = raw + roff[lo] + local;
+    uint32_t w0 = 0, w1 = 0, m = 0;
+    if (n == 32 && ((uintptr_t)src & 3) == 0) {  // whole group, word-aligned source: eight 4-byte loads
+      const uint32_t* s4 = (const uint32_t*)src;
+      uint32_t v[8];
 #pragma unroll
-      for (int b = 0; b < 4; b++) {
-        const uint32_t c = (v >> (8 * b)) & 0xffu;
-        const int i = 4 * q + b;
+      for (int q = 0; q < 8; q++) v[q] = s4[q];
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          const uint32_t c = (v[q] >> (8 * b)) & 0xffu;
+          const int i = 4 * q + b;
+          if (c >= 4u) m |= 1u << i;
+          else if (i < 16) w0 |= c << (2 * i);
+          else w1 |= c << (2 * (i - 16));
+        }
+      }
+    } else {
+      for (int i = 0; i < n; i++) {
+        const uint32_t c = src[i];
         if (c >= 4u) m |= 1u << i;
         else if (i < 16) w0 |= c << (2 * i);
         else w1 |= c << (2 * (i - 16));
       }
     }
-  } else {
-    for (int i = 0; i < n; i++) {
-      const uint32_t c = src[i];
-      if (c >= 4u) m |= 1u << i;
-      else if (i < 16) w0 |= c << (2 * i);
-      else w1 |= c << (2 * (i - 16));
-    }
+    const uint64_t G = group0 + g;
+    packed[2 * G] = w0;
+    packed[2 * G + 1] = w1;
+    nmask[G] = m;
   }
-  const uint64_t G = group0 + g;
-  packed[2 * G] = w0;
-  packed[2 * G + 1] = w1;
-  nmask[G] = m;
 }
 
 // ---- f3: ABlast::findHits on the device (ablast.cc:41-76, ablast.hpp:52-107) ----------------------
@@ -413,10 +420,11 @@ struct PinBuf {
   size_t cap = 0;
 };
 
-// Per-batch buffers.  Two slots per device, each with its own stream, so that the pipelined
+// Per-batch buffers.  kSlots slots per device, each with its own streams, so that the pipelined
 // gamx_align_batch can prepare / upload chunk c+1 and read back chunk c-1 while chunk c computes
 // (and the kernel of chunk c+1 fills the SMs chunk c's persistent warps leave).  Everything that is
 // not pipelined uses slot 0.
+constexpr int kSlots = 4;  // chunks of a pipelined batch in flight (slot 0 also serves everything unpipelined)
 struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -436,7 +444,7 @@ struct Device {
   int id = 0;
   int sm_count = 0;
   size_t total_mem = 0;
-  Slot s[2];
+  Slot s[kSlots];
   cudaStream_t stream = nullptr;  // == s[0].stream
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf packed, nmask;           // contig store replica (2 bits per base + N mask)
@@ -507,7 +515,7 @@ struct gamx_ctx {
   Upload up;
   PinBuf h_meta;                  // roff[n+1], sgroup[n+1] of the upload in flight (pinned, shared by the devices)
   uint64_t pipeline_chunk = 65536;  // gamx_set_pipeline_chunk
-  uint64_t piece_bytes = 32u << 20;  // raw bytes per upload piece (GAMX_UPLOAD_PIECE_BYTES)
+  uint64_t piece_bytes = 64u << 20;  // raw bytes per upload piece (GAMX_UPLOAD_PIECE_BYTES)
   std::mutex mu;
   std::string err;
 };
@@ -645,9 +653,11 @@ int upload_advance(gamx_ctx* ctx, size_t upto) {
     for (Device& d : ctx->devs) {
       CU(cudaSetDevice(d.id));
       if (int rc = h2d_raw(ctx, d, (uint8_t*)d.raw.p + u.roff[c0], u.raw + u.roff[c0], u.roff[c1] - u.roff[c0], pinned)) return rc;
+      // (K0 runs on the copy stream itself: letting the copies run ahead on their own stream was
+      //  measured slower end to end - the job-descriptor copies of the chunks then queue behind them)
       if (g1 > g0) {
         const uint64_t* dm = (const uint64_t*)d.meta.p;  // roff[n+1], sgroup[n+1]
-        const unsigned blocks = (unsigned)((g1 - g0 + kPackThreads - 1) / kPackThreads);
+        const unsigned blocks = (unsigned)((g1 - g0 + kPackGroups - 1) / kPackGroups);
         pack_kernel<<<blocks, kPackThreads, 0, d.up_stream>>>((const uint8_t*)d.raw.p, dm + c0, dm + (u.n + 1) + c0, (int)(c1 - c0),
                                                     u.group0, g0, g1 - g0, (uint32_t*)d.packed.p, (uint32_t*)d.nmask.p);
         CU(cudaGetLastError());
@@ -792,6 +802,7 @@ struct DevPlan {
   uint64_t ops_base = 0;   // position (in ops) of this device's buffer in the caller's ops_buf
   uint64_t dirs_words = 0, grows = 0, gdirs = 0;  // dirs_words: one scratch half
   uint32_t n_launches = 0;
+  bool two_halves = false;  // the direction scratch has a second half (some group takes several waves)
   float last_ms = 0.f;
 };
 
@@ -985,7 +996,7 @@ int gamx_create(gamx_ctx** out, const int* device_ids, int n_devices) {
     if (d.id < 0 || d.id >= visible) { delete ctx; return GAMX_ERR_INVALID; }
     cudaDeviceProp prop;
     bool ok = cudaSetDevice(d.id) == cudaSuccess && cudaGetDeviceProperties(&prop, d.id) == cudaSuccess;
-    for (int k = 0; ok && k < 2; k++)
+    for (int k = 0; ok && k < kSlots; k++)
       ok = cudaStreamCreateWithFlags(&d.s[k].stream, cudaStreamNonBlocking) == cudaSuccess &&
            cudaStreamCreateWithFlags(&d.s[k].tb_stream, cudaStreamNonBlocking) == cudaSuccess &&
            cudaStreamCreateWithFlags(&d.s[k].stream2, cudaStreamNonBlocking) == cudaSuccess &&
@@ -1453,7 +1464,9 @@ static int plan_upload(gamx_plan* pl) {
         min_words = std::max(min_words, g.max_dir_words);
       }
     }
-    uint64_t half_words = sl.dirs.cap > 64 ? (sl.dirs.cap - 64) / 8 : 0;  // what the slot owns already (two halves of 4-byte words)
+    // what the slot owns already: one half if that holds every group, else two
+    uint64_t half_words = sl.dirs.cap > 64 ? (sl.dirs.cap - 64) / 4 : 0;
+    if (want_words > half_words) half_words /= 2;
     if (want_words > half_words) {
       // Few large waves beat many small ones (every wave boundary costs a partly idle tail, and a
       // wave should hold many times the jobs that are resident at once): a half may take up to 15 % of
@@ -1461,7 +1474,9 @@ static int plan_upload(gamx_plan* pl) {
       size_t free_b = 0, total_b = 0;
       CU(cudaMemGetInfo(&free_b, &total_b));
       const uint64_t avail = (uint64_t)free_b + sl.dirs.cap;
-      const uint64_t budget = std::max<uint64_t>((uint64_t)(avail * 0.15), std::min<uint64_t>((uint64_t)4 << 30, avail / 4)) / 4;
+      uint64_t budget = std::max<uint64_t>((uint64_t)(avail * 0.15), std::min<uint64_t>((uint64_t)4 << 30, avail / 4)) / 4;
+      static const uint64_t forced = [] { const char* e = getenv("GAMX_DIRS_HALF_BYTES"); return e ? (uint64_t)strtoull(e, nullptr, 10) : 0; }();
+      if (forced) budget = std::max<uint64_t>(forced / 4, min_words);  // tests: small halves, many waves
       half_words = std::max(half_words, std::min(want_words, budget));
       if (half_words < min_words) { ctx->err = "direction scratch of one job exceeds device memory"; return GAMX_ERR_NOMEM; }
     }
@@ -1476,7 +1491,9 @@ static int plan_upload(gamx_plan* pl) {
       }
     }
     dp.dirs_words = want_words ? half_words : 0;
-    if (int rc = ensure_dev(ctx, sl.dirs, dp.dirs_words * 8 + 64)) return rc;
+    // (the second half is only needed when a group takes more than one wave)
+    dp.two_halves = want_words > half_words;
+    if (int rc = ensure_dev(ctx, sl.dirs, dp.dirs_words * (dp.two_halves ? 8 : 4) + 64)) return rc;
     if (int rc = ensure_dev(ctx, sl.counters, sizeof(int) * (dp.n_launches + 1))) return rc;
     lap(2);
     DevJob* hj = (DevJob*)sl.h_jobs.p;
@@ -1555,7 +1572,7 @@ static int plan_run_locked(gamx_plan* pl) {
       const bool walk = g.dirs && g.max_dir_words;
       for (uint64_t w0 = 0; w0 < n; w0 += g.wave_jobs) {
         const uint64_t nw = std::min(g.wave_jobs, n - w0);
-        const int h = walk ? (int)(wave & 1) : 0;
+        const int h = (walk && dp.two_halves) ? (int)(wave & 1) : 0;
         cudaStream_t fs = h ? sl.stream2 : sl.stream;  // fill stream of this wave
         uint32_t* half = (uint32_t*)sl.dirs.p + (uint64_t)h * dp.dirs_words;
         if (walk && half_used[h]) CU(cudaStreamWaitEvent(fs, sl.ev_tb[h], 0));  // half h is free again
@@ -1699,8 +1716,8 @@ void gamx_plan_destroy(gamx_plan* pl) { delete pl; }
 
 // Pipelined form of gamx_align_batch for large batches without edit strings: the batch is cut into
 // chunks in the caller's order; a helper thread prepares chunk c+1 (guards, classification,
-// descriptors) while the main thread uploads and launches chunk c on slot c & 1 and converts the
-// results of chunk c-2.  Each chunk's kernel is stream-ordered behind the contig upload pieces it
+// descriptors) while the main thread uploads and launches chunk c on slot c % kSlots and converts the
+// results of chunk c-kSlots.  Each chunk's kernel is stream-ordered behind the contig upload pieces it
 // needs only, so with gamx_add_contigs_async the sequence upload, the alignment kernels, the result
 // copies and the host work all overlap.
 static int align_batch_pipelined(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_result* results, uint64_t chunk) {
@@ -1744,9 +1761,19 @@ static int align_batch_pipelined(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n
   });
   std::vector<gamx_plan*> live(nchunks, nullptr);
   int rc = GAMX_OK;
+  if (timing) { cudaSetDevice(ctx->devs[0].id); cudaEventRecord(ctx->devs[0].ev0, ctx->devs[0].s[0].stream); }
+  const auto t_begin = now();
   auto finish = [&](uint64_t c) {
     if (!live[c]) return;
     if (!rc) rc = plan_fetch_finish(live[c], results + lo_of[c], nullptr);
+    if (timing && !rc) {  // device timeline of the chunk relative to the start of the batch
+      Slot& sl = ctx->devs[0].s[c % kSlots];
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, ctx->devs[0].ev0, sl.ev0);
+      cudaEventElapsedTime(&b, ctx->devs[0].ev0, sl.ev1);
+      fprintf(stderr, "[gamx]   chunk %2llu (%6llu jobs): device %.2f .. %.2f ms, host done at %.2f ms\n", (unsigned long long)c,
+              (unsigned long long)(lo_of[c + 1] - lo_of[c]), a, b, ms(t_begin, now()));
+    }
     delete live[c];
     live[c] = nullptr;
   };
@@ -1763,12 +1790,12 @@ static int align_batch_pipelined(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n
       qcv.notify_all();
     }
     const auto t1 = now();
-    if (c >= 2) finish(c - 2);  // frees slot c & 1
+    if (c >= (uint64_t)kSlots) finish(c - kSlots);  // frees slot c % kSlots
     const auto t2 = now();
     if (!rc && cur.rc) { rc = cur.rc; if (cur.pl) ctx->err = cur.pl->err; }
     auto t3 = t2;
     if (!rc) {
-      cur.pl->slot = (int)(c & 1);
+      cur.pl->slot = (int)(c % kSlots);
       rc = plan_upload(cur.pl);
       t3 = now();
       if (!rc) rc = plan_run_locked(cur.pl);

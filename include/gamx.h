@@ -152,7 +152,7 @@ GAMX_API int64_t gamx_add_contig_ascii(gamx_ctx* ctx, const char* seq, uint64_t 
 GAMX_API int64_t gamx_add_contigs(gamx_ctx* ctx, const uint8_t* codes, const uint64_t* lengths, uint64_t n);
 /* Same, but only enqueues the copies and the pack kernel on the devices' streams and returns: the
  * upload then overlaps the host-side planning of the next gamx_align_batch, which is stream-ordered
- * behind it.  The copy proceeds in pieces of ~32 MB that are enqueued as the batches need them, so a
+ * behind it.  The copy proceeds in pieces of ~64 MB that are enqueued as the batches need them, so a
  * pipelined gamx_align_batch starts computing on the first contigs while later ones still cross PCIe.
  * `codes` must be PINNED host memory and must stay valid and unchanged until that batch (or any
  * other synchronising call of this context) has returned. */

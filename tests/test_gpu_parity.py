@@ -384,3 +384,43 @@ def test_pipelined_batch_matches_single_launch_and_oracle():
                     band=int(jobs["band"][k]), gap=int(jobs["gap"][k]), force_start=False, force_end=bool(jobs["force_end"][k]))
         mode = int(jobs["mode"][k])
         assert result_to_expect(None, ref[k], None, mode) == project(oracle_expect(case), mode), k
+
+
+def test_many_waves_odd_wave_sizes():
+    """Direction scratch forced down to a few hundred KB per half (GAMX_DIRS_HALF_BYTES): a group then
+    takes many waves with odd job counts, alternating between the two halves and the two fill streams,
+    with the traceback kernel of one wave running beside the fill of the next.  An idle lane group of a
+    wave's last warp must not touch the neighbouring half."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, "tests")
+import gen, gam_ngs_b200 as g
+from gam_ngs_b200 import capi
+rng = np.random.default_rng(5)
+n = 1501
+a, al, b, bl = gen.bulk_pairs(rng, n, 0, div=0.03, len_lo=300, len_hi=900)
+ctx = g.Context(devices=[0])
+ctx.add_contigs(np.concatenate([a, b]), np.concatenate([al, bl]))
+jobs = g.make_jobs(n)
+jobs["a_id"] = np.arange(n); jobs["b_id"] = np.arange(n, 2 * n)
+jobs["end_a"] = al - 1; jobs["end_b"] = bl - 1; jobs["band"] = 64; jobs["mode"] = capi.MODE_FULL
+res, ops = ctx.align_batch(jobs)
+np.save(sys.argv[1], res)
+np.save(sys.argv[1] + ".ops", np.array([bytes(ctx.unpack_ops(ops, int(r["ops_offset"]), int(r["n_ops"]))).hex() for r in res]))
+'''
+    outs = []
+    for tag, env in (("big", {}), ("small", {"GAMX_DIRS_HALF_BYTES": str(37 * 33 * 1024)})):
+        path = f"/tmp/gamx_waves_{tag}.npy"
+        e = dict(os.environ, **env)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=e,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        outs.append((np.load(path), np.load(path + ".ops.npy")))
+    big, small = outs
+    cols = [f for f in big[0].dtype.names if f != "ops_offset"]
+    for f in cols:
+        assert (big[0][f] == small[0][f]).all(), f
+    assert (big[1] == small[1]).all()
+    assert int((big[0]["status"] == 0).sum()) == len(big[0])
