@@ -49,8 +49,9 @@ DEFAULT_WORKLOAD = "cfg2_1M_1kb_band64_endpoints"
 ALGO_LANE_OPS_PER_CELL = 4      # select + add + max + fused add-max in 32-bit
 DIR_BYTES_PER_CELL = 0.25       # 2 direction bits per cell
 # dram__bytes_read.sum + dram__bytes_write.sum of the fill kernel + traceback kernel per DP cell, from the
-# `ncu --set full` capture of 100k config-2 pairs in profiles/ (r1d_k1_c9_lg16_fill_100k.csv)
-NCU_DRAM_BYTES_PER_CELL = 0.31
+# `ncu --set full` capture of 100k config-2 pairs in profiles/ (r1d_k1_c9_lg16_fill_tb_100k.csv: 3.64 GB written + 0.11 GB read by the fill kernel,
+# 0.89 GB read by the traceback kernel, 12.9e9 cells)
+NCU_DRAM_BYTES_PER_CELL = 0.36
 
 
 def env_int(name, default):
@@ -188,7 +189,7 @@ def run_reference(args, spec, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
