@@ -822,6 +822,7 @@ struct gamx_plan {
   uint64_t ops_total = 0;  // ops capacity over all devices
   bool ran = false;
   int slot = 0;            // which of the devices' buffer slots / streams the plan uses
+  double grid_scale = 1.0; // share of the resident block slots a fill launch takes (pipelined chunks: 0.9)
   size_t max_contig = 0;   // largest contig id a job refers to (upload dependency)
   std::string err;         // plan_build reports here (it may run on a helper thread)
 };
@@ -1458,6 +1459,13 @@ static int plan_upload(gamx_plan* pl) {
       const uint64_t pairs_per_block = cta ? 1 : (uint64_t)kWarpsPerBlock * (32 / g.lg);
       const uint64_t need = (g.job_idx.size() + pairs_per_block - 1) / pairs_per_block;
       if (need < grid) grid = need;
+      // A pipelined chunk leaves a tenth of the block slots free: the pack launches of the upload and
+      // the traceback launches of earlier chunks then find room at once instead of squeezing in beside
+      // five resident fill blocks per SM (measured: 92 -> 74 ms per 1 M pairs end to end, fill rate
+      // unchanged).  GAMX_FILL_GRID_SCALE overrides the factor (experiments).
+      static const double forced_scale = [] { const char* e = getenv("GAMX_FILL_GRID_SCALE"); return e ? atof(e) : 0.0; }();
+      const double grid_scale = forced_scale > 0.0 ? forced_scale : pl->grid_scale;
+      if (grid_scale < 1.0 && grid == (uint64_t)d.sm_count * bps) grid = (uint64_t)(grid * grid_scale);
       g.grid = (int)std::max<uint64_t>(grid, 1);
       if (g.dirs && g.max_dir_words) {
         want_words = std::max(want_words, g.max_dir_words * (uint64_t)g.job_idx.size());
@@ -1796,6 +1804,7 @@ static int align_batch_pipelined(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n
     auto t3 = t2;
     if (!rc) {
       cur.pl->slot = (int)(c % kSlots);
+      cur.pl->grid_scale = 0.9;
       rc = plan_upload(cur.pl);
       t3 = now();
       if (!rc) rc = plan_run_locked(cur.pl);
