@@ -803,6 +803,7 @@ struct DevPlan {
   uint64_t dirs_words = 0, grows = 0, gdirs = 0;  // dirs_words: one scratch half
   uint32_t n_launches = 0;
   bool two_halves = false;  // the direction scratch has a second half (some group takes several waves)
+  bool two_halves_ok = false;  // splitting a group that fits one half into waves is allowed (not for pipelined chunks)
   float last_ms = 0.f;
 };
 
@@ -823,6 +824,7 @@ struct gamx_plan {
   bool ran = false;
   int slot = 0;            // which of the devices' buffer slots / streams the plan uses
   double grid_scale = 1.0; // share of the resident block slots a fill launch takes (pipelined chunks: 0.9)
+  bool chunked = false;    // a chunk of a pipelined batch: one wave, its traceback overlaps the next chunk
   size_t max_contig = 0;   // largest contig id a job refers to (upload dependency)
   std::string err;         // plan_build reports here (it may run on a helper thread)
 };
@@ -1450,6 +1452,7 @@ static int plan_upload(gamx_plan* pl) {
     //  scratch this slot already owns is too small to hold a whole group)
     uint64_t want_words = 0, min_words = 0;
     dp.n_launches = 0;
+    dp.two_halves_ok = !pl->chunked;
     for (Group& g : dp.groups) {
       if (!g.c) { g.grid = (int)((g.job_idx.size() + 63) / 64); dp.n_launches++; continue; }
       const bool cta = g.lg > 32;
@@ -1492,15 +1495,30 @@ static int plan_upload(gamx_plan* pl) {
       if (!g.c) continue;
       if (g.dirs && g.max_dir_words) {
         g.wave_jobs = std::min<uint64_t>(half_words / g.max_dir_words, g.job_idx.size());
+        // a big group is cut into at least four waves even when one would fit, so that all but the last
+        // traceback launch run beside a fill launch (needs the second scratch half; every wave still
+        // holds several times the resident jobs)
+        if (dp.two_halves_ok) {
+          const uint64_t pairs_per_block = g.lg > 32 ? 1 : (uint64_t)kWarpsPerBlock * (32 / g.lg);
+          const uint64_t resident = (uint64_t)g.grid * pairs_per_block;
+          const uint64_t quarter = (g.job_idx.size() + 3) / 4;
+          if (quarter >= 4 * resident) g.wave_jobs = std::min(g.wave_jobs, quarter);
+        }
         dp.n_launches += (uint32_t)((g.job_idx.size() + g.wave_jobs - 1) / g.wave_jobs);
       } else {
         g.wave_jobs = g.job_idx.size();
         dp.n_launches++;
       }
     }
-    dp.dirs_words = want_words ? half_words : 0;
     // (the second half is only needed when a group takes more than one wave)
-    dp.two_halves = want_words > half_words;
+    dp.two_halves = false;
+    uint64_t used_words = 0;  // what a half really has to hold
+    for (const Group& g : dp.groups)
+      if (g.c && g.dirs && g.max_dir_words) {
+        dp.two_halves = dp.two_halves || g.wave_jobs < g.job_idx.size();
+        used_words = std::max(used_words, g.wave_jobs * g.max_dir_words);
+      }
+    dp.dirs_words = dp.two_halves ? std::min(half_words, used_words) : (want_words ? half_words : 0);
     if (int rc = ensure_dev(ctx, sl.dirs, dp.dirs_words * (dp.two_halves ? 8 : 4) + 64)) return rc;
     if (int rc = ensure_dev(ctx, sl.counters, sizeof(int) * (dp.n_launches + 1))) return rc;
     lap(2);
@@ -1805,6 +1823,7 @@ static int align_batch_pipelined(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n
     if (!rc) {
       cur.pl->slot = (int)(c % kSlots);
       cur.pl->grid_scale = 0.9;
+      cur.pl->chunked = true;
       rc = plan_upload(cur.pl);
       t3 = now();
       if (!rc) rc = plan_run_locked(cur.pl);
