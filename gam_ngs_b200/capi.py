@@ -297,7 +297,7 @@ class Context:
         out: optional caller-owned RESULT_DTYPE array of len(jobs) records to write into."""
         jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
         n = len(jobs)
-        cap = self.ops_capacity(jobs) if (jobs["mode"] == MODE_FULL).any() else 0
+        cap = self.ops_capacity(jobs) if (n and jobs["mode"].max() == MODE_FULL) else 0
         if out is not None:
             assert out.dtype == RESULT_DTYPE and len(out) == n and out.flags["C_CONTIGUOUS"]
         results = out if out is not None else np.empty(n, dtype=RESULT_DTYPE)  # every record is written by the library

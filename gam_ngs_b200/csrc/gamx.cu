@@ -1746,6 +1746,7 @@ void gamx_plan_destroy(gamx_plan* pl) { delete pl; }
 // results of chunk c-kSlots.  Each chunk's kernel is stream-ordered behind the contig upload pieces it
 // needs only, so with gamx_add_contigs_async the sequence upload, the alignment kernels, the result
 // copies and the host work all overlap.
+constexpr int kNeedsSinglePlan = 1000;  // internal: a chunk holds a FULL-mode job
 static int align_batch_pipelined(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_result* results, uint64_t chunk) {
   // chunk boundaries: two short chunks first, so that the device starts early
   std::vector<uint64_t> lo_of;
@@ -1819,6 +1820,7 @@ static int align_batch_pipelined(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n
     if (c >= (uint64_t)kSlots) finish(c - kSlots);  // frees slot c % kSlots
     const auto t2 = now();
     if (!rc && cur.rc) { rc = cur.rc; if (cur.pl) ctx->err = cur.pl->err; }
+    if (!rc && cur.pl && cur.pl->ops_total > 0) rc = kNeedsSinglePlan;
     auto t3 = t2;
     if (!rc) {
       cur.pl->slot = (int)(c % kSlots);
@@ -1869,11 +1871,11 @@ int gamx_align_batch(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_resul
   // 0 disables); FULL-mode batches need one ops buffer per device and take the single-plan path
   const uint64_t chunk_cfg = ctx->pipeline_chunk;
   if (chunk_cfg && n >= 2 * chunk_cfg) {
-    bool any_full = false;
-    for (uint64_t i = 0; i < n && !any_full; i++) any_full = jobs[i].mode == GAMX_MODE_FULL;
-    if (!any_full) {
-      if (int rc = flush_pending(ctx)) return rc;
-      const int rc = align_batch_pipelined(ctx, jobs, n, results, chunk_cfg);
+    // (no scan for FULL-mode jobs up front: the pipelined path stops at the first chunk that holds
+    //  one and reports kNeedsSinglePlan; the batch then restarts on the single-plan path)
+    if (int rc = flush_pending(ctx)) return rc;
+    const int rc = align_batch_pipelined(ctx, jobs, n, results, chunk_cfg);
+    if (rc != kNeedsSinglePlan) {
       if (timing) fprintf(stderr, "[gamx] align_batch n=%llu pipelined in chunks of %llu: %.1f ms\n", (unsigned long long)n,
                           (unsigned long long)chunk_cfg, ms(t0, now()));
       return rc;

@@ -375,6 +375,18 @@ def test_pipelined_batch_matches_single_launch_and_oracle():
             c.add_contigs(host.data_ptr(), np.array(lengths, dtype=np.uint64), async_upload=True)
             got, _ = c.align_batch(jobs)
             assert got.tobytes() == ref.tobytes(), chunk
+        # an edit string requested somewhere in the batch: the pipelined path hands the whole batch
+        # back to the single-plan path
+        jf = jobs.copy()
+        jf["mode"][2000] = capi.MODE_FULL
+        c.set_pipeline_chunk(0)
+        want, wops = c.align_batch(jf)
+        c.set_pipeline_chunk(128)
+        got, gops = c.align_batch(jf)
+        assert got.tobytes() == want.tobytes()
+        assert bytes(c.unpack_ops(gops, int(got[2000]["ops_offset"]), int(got[2000]["n_ops"]))) == \
+            bytes(c.unpack_ops(wops, int(want[2000]["ops_offset"]), int(want[2000]["n_ops"])))
+        assert int(got[2000]["n_ops"]) > 100
     finally:
         c.close()
     assert int(ref["status"][5]) == capi.JOB_EMPTY
@@ -424,3 +436,46 @@ np.save(sys.argv[1] + ".ops", np.array([bytes(ctx.unpack_ops(ops, int(r["ops_off
         assert (big[0][f] == small[0][f]).all(), f
     assert (big[1] == small[1]).all()
     assert int((big[0]["status"] == 0).sum()) == len(big[0])
+
+
+def test_multi_device_context_matches_single_device():
+    """One context over two GPUs (the library's own cost-balanced sharding, host gather, no
+    collective): same results as one device, for a mixed batch (several kernel families, all modes)
+    and for a pipelined batch.  Skipped on a single-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(21)
+    n = 2400
+    lens = np.exp(rng.uniform(np.log(200), np.log(6000), size=n)).astype(np.int64)
+    a, al, b, bl = gen.bulk_pairs(rng, n, 0, div=0.03, lengths=lens)
+    jobs = g.make_jobs(n)
+    jobs["a_id"] = np.arange(n); jobs["b_id"] = np.arange(n, 2 * n)
+    jobs["end_a"], jobs["end_b"] = al - 1, bl - 1
+    jobs["band"] = rng.choice([16, 64, 150, 300], size=n)
+    jobs["mode"] = rng.choice([capi.MODE_SCORE, capi.MODE_ENDPOINTS, capi.MODE_FULL], size=n)
+    outs = []
+    for devs in ([0], [0, 1]):
+        c = g.Context(devices=devs)
+        try:
+            c.add_contigs(np.concatenate([a, b]), np.concatenate([al, bl]))
+            res, ops = c.align_batch(jobs)
+            strings = [bytes(c.unpack_ops(ops, int(r["ops_offset"]), int(r["n_ops"]))) if m == capi.MODE_FULL else b""
+                       for r, m in zip(res, jobs["mode"])]
+            j2 = jobs.copy()
+            j2["mode"] = np.where(j2["mode"] == capi.MODE_FULL, capi.MODE_ENDPOINTS, j2["mode"])
+            c.set_pipeline_chunk(300)
+            piped, _ = c.align_batch(j2)
+            outs.append((res, strings, piped))
+        finally:
+            c.close()
+    (r1, s1, p1), (r2, s2, p2) = outs
+    for f in r1.dtype.names:
+        if f != "ops_offset":
+            assert (r1[f] == r2[f]).all(), f
+    assert s1 == s2
+    assert p1.tobytes() == p2.tobytes()
+    ep = jobs["mode"] == capi.MODE_ENDPOINTS
+    for f in r1.dtype.names:
+        if f != "ops_offset":  # (meaningless without an edit string)
+            assert (r1[ep][f] == p1[ep][f]).all(), f
