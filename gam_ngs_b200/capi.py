@@ -16,6 +16,7 @@ MODE_SCORE, MODE_ENDPOINTS, MODE_FULL = 0, 1, 2
 JOB_OK, JOB_EMPTY, JOB_OUT_OF_RANGE, JOB_UNDEFINED = 0, 1, 2, 3
 DEFAULT_BAND, DEFAULT_GAP = 150, -8
 U64_MAX = 2**64 - 1
+ERR_OPS_CAPACITY = -4
 
 
 class GamxJob(C.Structure):
@@ -297,13 +298,21 @@ class Context:
         out: optional caller-owned RESULT_DTYPE array of len(jobs) records to write into."""
         jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
         n = len(jobs)
-        cap = self.ops_capacity(jobs) if (n and jobs["mode"].max() == MODE_FULL) else 0
         if out is not None:
             assert out.dtype == RESULT_DTYPE and len(out) == n and out.flags["C_CONTIGUOUS"]
         results = out if out is not None else np.empty(n, dtype=RESULT_DTYPE)  # every record is written by the library
+        # large batches are first tried without an ops buffer (no scan of the modes on the Python side);
+        # the library answers ERR_OPS_CAPACITY when some job wants its edit string
+        cap = 0
+        if n < 100000 and n and jobs["mode"].max() == MODE_FULL:
+            cap = self.ops_capacity(jobs)
         ops = np.zeros((cap + 3) // 4 + 8, dtype=np.uint8)
-        self._check(self.lib.gamx_align_batch(self._h, jobs.ctypes.data, n, results.ctypes.data,
-                                              ops.ctypes.data, cap))
+        rc = self.lib.gamx_align_batch(self._h, jobs.ctypes.data, n, results.ctypes.data, ops.ctypes.data, cap)
+        if rc == ERR_OPS_CAPACITY and cap == 0:
+            cap = self.ops_capacity(jobs)
+            ops = np.zeros((cap + 3) // 4 + 8, dtype=np.uint8)
+            rc = self.lib.gamx_align_batch(self._h, jobs.ctypes.data, n, results.ctypes.data, ops.ctypes.data, cap)
+        self._check(rc)
         return results, ops
 
     def find_hits_batch(self, jobs: np.ndarray) -> np.ndarray:
