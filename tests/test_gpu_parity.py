@@ -479,3 +479,67 @@ def test_multi_device_context_matches_single_device():
     for f in r1.dtype.names:
         if f != "ops_offset":  # (meaningless without an edit string)
             assert (r1[ep][f] == p1[ep][f]).all(), f
+
+
+def test_config2_full_size_properties():
+    """BASELINE.json configs[1] at its full size (1,000,000 pairs of 1 kb, band 64, score+endpoints):
+    three independent product paths - resident plan (two waves), single-launch gamx_align_batch and the
+    pipelined gamx_align_batch behind an asynchronous piece-wise upload - must agree bit for bit; every
+    alignment must satisfy the size-independent invariants of a banded overlap alignment; a seeded
+    sample is checked against the oracle."""
+    import torch
+    n = 1_000_000
+    rng = np.random.default_rng(2024)
+    a, al, b, bl = gen.bulk_pairs(rng, n, 1000, div=0.02)
+    ao = np.concatenate([[0], np.cumsum(al)]).astype(np.int64)
+    bo = np.concatenate([[0], np.cumsum(bl)]).astype(np.int64)
+    host = torch.empty(len(a) + len(b), dtype=torch.uint8, pin_memory=True)
+    hv = host.numpy()
+    lengths = np.empty(2 * n, dtype=np.uint64)
+    a_id = np.empty(n, np.uint32); b_id = np.empty(n, np.uint32)
+    pos = cid = 0
+    for lo in range(0, n, 16384):
+        hi = min(n, lo + 16384)
+        for src, off, ln, ids in ((a, ao, al, a_id), (b, bo, bl, b_id)):
+            seg = src[off[lo]:off[hi]]
+            hv[pos:pos + len(seg)] = seg; pos += len(seg)
+            lengths[cid:cid + hi - lo] = ln[lo:hi]
+            ids[lo:hi] = np.arange(cid, cid + hi - lo); cid += hi - lo
+    jobs = g.make_jobs(n)
+    jobs["a_id"], jobs["b_id"] = a_id, b_id
+    jobs["end_a"], jobs["end_b"] = al - 1, bl - 1
+    jobs["band"] = 64
+    jobs["mode"] = capi.MODE_ENDPOINTS
+    c = g.Context(devices=[0])
+    try:
+        c.add_contigs(host.data_ptr(), lengths)
+        plan = c.plan(jobs); plan.run(); plan.sync()
+        ref, _ = plan.fetch()
+        plan.close()
+        c.set_pipeline_chunk(0)
+        single, _ = c.align_batch(jobs)
+        assert single.tobytes() == ref.tobytes()
+        c.set_pipeline_chunk(65536)
+        c.clear_contigs()
+        c.add_contigs(host.data_ptr(), lengths, async_upload=True)
+        piped, _ = c.align_batch(jobs)
+        assert piped.tobytes() == ref.tobytes()
+    finally:
+        c.close()
+    r = ref
+    assert (r["status"] == 0).all()
+    m, x, ga, gb = (r[f].astype(np.int64) for f in ("n_match", "n_mismatch", "n_gap_a", "n_gap_b"))
+    assert (r["n_ops"].astype(np.int64) == m + x + ga + gb).all()
+    end_a_pos = r["end_i"] + r["end_j"] - 64                     # a-position of the end cell
+    assert (r["begin_a"].astype(np.int64) + m + x + gb == end_a_pos + 1).all()
+    assert (r["begin_b"].astype(np.int64) + m + x + ga == r["end_i"] + 1).all()
+    face = 5 * m - 4 * x - 8 * (ga + gb)                          # no N in this workload
+    assert (r["score"] >= face).all() and (r["score"] <= face + 8 * gb).all()  # (row-0 GAP_B moves are free, .cc:120)
+    # overlap alignments end in the last row or in the last column
+    assert ((r["end_i"] == bl.astype(np.int64) - 1) | (end_a_pos == al.astype(np.int64) - 1)).all()
+    assert (r["homology"] > 90.0).mean() > 0.999                 # 2 % divergence
+    for k in rng.choice(n, size=120, replace=False):
+        A, B = a[ao[k]:ao[k + 1]], b[bo[k]:bo[k + 1]]
+        case = dict(a=A, b=B, begin_a=0, end_a=len(A) - 1, begin_b=0, end_b=len(B) - 1, band=64, gap=-8,
+                    force_start=False, force_end=False)
+        assert result_to_expect(None, r[k], None, capi.MODE_ENDPOINTS) == project(oracle_expect(case), capi.MODE_ENDPOINTS), k
