@@ -49,9 +49,9 @@ DEFAULT_WORKLOAD = "cfg2_1M_1kb_band64_endpoints"
 ALGO_LANE_OPS_PER_CELL = 4      # select + add + max + fused add-max in 32-bit
 DIR_BYTES_PER_CELL = 0.25       # 2 direction bits per cell
 # dram__bytes_read.sum + dram__bytes_write.sum of the fill kernel + traceback kernel per DP cell, from the
-# `ncu --set full` capture of 100k config-2 pairs in profiles/ (r1d_k1_c9_lg16_fill_tb_100k.csv: 3.64 GB written + 0.11 GB read by the fill kernel,
-# 0.89 GB read by the traceback kernel, 12.9e9 cells)
-NCU_DRAM_BYTES_PER_CELL = 0.36
+# `ncu --set full` capture of 100k config-2 pairs in profiles/ (r1e_k1_c9_lg16_fill_tb_100k.csv, first wave = 25,000 pairs = 3.2e9 cells: 867 MB
+# written + 28 MB read by the fill kernel, 223 MB read + 7 MB written by the traceback kernel)
+NCU_DRAM_BYTES_PER_CELL = 0.35
 
 
 def env_int(name, default):
@@ -67,8 +67,10 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """Samples nvidia-smi clocks / throttle reasons.  nvidia-smi is started early (it can take longer to
+    come up than the whole timed region lasts); only the samples whose timestamps fall inside the
+    window marked by begin()/end() are reported."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -76,45 +78,64 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.path = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
+        time.sleep(0.12)  # let the sample that covers the end of the window arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, reasons, smax = [], set(), None
+        rows = []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
-                if len(f) < 9:
+                if len(f) < 10:
                     continue
                 try:
-                    sm.append(float(f[1])); smax = float(f[2])
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(f[2]), float(f[3]), f[6:10]))
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            busy = [x for x in sm if x > 0.5 * max(sm)] or sm
-            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=smax, reasons=sorted(reasons), samples=len(sm))
+        if not rows:
+            return out
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.05 <= r[0] <= (self.t1 or r[0]) + 0.1]
+        where = "timed region"
+        if not inside:  # clock skew between nvidia-smi's timestamps and time.time(): fall back to the busy samples
+            top = max(r[1] for r in rows)
+            inside = [r for r in rows if r[1] > 0.5 * top]
+            where = "whole run (no sample fell inside the timed region)"
+        reasons = set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        out.update(sm_mhz=statistics.median(r[1] for r in inside), sm_max_mhz=inside[-1][2], reasons=sorted(reasons),
+                   samples=len(inside), window=where)
         return out
 
 
@@ -260,11 +281,12 @@ def main():
     ctx.add_contigs(host.data_ptr(), lengths)
     plan = ctx.plan(jobs)
     cells = plan.cells
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         plan.run(); plan.sync()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.begin()
     t0 = time.perf_counter()
     dev_ms = 0.0
     for _ in range(args.steps):
@@ -272,6 +294,7 @@ def main():
         dev_ms += plan.last_ms  # CUDA events on the launching stream (this device)
     torch.cuda.synchronize()
     wall_s = time.perf_counter() - t0
+    sampler.end()
     barrier()
     clocks = sampler.stop()
     launches = plan.kernel_launches * args.steps
