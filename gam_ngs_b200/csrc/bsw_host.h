@@ -97,11 +97,16 @@ inline void geometry_for_band(uint64_t band, bool dirs, int* c_out, int* lg_out)
     const int lg = lgs[n];
     int c = (int)((y + lg - 1) / lg);
     if (c < 2) c = 2;
+    // stripes of 13 or 17 slots read their selector windows with a lane stride of 6 or 8 words: 2- and
+    // 8-way shared-memory bank conflicts that make the LSU the bottleneck (band 256, score only: 2963
+    // GCUPS with C = 17, 4735 with C = 18) - take one slot more
+    static const bool no_even = getenv("GAMX_NO_EVEN_C") != nullptr;  // experiments only
+    if (!no_even && (c == 13 || c == 17) && c + 1 <= kMaxC) c++;
     if (forced_c > c && forced_c <= kMaxC) c = forced_c;
     if (c > kMaxC) continue;
     if (forced && lg != forced && (y + forced - 1) / forced <= (uint64_t)kMaxC) continue;
     if (!forced && lg < 32 && c < 5 && y > 64) continue;
-    const double score = (double)y / (double)(lg * c) * (c > 12 ? 0.94 : 1.0);
+    const double score = (double)y / (double)(lg * c);
     if (score > best + 1e-9) { best = score; best_c = c; best_lg = lg; }
   }
   *c_out = best_c; *lg_out = best_lg;
@@ -115,6 +120,7 @@ inline bool geometry_cta(uint64_t band, int* c_out, int* lg_out) {
     const int lg = lgs[n];
     int c = (int)((y + lg - 1) / lg);
     if (c < 2) c = 2;
+    if ((c == 13 || c == 17) && c + 1 <= kMaxC) c++;  // (bank conflicts of the selector loads, see geometry_for_band)
     if (c > kMaxC) continue;
     *c_out = c; *lg_out = lg;
     return true;

@@ -63,11 +63,35 @@ GAMX_HD constexpr int unroll_of(int c) { return c <= GAMX_UF4_MAX_C ? 4 : 2; }
 
 struct alignas(16) Quad { uint32_t v[4]; };
 
+// Selector windows are 16-bit, and lane gl reads window gl*(C-1) + t + 4q: with C = 9 (band 64, the
+// headline shape) the lane stride is 4 words, i.e. 4-way bank conflicts on every selector load, and
+// the LSU pipe (one wavefront per cycle per SM, shared by the four schedulers) becomes a
+// co-bottleneck.  For C = 9 the array is therefore stored with one unused element after every four
+// windows: window w lives at w + (w >> 2), the lane stride becomes 10 elements = 5 words
+// (conflict-free), and because steady-state groups start at multiples of 4 every offset inside a
+// group is still a compile-time constant.  (Measured, band 64 score only: 3686 -> 4529 GCUPS.  C = 13
+// and 17 have the same problem and are avoided by the host, bsw_host.h; C = 5 measured no gain.)
+GAMX_HD constexpr bool asel_padded(int c) { return c == 9; }
+template <int C>
+GAMX_HD constexpr int asel_phys(int w) { return asel_padded(C) ? w + (w >> 2) : w; }
+// the groups of a warp sit in consecutive GroupSmem objects: their size is padded so that the second
+// group of a 16-lane pair lands 16 banks away (8 banks per group for 8-lane groups) and the groups'
+// selector loads do not collide with each other either
+GAMX_HD constexpr int group_bank_words(int lg) { return lg == 16 ? 16 : (lg == 8 ? 8 : 0); }
+template <int C, int LG>
+struct GroupSmemSizes {
+  static constexpr int kAsel = ((asel_phys<C>(kTileSteps + LG * C + 8) + 8 + 7) / 8) * 8;  // elements
+  static constexpr int kBaseBytes = (kTileSteps + LG) * 8 + kAsel * 2 + C * LG * 4;
+  static constexpr int kShift = (group_bank_words(LG) - (kBaseBytes / 4) % 32 + 64) % 32;  // words to add so that size/4 % 32 is the target
+  static constexpr int kPadWords = (LG >= 32 || !asel_padded(C)) ? 4 : (kShift == 0 ? 32 : kShift);
+};
+
 template <int C, int LG>
 struct alignas(16) GroupSmem {
-  uint64_t btab[kTileSteps + LG];            // b-rows of the tile as 8-byte Cd tables
-  uint16_t asel[kTileSteps + LG * C + 8];    // a-bases as 4-nibble windows: codes of positions p..p+3
-  int cap[C * LG];                           // latched "last column" cells, [slot][lane]
+  uint64_t btab[kTileSteps + LG];               // b-rows of the tile as 8-byte Cd tables
+  uint16_t asel[GroupSmemSizes<C, LG>::kAsel];  // a-bases as 4-nibble windows: codes of positions p..p+3 (asel_phys)
+  int cap[C * LG];                              // latched "last column" cells, [slot][lane]
+  uint32_t bank_shift[GroupSmemSizes<C, LG>::kPadWords];
 };
 template <int C, int LG>
 struct WarpSmem {
@@ -195,9 +219,14 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
         const uint32_t x = j == 0 ? nlo : funnel_r(nlo, nhi, 8u * j);   /* nibbles 2j .. 2j+7 */      \
         ow[j] = (x & 0xffffu) | ((x << 12) & 0xffff0000u);               /* windows 2j, 2j+1 */        \
       }                                                                                               \
-      Quad qv;                                                                                        \
-      qv.v[0] = ow[0]; qv.v[1] = ow[1]; qv.v[2] = ow[2]; qv.v[3] = ow[3];                             \
-      *reinterpret_cast<Quad*>(sm.asel + c0) = qv;    /* c0 % 8 == 0: 16-byte aligned */              \
+      if (asel_padded(C)) {                                                                           \
+        _Pragma("unroll") for (int q = 0; q < 8; q++)                                                 \
+          sm.asel[asel_phys<C>(c0 + q)] = (uint16_t)(ow[q >> 1] >> (16 * (q & 1)));                   \
+      } else {                                                                                        \
+        Quad qv;                                                                                      \
+        qv.v[0] = ow[0]; qv.v[1] = ow[1]; qv.v[2] = ow[2]; qv.v[3] = ow[3];                           \
+        *reinterpret_cast<Quad*>(sm.asel + c0) = qv;  /* c0 % 8 == 0: 16-byte aligned */              \
+      }                                                                                               \
     }                                                                                                 \
     const int nb = kTileSteps + LG - 1;                                                               \
     for (int r0 = gl * 8; r0 < nb; r0 += LG * 8) {                                                    \
@@ -226,7 +255,6 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
   // a prefix maximum of S that restarts at the cell with pos == 0.  Never-written cells are 0.
   GAMX_STAGE_TILE(0)
   {
-    const uint16_t* pa = sm.asel + gl * (C - 1);
     const uint64_t tb = sm.btab[LG - 1];  // row 0
     const uint32_t tlo = (uint32_t)tb, thi = (uint32_t)(tb >> 32);
     const int kNone = -(1 << 28);
@@ -235,7 +263,7 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
 #pragma unroll
     for (int k = 0; k < C; k++) {
       const int j = j0 + k, pos = p0 + j;
-      const uint32_t cd4 = prmt(tlo, thi, pa[gl + 4 * (k / 4)]);
+      const uint32_t cd4 = prmt(tlo, thi, sm.asel[asel_phys<C>(gl * C + 4 * (k / 4))]);
       const int cd = (int)((cd4 >> (8 * (k % 4))) & 0xffu);
       const bool valid = live && pos >= 0 && pos < la && j < Y;
       sc[k] = valid ? cd : -1;                        // Cd byte of the cell, -1: never written
@@ -278,11 +306,13 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
   }
 
   // The Cd bytes of one step: PA / PB point at the selector windows / row table of that step.
-#define GAMX_LOAD_CD(CD, PA, PB)                                                                      \
+  // PA + PHYS(J0 + 4q) is the selector window of slots 4q.. of that step (PHYS: asel_phys relative
+  // to a window index that is a multiple of 4, so that it is a compile-time constant in the FAST path)
+#define GAMX_LOAD_CD(CD, PA, J0, PB)                                                                  \
   {                                                                                                   \
     const uint64_t tb = *(PB);                                                                        \
     const uint32_t tlo = (uint32_t)tb, thi = (uint32_t)(tb >> 32);                                    \
-    _Pragma("unroll") for (int q = 0; q < NQ; q++) (CD)[q] = prmt(tlo, thi, (PA)[4 * q]);             \
+    _Pragma("unroll") for (int q = 0; q < NQ; q++) (CD)[q] = prmt(tlo, thi, (PA)[asel_phys<C>((J0) + 4 * q)]); \
   }
   // One step tt with its Cd bytes in CD.  SLOW: lanes whose row is outside [1, X-1] keep their
   // registers (direction words keep shifting once a lane has started), "last column" cells are
@@ -323,7 +353,7 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
   int t0 = 0;
   while (t < T_total) {
     if (t >= t0 + kTileSteps) { t0 += kTileSteps; GAMX_STAGE_TILE(t0) }
-    const uint16_t* pa = sm.asel + (gl * (C - 1) - t0);    // pa[t + k]: window starting at slot k's base at step t
+    const int wl = gl * (C - 1);                           // window of this lane's slot 0 at step t0 (with padding: a multiple of 4)
     const uint64_t* pb = sm.btab + ((LG - 1) - gl - t0);   // pb[t]: table of row t - gl
     const int stop = imin(t0 + kTileSteps, T_total);       // first step this tile does not cover
     while (t < stop) {
@@ -337,20 +367,21 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
         // the cells of step t, so their latency never sits in front of a step's dependent chain
         // (the look-ahead of a group's last step reads one entry past the group: inside the arrays,
         // and overwritten before use when it belongs to the next tile)
-        const uint16_t* pa_t = pa + t;
+        // (t - t0 and wl are multiples of 4 when the array is padded: UF = 4 there)
+        const uint16_t* pa_t = sm.asel + asel_phys<C>(wl + (t - t0));
         const uint64_t* pb_t = pb + t;
         uint32_t cdn[NQ];
-        GAMX_LOAD_CD(cdn, pa_t, pb_t)
+        GAMX_LOAD_CD(cdn, pa_t, 0, pb_t)
         do {
 #pragma unroll
           for (int u = 0; u < UF; u++) {
             uint32_t cd4[NQ];
 #pragma unroll
             for (int q = 0; q < NQ; q++) cd4[q] = cdn[q];
-            GAMX_LOAD_CD(cdn, pa_t + u + 1, pb_t + u + 1)
+            GAMX_LOAD_CD(cdn, pa_t, u + 1, pb_t + u + 1)
             GAMX_STEP(false, t + u, cd4)
           }
-          t += UF; pa_t += UF; pb_t += UF;
+          t += UF; pa_t += asel_phys<C>(UF); pb_t += UF;
           if (DIRS && (t & 15) == 0) {
 #pragma unroll
             for (int k = 0; k < C; k++) if (live) fp[k * LG] = acc[k];  // (an idle group owns no scratch)
@@ -361,7 +392,13 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
         const int slow_stop = imin(stop, (t & ~(UF - 1)) + UF);  // up to the next group boundary
         do {
           uint32_t cd4[NQ];
-          GAMX_LOAD_CD(cd4, pa + t, pb + t)
+          {  // any t: the physical index is computed at run time
+            const uint64_t tb = pb[t];
+            const uint32_t tlo = (uint32_t)tb, thi = (uint32_t)(tb >> 32);
+            const int w0 = wl + (t - t0);
+#pragma unroll
+            for (int q = 0; q < NQ; q++) cd4[q] = prmt(tlo, thi, sm.asel[asel_phys<C>(w0 + 4 * q)]);
+          }
           GAMX_STEP(true, t, cd4)
           t++;
         } while (t < slow_stop);
