@@ -354,13 +354,16 @@ def main():
                "includes": "raw sequence H2D from pinned memory + device 2-bit pack, job descriptor H2D, kernels, result D2H",
                "pipeline": "chunks of 65536 jobs over 4 buffer slots/streams; upload pieces of 64 MB on their own stream"}
     # ---- roofline --------------------------------------------------------------------------------
+    geo = capi.band_geometry(spec["band"]) or (0, 0)
+    kernel_name = f"{'k1' if geo[1] <= 32 else 'k2'}_kernel<{geo[0]},{geo[1]},{'true' if spec['mode'] else 'false'}>" + \
+                  (" (+ tb_kernel)" if spec["mode"] else "")
     peaks, peak_src = load_peaks()
     kernel_s = dev_s / args.steps
     cells_rank = float(cells)
     ach_int = cells_rank / (dev_ms * 1e-3 / args.steps) * ALGO_LANE_OPS_PER_CELL / 1e12
     roofline = {"bound": "int_alu", "achieved": ach_int, "peak": int_peak / 1e12, "unit": "Tlaneop/s",
                 "frac": ach_int / (int_peak / 1e12) if int_peak else None, "traffic": None,
-                "kernel": "k1_kernel<9,16,true> (+ tb_kernel)" if spec["mode"] else "k1_kernel<9,16,false>",
+                "kernel": kernel_name,
                 "algorithmic": f"{ALGO_LANE_OPS_PER_CELL} int32 lane-ops per cell (SURVEY 8d) x {int(cells_rank)} cells per launch",
                 "peak_source": "VIADDMNMX issue rate measured live by gamx_measure_int_peak (register-only kernel)"}
     seq_bytes = total_bases * 3 / 8

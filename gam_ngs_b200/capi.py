@@ -90,7 +90,7 @@ EXPORTS = [
     "gamx_ops_capacity", "gamx_set_pipeline_chunk", "gamx_align_batch", "gamx_unpack_ops", "gamx_cigar_rle",
     "gamx_plan_create", "gamx_plan_run", "gamx_plan_sync", "gamx_plan_fetch", "gamx_plan_last_ms",
     "gamx_plan_cells", "gamx_plan_kernel_launches", "gamx_plan_destroy", "gamx_measure_int_peak",
-    "gamx_shard_by_cost", "gamx_find_hits_batch", "gamx_merge_align",
+    "gamx_shard_by_cost", "gamx_find_hits_batch", "gamx_merge_align", "gamx_band_geometry",
 ]
 
 _lib = None
@@ -162,10 +162,20 @@ def load_library(build_if_missing: bool = True):
     L.gamx_find_hits_batch.restype = C.c_int
     L.gamx_merge_align.argtypes = [vp, vp, u64, vp, u64, vp, vp]
     L.gamx_merge_align.restype = C.c_int
+    L.gamx_band_geometry.argtypes = [u64, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.gamx_band_geometry.restype = C.c_int
     L.gamx_measure_int_peak.argtypes = [vp, C.c_int, C.c_int]
     L.gamx_measure_int_peak.restype = C.c_double
     _lib = L
     return L
+
+
+def band_geometry(band: int):
+    """(stripe width C, lanes per pair LG) of the fill kernel a band width maps to."""
+    c, lg = C.c_int(0), C.c_int(0)
+    if load_library().gamx_band_geometry(int(band), C.byref(c), C.byref(lg)) != 0:
+        return None
+    return c.value, lg.value
 
 
 def make_hits_jobs(n: int) -> np.ndarray:

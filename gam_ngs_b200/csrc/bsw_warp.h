@@ -51,7 +51,7 @@
 namespace gamx {
 
 constexpr int kTileSteps = 128;  // steps per shared-memory sequence tile
-constexpr int kMaxC = 18;        // widest lane stripe: band <= (32*18-1)/2 = 287
+constexpr int kMaxC = 18;        // widest lane stripe: band <= (32*18-1)/2 = 287 (19 and 20 were tried: no gain)
 
 GAMX_HD constexpr bool stripe_supported(int c) { return c >= 2 && c <= kMaxC; }
 // steps per unrolled steady-state group (divides 16, so that a direction flush falls on a group end):
@@ -63,35 +63,19 @@ GAMX_HD constexpr int unroll_of(int c) { return c <= GAMX_UF4_MAX_C ? 4 : 2; }
 
 struct alignas(16) Quad { uint32_t v[4]; };
 
-// Selector windows are 16-bit, and lane gl reads window gl*(C-1) + t + 4q: with C = 9 (band 64, the
-// headline shape) the lane stride is 4 words, i.e. 4-way bank conflicts on every selector load, and
-// the LSU pipe (one wavefront per cycle per SM, shared by the four schedulers) becomes a
-// co-bottleneck.  For C = 9 the array is therefore stored with one unused element after every four
-// windows: window w lives at w + (w >> 2), the lane stride becomes 10 elements = 5 words
-// (conflict-free), and because steady-state groups start at multiples of 4 every offset inside a
-// group is still a compile-time constant.  (Measured, band 64 score only: 3686 -> 4529 GCUPS.  C = 13
-// and 17 have the same problem and are avoided by the host, bsw_host.h; C = 5 measured no gain.)
-GAMX_HD constexpr bool asel_padded(int c) { return c == 9; }
+// Selector windows are 16-bit and lane gl reads window gl*(C-1) + t + 4q, so the lane stride is
+// (C-1)/2 words: stripe widths with C-1 = 8, 12 or 16 read them with 4-, 2- and 8-way bank conflicts,
+// and the LSU pipe (one wavefront per cycle per SM for all four schedulers) then limits the kernel.
+// The host avoids those widths (bsw_host.h: 13 -> 14, 17 -> 18, and bands that would take 16 lanes x 9
+// slots take 8 lanes x 18 instead).  (A padded layout for C = 9 was tried and measured no gain.)
 template <int C>
-GAMX_HD constexpr int asel_phys(int w) { return asel_padded(C) ? w + (w >> 2) : w; }
-// the groups of a warp sit in consecutive GroupSmem objects: their size is padded so that the second
-// group of a 16-lane pair lands 16 banks away (8 banks per group for 8-lane groups) and the groups'
-// selector loads do not collide with each other either
-GAMX_HD constexpr int group_bank_words(int lg) { return lg == 16 ? 16 : (lg == 8 ? 8 : 0); }
-template <int C, int LG>
-struct GroupSmemSizes {
-  static constexpr int kAsel = ((asel_phys<C>(kTileSteps + LG * C + 8) + 8 + 7) / 8) * 8;  // elements
-  static constexpr int kBaseBytes = (kTileSteps + LG) * 8 + kAsel * 2 + C * LG * 4;
-  static constexpr int kShift = (group_bank_words(LG) - (kBaseBytes / 4) % 32 + 64) % 32;  // words to add so that size/4 % 32 is the target
-  static constexpr int kPadWords = (LG >= 32 || !asel_padded(C)) ? 4 : (kShift == 0 ? 32 : kShift);
-};
+GAMX_HD constexpr int asel_phys(int w) { return w; }
 
 template <int C, int LG>
 struct alignas(16) GroupSmem {
-  uint64_t btab[kTileSteps + LG];               // b-rows of the tile as 8-byte Cd tables
-  uint16_t asel[GroupSmemSizes<C, LG>::kAsel];  // a-bases as 4-nibble windows: codes of positions p..p+3 (asel_phys)
-  int cap[C * LG];                              // latched "last column" cells, [slot][lane]
-  uint32_t bank_shift[GroupSmemSizes<C, LG>::kPadWords];
+  uint64_t btab[kTileSteps + LG];            // b-rows of the tile as 8-byte Cd tables
+  uint16_t asel[kTileSteps + LG * C + 16];   // a-bases as 4-nibble windows: codes of positions p..p+3
+  int cap[C * LG];                           // latched "last column" cells, [slot][lane]
 };
 template <int C, int LG>
 struct WarpSmem {
@@ -219,14 +203,9 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
         const uint32_t x = j == 0 ? nlo : funnel_r(nlo, nhi, 8u * j);   /* nibbles 2j .. 2j+7 */      \
         ow[j] = (x & 0xffffu) | ((x << 12) & 0xffff0000u);               /* windows 2j, 2j+1 */        \
       }                                                                                               \
-      if (asel_padded(C)) {                                                                           \
-        _Pragma("unroll") for (int q = 0; q < 8; q++)                                                 \
-          sm.asel[asel_phys<C>(c0 + q)] = (uint16_t)(ow[q >> 1] >> (16 * (q & 1)));                   \
-      } else {                                                                                        \
-        Quad qv;                                                                                      \
-        qv.v[0] = ow[0]; qv.v[1] = ow[1]; qv.v[2] = ow[2]; qv.v[3] = ow[3];                           \
-        *reinterpret_cast<Quad*>(sm.asel + c0) = qv;  /* c0 % 8 == 0: 16-byte aligned */              \
-      }                                                                                               \
+      Quad qv;                                                                                        \
+      qv.v[0] = ow[0]; qv.v[1] = ow[1]; qv.v[2] = ow[2]; qv.v[3] = ow[3];                             \
+      *reinterpret_cast<Quad*>(sm.asel + c0) = qv;    /* c0 % 8 == 0: 16-byte aligned */              \
     }                                                                                                 \
     const int nb = kTileSteps + LG - 1;                                                               \
     for (int r0 = gl * 8; r0 < nb; r0 += LG * 8) {                                                    \
@@ -353,7 +332,7 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
   int t0 = 0;
   while (t < T_total) {
     if (t >= t0 + kTileSteps) { t0 += kTileSteps; GAMX_STAGE_TILE(t0) }
-    const int wl = gl * (C - 1);                           // window of this lane's slot 0 at step t0 (with padding: a multiple of 4)
+    const int wl = gl * (C - 1);                           // window of this lane's slot 0 at step t0
     const uint64_t* pb = sm.btab + ((LG - 1) - gl - t0);   // pb[t]: table of row t - gl
     const int stop = imin(t0 + kTileSteps, T_total);       // first step this tile does not cover
     while (t < stop) {
@@ -367,7 +346,6 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
         // the cells of step t, so their latency never sits in front of a step's dependent chain
         // (the look-ahead of a group's last step reads one entry past the group: inside the arrays,
         // and overwritten before use when it belongs to the next tile)
-        // (t - t0 and wl are multiples of 4 when the array is padded: UF = 4 there)
         const uint16_t* pa_t = sm.asel + asel_phys<C>(wl + (t - t0));
         const uint64_t* pb_t = pb + t;
         uint32_t cdn[NQ];

@@ -58,7 +58,7 @@ struct DevWarp {
 // shuffle / dependent-chain latencies and the leader-only traceback.  Measured +4..16 % across bands
 // against an unconstrained build in the same run (profiles/r1c_geometry_probe.txt).
 #ifndef GAMX_K1_MIN_BLOCKS
-#define GAMX_K1_MIN_BLOCKS(C) ((C) <= 6 ? 8 : ((C) <= 10 ? 5 : ((C) <= 14 ? 4 : 3)))
+#define GAMX_K1_MIN_BLOCKS(C) ((C) <= 6 ? 8 : ((C) <= 10 ? 5 : 4))
 #endif
 template <int C, int LG, bool DIRS>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, GAMX_K1_MIN_BLOCKS(C))
@@ -1413,6 +1413,12 @@ static int blocks_per_sm_cached(int c, int lg, bool dirs) {
   if (v == 0) {
     const int b = lg > 32 ? k2_blocks_per_sm(c, lg, dirs) : k1_blocks_per_sm(c, lg, dirs);
     v = b > 0 ? b : -1;
+    if (getenv("GAMX_TIMING")) {
+      cudaFuncAttributes fa = {};
+      if (c == 9 && lg == 16) cudaFuncGetAttributes(&fa, dirs ? (const void*)k1_kernel<9, 16, true> : (const void*)k1_kernel<9, 16, false>);
+      fprintf(stderr, "[gamx] kernel family C=%d LG=%d dirs=%d: %d resident blocks per SM (numRegs %d, static smem %zu)\n", c, lg,
+              (int)dirs, b, fa.numRegs, fa.sharedSizeBytes);
+    }
   }
   return v > 0 ? v : 0;
 }
@@ -2259,6 +2265,14 @@ int gamx_shard_by_cost(const uint64_t* cost, uint64_t n, int n_shards, int32_t* 
   for (uint64_t i = 0; i < n; i++) order[i] = (uint32_t)i;
   std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cost[a] > cost[b]; });
   lpt_assign(order, n_shards, [&](uint32_t i) { return cost[i]; }, shard_out);
+  return GAMX_OK;
+}
+
+int gamx_band_geometry(uint64_t band, int* stripe_width, int* lanes_per_pair) {
+  if (!stripe_width || !lanes_per_pair || band > kMaxBandCta) return GAMX_ERR_INVALID;
+  const uint64_t y = 2 * band + 1;
+  if (y <= 32ull * kMaxC) geometry_for_band(band, true, stripe_width, lanes_per_pair);
+  else if (!geometry_cta(band, stripe_width, lanes_per_pair)) return GAMX_ERR_INVALID;
   return GAMX_OK;
 }
 

@@ -277,6 +277,11 @@ GAMX_API int gamx_merge_align(gamx_ctx* ctx, const gamx_merge_block* mbs, uint64
  * same way: shard_out[i] in [0, n_shards) for job i of cost cost[i].  Pure host code. */
 GAMX_API int gamx_shard_by_cost(const uint64_t* cost, uint64_t n, int n_shards, int32_t* shard_out);
 
+/* Which fill kernel a band width maps to: *stripe_width = C (band columns per lane) and
+ * *lanes_per_pair = LG (8, 16, 32: warp-level kernel K1, 32/LG pairs per warp; 64, 128, 256: CTA-per-pair
+ * kernel K2).  Returns 0, or GAMX_ERR_INVALID when the band needs the generic kernel.  Pure host code. */
+GAMX_API int gamx_band_geometry(uint64_t band, int* stripe_width, int* lanes_per_pair);
+
 /* ---- microbenchmarks used for the roofline denominators (bench.py) ------------------ */
 
 /* Measures the integer/DPX issue peak of device `dev_index` of the context with a
