@@ -49,9 +49,9 @@ DEFAULT_WORKLOAD = "cfg2_1M_1kb_band64_endpoints"
 ALGO_LANE_OPS_PER_CELL = 4      # select + add + max + fused add-max in 32-bit
 DIR_BYTES_PER_CELL = 0.25       # 2 direction bits per cell
 # dram__bytes_read.sum + dram__bytes_write.sum of the fill kernel + traceback kernel per DP cell, from the
-# `ncu --set full` capture of 100k config-2 pairs in profiles/ (r1e_k1_c9_lg16_fill_tb_100k.csv, first wave = 25,000 pairs = 3.2e9 cells: 867 MB
-# written + 28 MB read by the fill kernel, 223 MB read + 7 MB written by the traceback kernel)
-NCU_DRAM_BYTES_PER_CELL = 0.35
+# `ncu --set full` capture of 100k config-2 pairs (12.9e9 cells) in profiles/r1f_k1_c18_lg8_fill_tb_100k.csv:
+# 3.63 GB written + 0.14 GB read by the fill kernel, 0.86 GB read by the traceback kernel
+NCU_DRAM_BYTES_PER_CELL = 0.36
 
 
 def env_int(name, default):
