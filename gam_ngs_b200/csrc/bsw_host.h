@@ -92,8 +92,8 @@ inline void geometry_for_band(uint64_t band, bool dirs, int* c_out, int* lg_out)
   const uint64_t y = 2 * band + 1;
   int best_c = 0, best_lg = 0;
   double best = -1.0;
-  const int lgs[3] = {8, 16, 32};
-  for (int n = 0; n < 3; n++) {
+  const int lgs[4] = {4, 8, 16, 32};
+  for (int n = 0; n < 4; n++) {
     const int lg = lgs[n];
     int c = (int)((y + lg - 1) / lg);
     if (c < 2) c = 2;

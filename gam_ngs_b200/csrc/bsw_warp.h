@@ -1,5 +1,5 @@
 // K1 - warp-level banded overlap DP with inter-task parallelism: every group of LG lanes
-// (LG = 32, 16 or 8; 1, 2 or 4 pairs per warp) owns one pair.
+// (LG = 32, 16, 8 or 4; 1, 2, 4 or 8 pairs per warp) owns one pair.
 // K2 - the same skewed anti-diagonal wavefront with LG = 64, 128 or 256 lanes: one pair per CTA
 // (wide bands, or few long pairs); only the exchange policy W differs.
 //
@@ -73,7 +73,7 @@ GAMX_HD constexpr int asel_phys(int w) { return w; }
 
 template <int C, int LG>
 struct alignas(16) GroupSmem {
-  uint64_t btab[kTileSteps + LG];            // b-rows of the tile as 8-byte Cd tables
+  uint64_t btab[(kTileSteps + LG + 7) / 8 * 8];  // b-rows of the tile as 8-byte Cd tables (staged in runs of 8)
   uint16_t asel[kTileSteps + LG * C + 16];   // a-bases as 4-nibble windows: codes of positions p..p+3
   int cap[C * LG];                           // latched "last column" cells, [slot][lane]
 };
@@ -108,7 +108,7 @@ GAMX_HD void warp_align(W& w, const DevJob* Jp, const SeqStore& store, WarpSmem<
   static_assert(stripe_supported(C), "lane stripe width");
   // LG <= 32: groups inside one warp (K1).  LG = 64..256: one pair per CTA (K2); the policy W then
   // implements the neighbour exchanges through shared memory and a block barrier.
-  static_assert(LG == 8 || LG == 16 || LG == 32 || LG == 64 || LG == 128 || LG == 256, "lanes per pair");
+  static_assert(LG == 4 || LG == 8 || LG == 16 || LG == 32 || LG == 64 || LG == 128 || LG == 256, "lanes per pair");
   constexpr int SH = DIRS ? 2 : 0;
   constexpr int UF = unroll_of(C);
   constexpr int NQ = (C + 3) / 4;  // 4-slot selector groups

@@ -44,7 +44,9 @@ using namespace gamx;
 // =============================================================================================
 namespace {
 
-constexpr int kWarpsPerBlock = 4;
+// warps per K1 block: 4, or 2 for 4-lane groups (8 pairs per warp: the per-pair shared-memory tiles of a
+// block must stay below the 48 KB of static shared memory)
+__host__ __device__ constexpr int warps_per_block(int lg) { return lg == 4 ? 2 : 4; }
 
 struct DevWarp {
   __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31); }
@@ -61,12 +63,12 @@ struct DevWarp {
 #define GAMX_K1_MIN_BLOCKS(C) ((C) <= 6 ? 8 : ((C) <= 10 ? 5 : 4))
 #endif
 template <int C, int LG, bool DIRS>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, GAMX_K1_MIN_BLOCKS(C))
+__global__ void __launch_bounds__(warps_per_block(LG) * 32, GAMX_K1_MIN_BLOCKS(C) * 4 / warps_per_block(LG))
 k1_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counter, SeqStore store,
           uint32_t* __restrict__ dirs, uint64_t group_stride, uint32_t* __restrict__ ops,
           DevResult* __restrict__ results) {
   constexpr int G = 32 / LG;  // pairs per warp
-  __shared__ WarpSmem<C, LG> sm[kWarpsPerBlock];
+  __shared__ WarpSmem<C, LG> sm[warps_per_block(LG)];
   DevWarp w;
   const int warp = (int)(threadIdx.x >> 5);
   const int grp = w.lane() / LG;
@@ -835,7 +837,7 @@ template <int C, int LG, bool DIRS>
 int launch_k1_t(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, int n_jobs, const DevJob* jobs, int* counter, uint32_t* dirs,
                 uint64_t stride, uint32_t* ops, DevResult* results) {
   SeqStore st{(const uint32_t*)d.packed.p, (const uint32_t*)d.nmask.p};
-  k1_kernel<C, LG, DIRS><<<g.grid, kWarpsPerBlock * 32, 0, stream>>>(jobs, n_jobs, counter, st, dirs,
+  k1_kernel<C, LG, DIRS><<<g.grid, warps_per_block(LG) * 32, 0, stream>>>(jobs, n_jobs, counter, st, dirs,
                                                                       stride, ops, results);
   CU(cudaGetLastError());
   return GAMX_OK;
@@ -843,7 +845,7 @@ int launch_k1_t(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, i
 
 template <int C, int LG, bool DIRS>
 int occupancy_k1_t(int* blocks_per_sm) {
-  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k1_kernel<C, LG, DIRS>, kWarpsPerBlock * 32, 0);
+  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k1_kernel<C, LG, DIRS>, warps_per_block(LG) * 32, 0);
 }
 
 #define GAMX_FOR_EACH_C(M, LG) M(2, LG) M(3, LG) M(4, LG) M(5, LG) M(6, LG) M(7, LG) M(8, LG) M(9, LG) M(10, LG) \
@@ -863,7 +865,8 @@ int k1_blocks_per_sm_lg(int c, bool dirs) {
   return b;
 }
 int k1_blocks_per_sm(int c, int lg, bool dirs) {
-  return lg == 32 ? k1_blocks_per_sm_lg<32>(c, dirs) : lg == 16 ? k1_blocks_per_sm_lg<16>(c, dirs) : k1_blocks_per_sm_lg<8>(c, dirs);
+  return lg == 32 ? k1_blocks_per_sm_lg<32>(c, dirs) : lg == 16 ? k1_blocks_per_sm_lg<16>(c, dirs)
+                  : lg == 8 ? k1_blocks_per_sm_lg<8>(c, dirs) : k1_blocks_per_sm_lg<4>(c, dirs);
 }
 
 template <int LG>
@@ -881,7 +884,8 @@ int launch_k1(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, int
               uint64_t stride, uint32_t* ops, DevResult* results) {
   if (g.lg == 32) return launch_k1_lg<32>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results);
   if (g.lg == 16) return launch_k1_lg<16>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results);
-  return launch_k1_lg<8>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results);
+  if (g.lg == 8) return launch_k1_lg<8>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results);
+  return launch_k1_lg<4>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results);
 }
 
 // stable LSD radix sort of job indices by descending cost
@@ -1402,8 +1406,8 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
 // resident blocks per SM of a kernel family (the occupancy query is cached: it is asked per chunk)
 static int blocks_per_sm_cached(int c, int lg, bool dirs) {
   static std::mutex mu;
-  static int cache[kMaxC + 1][5][2];  // [c][lg index][dirs], 0 = not asked yet, -1 = does not fit
-  const int li = lg == 8 ? 0 : lg == 16 ? 1 : lg == 32 ? 2 : lg == 64 ? 3 : 4;
+  static int cache[kMaxC + 1][6][2];  // [c][lg index][dirs], 0 = not asked yet, -1 = does not fit
+  const int li = lg == 8 ? 0 : lg == 16 ? 1 : lg == 32 ? 2 : lg == 64 ? 3 : lg == 4 ? 5 : 4;
   if (c < 0 || c > kMaxC || (lg > 64 && lg != 128 && lg != 256)) return 0;
   std::lock_guard<std::mutex> lk(mu);
   int& v = (lg == 256 ? cache[c][4][dirs] : lg == 128 ? cache[c][4][dirs] : cache[c][li][dirs]);
@@ -1465,7 +1469,7 @@ static int plan_upload(gamx_plan* pl) {
       const int bps = blocks_per_sm_cached(g.c, g.lg, g.dirs);
       if (bps <= 0) { ctx->err = "alignment kernel does not fit on the device"; return GAMX_ERR_CUDA; }
       uint64_t grid = (uint64_t)d.sm_count * bps;
-      const uint64_t pairs_per_block = cta ? 1 : (uint64_t)kWarpsPerBlock * (32 / g.lg);
+      const uint64_t pairs_per_block = cta ? 1 : (uint64_t)warps_per_block(g.lg) * (32 / g.lg);
       const uint64_t need = (g.job_idx.size() + pairs_per_block - 1) / pairs_per_block;
       if (need < grid) grid = need;
       // A pipelined chunk leaves a tenth of the block slots free: the pack launches of the upload and
@@ -1505,7 +1509,7 @@ static int plan_upload(gamx_plan* pl) {
         // traceback launch run beside a fill launch (needs the second scratch half; every wave still
         // holds several times the resident jobs)
         if (dp.two_halves_ok) {
-          const uint64_t pairs_per_block = g.lg > 32 ? 1 : (uint64_t)kWarpsPerBlock * (32 / g.lg);
+          const uint64_t pairs_per_block = g.lg > 32 ? 1 : (uint64_t)warps_per_block(g.lg) * (32 / g.lg);
           const uint64_t resident = (uint64_t)g.grid * pairs_per_block;
           const uint64_t quarter = (g.job_idx.size() + 3) / 4;
           if (quarter >= 4 * resident) g.wave_jobs = std::min(g.wave_jobs, quarter);
@@ -1610,7 +1614,7 @@ static int plan_run_locked(gamx_plan* pl) {
         if (walk && half_used[h]) CU(cudaStreamWaitEvent(fs, sl.ev_tb[h], 0));  // half h is free again
         Group gw;  // launch view of the wave (no job list needed)
         gw.c = g.c; gw.lg = g.lg; gw.dirs = g.dirs;
-        const uint64_t pairs_per_block = g.lg > 32 ? 1 : (uint64_t)kWarpsPerBlock * (32 / g.lg);
+        const uint64_t pairs_per_block = g.lg > 32 ? 1 : (uint64_t)warps_per_block(g.lg) * (32 / g.lg);
         gw.grid = (int)std::min<uint64_t>((uint64_t)g.grid, (nw + pairs_per_block - 1) / pairs_per_block);
         const int rc = g.lg > 32 ? launch_k2(ctx, d, fs, gw, (int)nw, dj + w0, (int*)sl.counters.p + launch, half,
                                              g.max_dir_words, (uint32_t*)sl.ops.p, res + w0)

@@ -100,8 +100,8 @@ int SimWarp::exchange(int v, int src) {
 }
 
 struct WarpArgs {
-  const DevJob* job[4];   // per group (null: idle)
-  DevResult* out[4];
+  const DevJob* job[8];   // per group (null: idle)
+  DevResult* out[8];
   SeqStore store;
   void* smem;
   uint32_t* dirs;
@@ -143,6 +143,7 @@ void run_warp(WarpArgs& a, bool desc) {
   if (a.lg == 32) run_warp_lg<32>(a, desc);
   else if (a.lg == 16) run_warp_lg<16>(a, desc);
   else if (a.lg == 8) run_warp_lg<8>(a, desc);
+  else if (a.lg == 4) run_warp_lg<4>(a, desc);
   else if (a.lg == 64) run_warp_lg<64>(a, desc);
   else if (a.lg == 128) run_warp_lg<128>(a, desc);
   else run_warp_lg<256>(a, desc);
