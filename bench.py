@@ -193,8 +193,11 @@ def run_reference(args, spec, rank, world):
         cpu_baseline(spec, a, al, b, bl, seconds_target=1.0)
     t0 = time.perf_counter()
     last = None
+    # each step is a bounded sample of the workload; the sample shrinks with the step count so that
+    # the whole run stays within about two minutes
+    per_step = min(8.0, max(1.0, 100.0 / max(1, args.steps)))
     for _ in range(args.steps):
-        last = cpu_baseline(spec, a, al, b, bl, seconds_target=8.0)
+        last = cpu_baseline(spec, a, al, b, bl, seconds_target=per_step)
         vals.append(last["value"])
     wall = time.perf_counter() - t0
     v = float(np.mean(vals))
