@@ -1,17 +1,22 @@
 // libgamx.so - sm_100a kernels and the C-ABI host layer (include/gamx.h).
 //
 // Kernels
-//   k1_kernel<C, DIRS>   warp-per-pair banded DP (body: bsw_warp.h), persistent warps pulling
-//                        jobs from a device counter; DIRS adds the 2-bit direction store and
-//                        the on-device traceback / edit-string emission.
+//   k1_kernel<C, LG, DIRS>  warp-level banded DP (body: bsw_warp.h), LG = 4/8/16/32 lanes per pair, persistent
+//                        warps pulling jobs from a device counter; DIRS adds the 2-bit direction store.
+//   k2_kernel<C, LG, DIRS>  the same body, one pair per CTA of 64/128/256 threads (wide bands, few long pairs).
+//   tb_kernel / tbw_kernel  traceback of a fill wave: one job per thread / per warp (long jobs); coordinates,
+//                        op counts, first/last match and - FULL mode - the edit string.
 //   generic_kernel       one thread per job, literal restatement of the reference for the
-//                        jobs outside K1's parameter range (body: bsw_generic.h).
+//                        jobs outside K1/K2's parameter range (body: bsw_generic.h).
+//   pack_kernel          K0: raw base codes -> 2 bits per base + N mask.
+//   hits_*_kernel        ABlast::findHits (k-mer diagonal voting).
 //   intpeak_kernel<W>    register-only issue-rate microbenchmarks for the roofline denominator.
 //
-// Host layer: contig store (2-bit + N mask, pinned staging, async upload), batch planning
-// (guards of banded_smith_waterman.cc:90-97, classification, cost-balanced sharding over the
-// context's devices), launch, gather.  No CPU compute path exists here: if CUDA is not usable
-// every entry point fails.
+// Host layer: contig store (piece-wise pinned async upload on its own stream, packed on the device),
+// batch planning (guards of banded_smith_waterman.cc:90-97, classification, cost-balanced sharding
+// over the context's devices), waves over a two-half direction scratch, the pipelined
+// gamx_align_batch (producer thread, four buffer slots), gather.  No CPU compute path exists here:
+// if CUDA is not usable every entry point fails.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <stdint.h>
