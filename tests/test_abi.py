@@ -82,3 +82,21 @@ def test_cpp_dropin_compiles_links_and_fails_loudly_without_gpu(tmp_path):
     exe = _build_dropin(tmp_path)
     rc = subprocess.run([exe], capture_output=True).returncode
     assert rc == (0 if torch.cuda.is_available() else 77)
+
+
+def test_band_geometry_is_pure_host_code():
+    """gamx_band_geometry needs no device: the kernel family a band width maps to (stripe width C,
+    lanes per pair LG).  Even stripe widths instead of 13/17, fewest lanes per pair on ties."""
+    from gam_ngs_b200 import capi
+    assert capi.band_geometry(16) == (9, 4)      # 8 pairs per warp
+    assert capi.band_geometry(32) == (18, 4)
+    assert capi.band_geometry(64) == (18, 8)     # BASELINE config 2: 4 pairs per warp
+    assert capi.band_geometry(150) == (10, 32)   # the reference's default band
+    assert capi.band_geometry(256) == (18, 32)   # BASELINE config 3
+    assert capi.band_geometry(512) == (18, 64)   # CTA-per-pair kernel
+    assert capi.band_geometry(1024) == (18, 128)
+    assert capi.band_geometry(2303) == (18, 256)
+    assert capi.band_geometry(2304) is None      # generic kernel
+    for band in range(0, 2304, 7):
+        c, lg = capi.band_geometry(band)
+        assert 2 <= c <= 18 and lg in (4, 8, 16, 32, 64, 128, 256) and c * lg >= 2 * band + 1 and c not in (13, 17)
