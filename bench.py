@@ -365,7 +365,9 @@ def main():
     cells_rank = float(cells)
     ach_int = cells_rank / (dev_ms * 1e-3 / args.steps) * ALGO_LANE_OPS_PER_CELL / 1e12
     roofline = {"bound": "int_alu", "achieved": ach_int, "peak": int_peak / 1e12, "unit": "Tlaneop/s",
-                "frac": ach_int / (int_peak / 1e12) if int_peak else None, "traffic": None,
+                "frac": ach_int / (int_peak / 1e12) if int_peak else None,
+                "traffic": NCU_DRAM_BYTES_PER_CELL * cells_rank if spec["mode"] else None,
+                "traffic_note": "DRAM bytes per step = ncu dram bytes per cell (profiles/, 100k-pair --set full capture) x cells",
                 "kernel": kernel_name,
                 "algorithmic": f"{ALGO_LANE_OPS_PER_CELL} int32 lane-ops per cell (SURVEY 8d) x {int(cells_rank)} cells per launch",
                 "peak_source": "VIADDMNMX issue rate measured live by gamx_measure_int_peak (register-only kernel)"}
