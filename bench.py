@@ -355,7 +355,7 @@ def main():
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": e2e_s / args.steps * 1e3,
                "includes": "raw sequence H2D from pinned memory + device 2-bit pack, job descriptor H2D, kernels, result D2H",
-               "pipeline": "chunks of 65536 jobs over 4 buffer slots/streams; upload pieces of 64 MB on their own stream"}
+               "pipeline": "chunks of 65536 jobs over 4 buffer slots/streams; upload pieces of 128 MB on their own stream"}
     # ---- roofline --------------------------------------------------------------------------------
     geo = capi.band_geometry(spec["band"]) or (0, 0)
     kernel_name = f"{'k1' if geo[1] <= 32 else 'k2'}_kernel<{geo[0]},{geo[1]},{'true' if spec['mode'] else 'false'}>" + \

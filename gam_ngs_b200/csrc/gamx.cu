@@ -522,7 +522,7 @@ struct gamx_ctx {
   Upload up;
   PinBuf h_meta;                  // roff[n+1], sgroup[n+1] of the upload in flight (pinned, shared by the devices)
   uint64_t pipeline_chunk = 65536;  // gamx_set_pipeline_chunk
-  uint64_t piece_bytes = 64u << 20;  // raw bytes per upload piece (GAMX_UPLOAD_PIECE_BYTES)
+  uint64_t piece_bytes = 128u << 20;  // raw bytes per upload piece; 128 MB measured 2-3 ms per 2.1 GB faster than 64 MB (GAMX_UPLOAD_PIECE_BYTES)
   std::mutex mu;
   std::string err;
 };
