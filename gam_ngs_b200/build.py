@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgamx.so")
 SOURCES = [os.path.join(CSRC, "gamx.cu")]
 HEADERS = [os.path.join(CSRC, f) for f in
-           ("bsw_common.h", "bsw_warp.h", "bsw_generic.h", "bsw_traceback.h", "bsw_host.h", "merge_collector.h")] + \
+           ("bsw_common.h", "bsw_warp.h", "bsw_warp16.h", "bsw_generic.h", "bsw_traceback.h", "bsw_host.h", "merge_collector.h")] + \
           [os.path.join(os.path.dirname(HERE), "include", "gamx.h")]
 
 NVCC_FLAGS = ["-split-compile", "0", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

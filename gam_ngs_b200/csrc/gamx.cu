@@ -40,6 +40,7 @@
 #include "bsw_host.h"
 #include "bsw_traceback.h"
 #include "bsw_warp.h"
+#include "bsw_warp16.h"
 #include "merge_collector.h"
 
 using namespace gamx;
@@ -87,6 +88,47 @@ k1_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counter
     // direction words of job `mine` of this launch: dirs + mine * group_stride (read back by tb_kernel)
     uint32_t* my_dirs = DIRS ? dirs + (uint64_t)j * group_stride : nullptr;
     warp_align<C, LG, DIRS, false>(w, Jp, store, sm[warp], my_dirs, group_stride, ops, results + (mine < n_jobs ? mine : 0));
+  }
+}
+
+// K1s: the 16x2 form (bsw_warp16.h).  A lane group takes TWO consecutive jobs of the launch and runs them as
+// the two half-words of one register set.  The pair form needs what the half-word arithmetic and its 4-entry
+// substitution tables cannot express to be absent: both jobs must take the same band and gap, and no window
+// may hold an N (checked here on the store's N masks, every lane a share of the words).  When any pair of
+// the warp fails the test the whole warp runs its jobs through the 32-bit body instead, one job per group
+// and round (the groups of a warp share their step loop) - same results, same direction regions: job m of
+// the launch owns words [m * stride, (m+1) * stride), a pair the two regions of its jobs together.
+template <int C, int LG, bool DIRS>
+__global__ void __launch_bounds__(warps_per_block(LG) * 32, GAMX_K1_MIN_BLOCKS(C) * 4 / warps_per_block(LG))
+k1s_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counter, SeqStore store,
+           uint32_t* __restrict__ dirs, uint64_t stride, uint32_t* __restrict__ ops,
+           DevResult* __restrict__ results) {
+  constexpr int G = 32 / LG;  // pairs per warp
+  union Smem { WarpSmem<C, LG> s32; WarpSmem16<C, LG> s16; };
+  __shared__ Smem sm[warps_per_block(LG)];
+  DevWarp w;
+  const int warp = (int)(threadIdx.x >> 5);
+  const int grp = w.lane() / LG, gl = w.lane() % LG;
+  for (;;) {
+    int j = 0;
+    if (w.lane() == 0) j = atomicAdd(counter, 2 * G);
+    j = __shfl_sync(0xffffffffu, j, 0);
+    if (j >= n_jobs) break;
+    const int ma = j + 2 * grp, mb = ma + 1;  // jobs are sorted by cost: the jobs of a warp get similar work
+    const DevJob* JA = ma < n_jobs ? jobs + ma : nullptr;
+    const DevJob* JB = mb < n_jobs ? jobs + mb : nullptr;
+    bool ok = !(JA && JB) || (JA->band == JB->band && JA->gap == JB->gap);
+    ok = ok && (job_n_bits(store, JA, gl, LG) | job_n_bits(store, JB, gl, LG)) == 0u;
+    if (__all_sync(0xffffffffu, ok)) {
+      warp_align16<C, LG, DIRS>(w, JA, JB, store, sm[warp].s16, DIRS ? dirs + (uint64_t)ma * stride : nullptr,
+                                results + (JA ? ma : 0), results + (JB ? mb : 0));
+    } else {
+      // (warp_align adds grp * stride to the pointer it is given)
+      warp_align<C, LG, DIRS, false>(w, JA, store, sm[warp].s32, DIRS ? dirs + (uint64_t)(ma - grp) * stride : nullptr, stride, ops,
+                                     results + (JA ? ma : 0));
+      warp_align<C, LG, DIRS, false>(w, JB, store, sm[warp].s32, DIRS ? dirs + (uint64_t)(mb - grp) * stride : nullptr, stride, ops,
+                                     results + (JB ? mb : 0));
+    }
   }
 }
 
@@ -154,8 +196,14 @@ tb_kernel(const DevJob* __restrict__ jobs, int n_jobs, const uint32_t* __restric
   if (Jp->x >= kTbWarpRows) return;  // tbw_kernel's
   DevResult R = results[j];
   if (R.status != kStatusOk || (Jp->mode & 0x100)) return;  // empty / out of range: nothing to walk
-  k1_traceback(dirs + (uint64_t)j * stride, c, lg, R.end_i, R.end_j, Jp->p0, (Jp->mode & 0xff) == kModeFull,
-               ops + Jp->ops_word, Jp->ops_cap, R);
+  const int lay = R.has_match;  // left by the fill kernel: 0 = 32-bit layout, 1 + h = half h of a 16x2 pair region
+  if (lay == 0) {
+    k1_traceback(dirs + (uint64_t)j * stride, c, lg, R.end_i, R.end_j, Jp->p0, (Jp->mode & 0xff) == kModeFull,
+                 ops + Jp->ops_word, Jp->ops_cap, R);
+  } else {
+    PairFetch f{dirs + (uint64_t)(j & ~1) * stride, c, lg, lay - 1};
+    k1_traceback_t(f, c, R.end_i, R.end_j, Jp->p0, (Jp->mode & 0xff) == kModeFull, ops + Jp->ops_word, Jp->ops_cap, R);
+  }
   R.ops_start = Jp->ops_word * 16 + Jp->ops_cap - R.n_ops;
   results[j] = R;
 }
@@ -179,6 +227,27 @@ struct WarpFetch {
   }
 };
 
+// the same for half `half` of a 16x2 pair region (two 8-step blocks per 16-step word)
+struct WarpFetch16 {
+  const uint32_t* dirs;
+  int C, LG, half;
+  int cb, ck, cl;
+  uint32_t mine;
+  __device__ __forceinline__ uint32_t operator()(int blk, int k, int l) {
+    if (k != ck || l != cl || blk > cb || blk < cb - 31) {
+      cb = blk; ck = k; cl = l;
+      const int b = blk - (int)(threadIdx.x & 31);
+      mine = 0u;
+      if (b >= 0) {
+        const uint32_t w0 = dirs[((uint32_t)(2 * b) * (uint32_t)C + (uint32_t)k) * (uint32_t)LG + (uint32_t)l];
+        const uint32_t w1 = dirs[((uint32_t)(2 * b + 1) * (uint32_t)C + (uint32_t)k) * (uint32_t)LG + (uint32_t)l];
+        mine = half ? ((w0 & 0xffff0000u) | (w1 >> 16)) : ((w0 << 16) | (w1 & 0xffffu));
+      }
+    }
+    return __shfl_sync(0xffffffffu, mine, cb - blk);
+  }
+};
+
 constexpr int kTbwThreads = 128;
 __global__ void __launch_bounds__(kTbwThreads, 8)
 tbw_kernel(const DevJob* __restrict__ jobs, int n_jobs, const uint32_t* __restrict__ dirs, uint64_t stride, int c, int lg,
@@ -190,8 +259,14 @@ tbw_kernel(const DevJob* __restrict__ jobs, int n_jobs, const uint32_t* __restri
   DevResult R = results[j];
   if (R.status != kStatusOk || (Jp->mode & 0x100)) return;
   const bool leader = (threadIdx.x & 31) == 0;
-  WarpFetch f{dirs + (uint64_t)j * stride, c, lg, -1, -1, -1, 0u};
-  k1_traceback_t(f, c, R.end_i, R.end_j, Jp->p0, leader && (Jp->mode & 0xff) == kModeFull, ops + Jp->ops_word, Jp->ops_cap, R);
+  const int lay = R.has_match;  // 0 = 32-bit layout, 1 + h = half h of a 16x2 pair region
+  if (lay == 0) {
+    WarpFetch f{dirs + (uint64_t)j * stride, c, lg, -1, -1, -1, 0u};
+    k1_traceback_t(f, c, R.end_i, R.end_j, Jp->p0, leader && (Jp->mode & 0xff) == kModeFull, ops + Jp->ops_word, Jp->ops_cap, R);
+  } else {
+    WarpFetch16 f{dirs + (uint64_t)(j & ~1) * stride, c, lg, lay - 1, -1, -1, -1, 0u};
+    k1_traceback_t(f, c, R.end_i, R.end_j, Jp->p0, leader && (Jp->mode & 0xff) == kModeFull, ops + Jp->ops_word, Jp->ops_cap, R);
+  }
   if (leader) {
     R.ops_start = Jp->ops_word * 16 + Jp->ops_cap - R.n_ops;
     results[j] = R;
@@ -792,6 +867,7 @@ struct Group {
   int c = 0;          // stripe width (0: generic)
   int lg = 32;        // lanes per pair
   bool dirs = false;  // K1 with direction store
+  int band = -1, gap = 0;  // K1 groups are uniform in band and gap, so that any two neighbours can share registers (k1s_kernel)
   std::vector<uint32_t> job_idx;  // indices into the batch
   uint64_t max_dir_words = 0;
   uint32_t res_off = 0;  // offset of this group's results in the device result array
@@ -838,18 +914,31 @@ struct gamx_plan {
 
 namespace {
 
+// Warp-level launches use the 16x2 kernel (two jobs per lane group, k1s_kernel) unless GAMX_NO_S16 is set
+// (experiments: the 32-bit kernel of round 1 for comparison).
+bool use_s16() {
+  static const bool on = getenv("GAMX_NO_S16") == nullptr;
+  return on;
+}
+// jobs a K1 block takes per visit of the job counter
+uint64_t k1_jobs_per_block(int lg) { return (uint64_t)warps_per_block(lg) * (32 / lg) * (use_s16() ? 2 : 1); }
+
 template <int C, int LG, bool DIRS>
 int launch_k1_t(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, int n_jobs, const DevJob* jobs, int* counter, uint32_t* dirs,
                 uint64_t stride, uint32_t* ops, DevResult* results) {
   SeqStore st{(const uint32_t*)d.packed.p, (const uint32_t*)d.nmask.p};
-  k1_kernel<C, LG, DIRS><<<g.grid, warps_per_block(LG) * 32, 0, stream>>>(jobs, n_jobs, counter, st, dirs,
-                                                                      stride, ops, results);
+  if (use_s16())
+    k1s_kernel<C, LG, DIRS><<<g.grid, warps_per_block(LG) * 32, 0, stream>>>(jobs, n_jobs, counter, st, dirs, stride, ops, results);
+  else
+    k1_kernel<C, LG, DIRS><<<g.grid, warps_per_block(LG) * 32, 0, stream>>>(jobs, n_jobs, counter, st, dirs, stride, ops, results);
   CU(cudaGetLastError());
   return GAMX_OK;
 }
 
 template <int C, int LG, bool DIRS>
 int occupancy_k1_t(int* blocks_per_sm) {
+  if (use_s16())
+    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k1s_kernel<C, LG, DIRS>, warps_per_block(LG) * 32, 0);
   return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k1_kernel<C, LG, DIRS>, warps_per_block(LG) * 32, 0);
 }
 
@@ -1215,6 +1304,7 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
     uint64_t cells = 0, cmin = ~0ull, cmax = 0, max_dir_words = 0, n_special = 0, xmin = ~0ull, xmax = 0;
     size_t max_contig = 0;
     int c = -1, lg = 0, dirs = 0;  // kernel family of the slice's first job
+    int band = 0, gap = 0;
     bool mixed = false;
   };
   Summary sums[kMaxHostThreads];
@@ -1241,8 +1331,8 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
       S.max_dir_words = std::max(S.max_dir_words, P.dir_words);
       S.xmin = std::min(S.xmin, P.x_size); S.xmax = std::max(S.xmax, P.x_size);
       const int dirs = j.mode != GAMX_MODE_SCORE;
-      if (S.c < 0) { S.c = P.c; S.lg = P.lg; S.dirs = dirs; }
-      else if (S.c != P.c || S.lg != P.lg || S.dirs != dirs) S.mixed = true;
+      if (S.c < 0) { S.c = P.c; S.lg = P.lg; S.dirs = dirs; S.band = P.dj.band; S.gap = P.dj.gap; }
+      else if (S.c != P.c || S.lg != P.lg || S.dirs != dirs || S.band != P.dj.band || S.gap != P.dj.gap) S.mixed = true;
     }
     sums[t] = S;
   });
@@ -1261,8 +1351,8 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
       A.xmin = std::min(A.xmin, S.xmin); A.xmax = std::max(A.xmax, S.xmax);
       A.max_contig = std::max(A.max_contig, S.max_contig);
       if (S.c >= 0) {
-        if (A.c < 0) { A.c = S.c; A.lg = S.lg; A.dirs = S.dirs; }
-        else if (A.c != S.c || A.lg != S.lg || A.dirs != S.dirs) A.mixed = true;
+        if (A.c < 0) { A.c = S.c; A.lg = S.lg; A.dirs = S.dirs; A.band = S.band; A.gap = S.gap; }
+        else if (A.c != S.c || A.lg != S.lg || A.dirs != S.dirs || A.band != S.band || A.gap != S.gap) A.mixed = true;
       }
       A.mixed = A.mixed || S.mixed;
     }
@@ -1272,7 +1362,7 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
     if (nd == 1 && n > 0 && A.n_special == 0 && !A.mixed && A.c >= 0 && A.cmax <= A.cmin + A.cmin / 4 && !latency_candidate) {
       // fast path: the whole batch is one launch in the caller's order
       DevPlan& dp = pl->dps[0];
-      Group g; g.c = A.c; g.lg = A.lg; g.dirs = A.dirs != 0;
+      Group g; g.c = A.c; g.lg = A.lg; g.dirs = A.dirs != 0; g.band = A.band; g.gap = A.gap;
       g.job_idx.resize(n);
       g.max_dir_words = A.max_dir_words;
       g.min_x = A.xmin; g.max_x = A.xmax;
@@ -1335,22 +1425,22 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
     DevPlan& dp = pl->dps[d];
     dp.n_jobs = (uint32_t)per_dev[d].size();
     std::vector<Group> groups;
-    auto find_group = [&](int c, int lg, bool dirs) -> int {
+    auto find_group = [&](int c, int lg, bool dirs, int band, int gap) -> int {
       for (size_t g = 0; g < groups.size(); g++)
-        if (groups[g].c == c && groups[g].lg == lg && groups[g].dirs == dirs) return (int)g;
-      Group g; g.c = c; g.lg = lg; g.dirs = dirs;
+        if (groups[g].c == c && groups[g].lg == lg && groups[g].dirs == dirs && groups[g].band == band && groups[g].gap == gap) return (int)g;
+      Group g; g.c = c; g.lg = lg; g.dirs = dirs; g.band = band; g.gap = gap;
       groups.push_back(g);
       return (int)groups.size() - 1;
     };
     for (uint32_t i : per_dev[d]) {
       const Prepared& P = preps[i];
       if (P.cls == kClassWarp || P.cls == kClassCta) {
-        Group& g = groups[find_group(P.c, P.lg, pl->modes[i] != GAMX_MODE_SCORE)];
+        Group& g = groups[find_group(P.c, P.lg, pl->modes[i] != GAMX_MODE_SCORE, P.dj.band, P.dj.gap)];
         g.job_idx.push_back(i);
         g.max_dir_words = std::max(g.max_dir_words, P.dir_words);
         g.min_x = std::min(g.min_x, P.x_size); g.max_x = std::max(g.max_x, P.x_size);
       } else {
-        groups[find_group(0, 32, true)].job_idx.push_back(i);
+        groups[find_group(0, 32, true, -1, 0)].job_idx.push_back(i);
       }
     }
     // Latency mode: a launch of few long pairs cannot fill the device with one warp per pair, so
@@ -1474,7 +1564,7 @@ static int plan_upload(gamx_plan* pl) {
       const int bps = blocks_per_sm_cached(g.c, g.lg, g.dirs);
       if (bps <= 0) { ctx->err = "alignment kernel does not fit on the device"; return GAMX_ERR_CUDA; }
       uint64_t grid = (uint64_t)d.sm_count * bps;
-      const uint64_t pairs_per_block = cta ? 1 : (uint64_t)warps_per_block(g.lg) * (32 / g.lg);
+      const uint64_t pairs_per_block = cta ? 1 : k1_jobs_per_block(g.lg);
       const uint64_t need = (g.job_idx.size() + pairs_per_block - 1) / pairs_per_block;
       if (need < grid) grid = need;
       // A pipelined chunk leaves a tenth of the block slots free: the pack launches of the upload and
@@ -1486,8 +1576,9 @@ static int plan_upload(gamx_plan* pl) {
       if (grid_scale < 1.0 && grid == (uint64_t)d.sm_count * bps) grid = (uint64_t)(grid * grid_scale);
       g.grid = (int)std::max<uint64_t>(grid, 1);
       if (g.dirs && g.max_dir_words) {
-        want_words = std::max(want_words, g.max_dir_words * (uint64_t)g.job_idx.size());
-        min_words = std::max(min_words, g.max_dir_words);
+        // (a 16x2 pair writes the regions of both its jobs, also when the second job does not exist: even counts)
+        want_words = std::max<uint64_t>(want_words, g.max_dir_words * (((uint64_t)g.job_idx.size() + 1) & ~(uint64_t)1));
+        min_words = std::max<uint64_t>(min_words, 2 * g.max_dir_words);
       }
     }
     // what the slot owns already: one half if that holds every group, else two
@@ -1509,14 +1600,14 @@ static int plan_upload(gamx_plan* pl) {
     for (Group& g : dp.groups) {
       if (!g.c) continue;
       if (g.dirs && g.max_dir_words) {
-        g.wave_jobs = std::min<uint64_t>(half_words / g.max_dir_words, g.job_idx.size());
+        g.wave_jobs = std::min<uint64_t>((half_words / g.max_dir_words) & ~1ull, ((uint64_t)g.job_idx.size() + 1) & ~1ull);  // even: pairs stay together
         // a big group is cut into at least four waves even when one would fit, so that all but the last
         // traceback launch run beside a fill launch (needs the second scratch half; every wave still
         // holds several times the resident jobs)
         if (dp.two_halves_ok) {
-          const uint64_t pairs_per_block = g.lg > 32 ? 1 : (uint64_t)warps_per_block(g.lg) * (32 / g.lg);
+          const uint64_t pairs_per_block = g.lg > 32 ? 1 : k1_jobs_per_block(g.lg);
           const uint64_t resident = (uint64_t)g.grid * pairs_per_block;
-          const uint64_t quarter = (g.job_idx.size() + 3) / 4;
+          const uint64_t quarter = (((uint64_t)g.job_idx.size() + 3) / 4 + 1) & ~1ull;
           if (quarter >= 4 * resident) g.wave_jobs = std::min(g.wave_jobs, quarter);
         }
         dp.n_launches += (uint32_t)((g.job_idx.size() + g.wave_jobs - 1) / g.wave_jobs);
@@ -1619,7 +1710,7 @@ static int plan_run_locked(gamx_plan* pl) {
         if (walk && half_used[h]) CU(cudaStreamWaitEvent(fs, sl.ev_tb[h], 0));  // half h is free again
         Group gw;  // launch view of the wave (no job list needed)
         gw.c = g.c; gw.lg = g.lg; gw.dirs = g.dirs;
-        const uint64_t pairs_per_block = g.lg > 32 ? 1 : (uint64_t)warps_per_block(g.lg) * (32 / g.lg);
+        const uint64_t pairs_per_block = g.lg > 32 ? 1 : k1_jobs_per_block(g.lg);
         gw.grid = (int)std::min<uint64_t>((uint64_t)g.grid, (nw + pairs_per_block - 1) / pairs_per_block);
         const int rc = g.lg > 32 ? launch_k2(ctx, d, fs, gw, (int)nw, dj + w0, (int*)sl.counters.p + launch, half,
                                              g.max_dir_words, (uint32_t*)sl.ops.p, res + w0)

@@ -20,6 +20,7 @@
 #include "../../gam_ngs_b200/csrc/bsw_generic.h"
 #include "../../gam_ngs_b200/csrc/bsw_host.h"
 #include "../../gam_ngs_b200/csrc/bsw_warp.h"
+#include "../../gam_ngs_b200/csrc/bsw_warp16.h"
 
 using namespace gamx;
 
@@ -147,6 +148,62 @@ void run_warp(WarpArgs& a, bool desc) {
   else if (a.lg == 64) run_warp_lg<64>(a, desc);
   else if (a.lg == 128) run_warp_lg<128>(a, desc);
   else run_warp_lg<256>(a, desc);
+}
+
+
+// ---- 16x2 pairs (bsw_warp16.h) -------------------------------------------------------------------
+struct PairArgs {
+  const DevJob* ja[8];    // per group (null: idle half / group)
+  const DevJob* jb[8];
+  DevResult* oa[8];
+  DevResult* ob[8];
+  uint32_t* pdirs[8];
+  SeqStore store;
+  void* smem;
+  int c, lg;
+  bool dirs_on;
+  uint32_t nbits[8];      // OR over the group's lanes of job_n_bits (checked by the harness)
+};
+
+template <int C, int LG>
+void body_pair(SimWarp& w, void* p) {
+  PairArgs* a = (PairArgs*)p;
+  WarpSmem16<C, LG>& sm = *(WarpSmem16<C, LG>*)a->smem;
+  const int grp = w.lane() / LG, gl = w.lane() % LG;
+  // the N pre-scan the kernel does (every lane a share of the mask words, OR-reduced over the group)
+  uint32_t nb = job_n_bits(a->store, a->ja[grp], gl, LG) | job_n_bits(a->store, a->jb[grp], gl, LG);
+  for (int d = 1; d < LG; d <<= 1) nb |= (uint32_t)w.shfl_xor((int)nb, d, 32);
+  if (gl == 0) a->nbits[grp] = nb;
+  int any = nb != 0;
+  for (int d = 1; d < 32; d <<= 1) any |= w.shfl_xor(any, d, 32);
+  if (any) return;
+  if (a->dirs_on) warp_align16<C, LG, true>(w, a->ja[grp], a->jb[grp], a->store, sm, a->pdirs[grp], a->oa[grp], a->ob[grp]);
+  else warp_align16<C, LG, false>(w, a->ja[grp], a->jb[grp], a->store, sm, a->pdirs[grp], a->oa[grp], a->ob[grp]);
+}
+
+template <int C, int LG>
+void dispatch_pair(PairArgs& a, bool desc) {
+  std::vector<uint64_t> smem((sizeof(WarpSmem16<C, LG>) + 7) / 8);
+  a.smem = smem.data();
+  Sched* s = new Sched();
+  s->run(body_pair<C, LG>, &a, desc, 32);
+  delete s;
+}
+template <int LG>
+void run_pair_lg(PairArgs& a, bool desc) {
+  switch (a.c) {
+#define CASE(N) case N: dispatch_pair<N, LG>(a, desc); break;
+    CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
+    CASE(14) CASE(15) CASE(16) CASE(17) CASE(18)
+#undef CASE
+    default: break;
+  }
+}
+void run_pair(PairArgs& a, bool desc) {
+  if (a.lg == 32) run_pair_lg<32>(a, desc);
+  else if (a.lg == 16) run_pair_lg<16>(a, desc);
+  else if (a.lg == 8) run_pair_lg<8>(a, desc);
+  else run_pair_lg<4>(a, desc);
 }
 
 }  // namespace
@@ -277,5 +334,67 @@ int sim_align_multi(int n_jobs, const uint8_t* const* a, const uint64_t* la, con
   }
   return ran;
 }
+
+// Jobs 2g and 2g+1 run as the 16x2 PAIR of lane group g of ONE simulated warp (bsw_warp16.h), then the
+// traceback walks each job's half of the pair region (PairFetch), like k1s_kernel + tb_kernel do.  All
+// jobs take the same band and gap and full-contig views; an odd job count leaves the last high half idle.
+// first_group: lane group of pair 0 (groups before it idle).  Returns the number of jobs that ran, or
+// -1 when a job is not a warp-kernel job, -2 when a window holds an N (the kernel would fall back).
+int sim_align_pairs(int n_jobs, const uint8_t* const* a, const uint64_t* la, const uint8_t* const* b,
+                    const uint64_t* lb, const uint64_t* begin_a, const uint64_t* end_a, const uint64_t* begin_b,
+                    const uint64_t* end_b, uint64_t band, int64_t gap, const int* fs, const int* fe, int mode,
+                    int lane_order, int first_group, gamx_result* results, uint8_t* const* ops_out, uint64_t ops_out_cap) {
+  HostStore hs;
+  std::vector<Prepared> P(n_jobs);
+  std::vector<DevResult> dr(n_jobs);
+  int c = 0, lg = 0;
+  uint64_t xmax = 0, ops_words = 0;
+  for (int k = 0; k < n_jobs; k++) {
+    const int64_t ia = hs.add(a[k], la[k]), ib = hs.add(b[k], lb[k]);
+    prepare_job(P[k], nullptr, make_view(hs.start[ia], la[k], false, 0), la[k], make_view(hs.start[ib], lb[k], false, 0),
+                lb[k], begin_a[k], end_a[k], begin_b[k], end_b[k], band, gap, fs[k] != 0, fe[k] != 0, mode);
+    memset(&dr[k], 0, sizeof(DevResult));
+    if (P[k].cls != kClassWarp) return -1;
+    c = P[k].c; lg = P[k].lg;
+    xmax = std::max(xmax, P[k].x_size);
+    P[k].dj.ops_word = ops_words;
+    ops_words += P[k].ops_cap / 16 + 1;
+  }
+  const int G = 32 / lg;
+  if (first_group + (n_jobs + 1) / 2 > G) return -1;
+  const uint64_t stride = k1_dir_words16((int)xmax, c, lg);  // per pair
+  std::vector<uint32_t> ops(ops_words + 1, 0u);
+  std::vector<uint32_t> dirs(stride * G + 1, 0xdeadbeefu);
+  SeqStore st{hs.packed.data(), hs.nmask.data()};
+  PairArgs pa;
+  memset(&pa, 0, sizeof(pa));
+  for (int k = 0; k < n_jobs; k++) {
+    const int g = first_group + k / 2;
+    if (k & 1) { pa.jb[g] = &P[k].dj; pa.ob[g] = &dr[k]; }
+    else { pa.ja[g] = &P[k].dj; pa.oa[g] = &dr[k]; }
+    pa.pdirs[g] = dirs.data() + (uint64_t)g * stride;
+  }
+  pa.store = st; pa.c = c; pa.lg = lg; pa.dirs_on = mode != kModeScore;
+  run_pair(pa, (lane_order & 1) != 0);
+  for (int g = 0; g < G; g++) if (pa.nbits[g]) return -2;
+  for (int k = 0; k < n_jobs; k++) {
+    DevResult& R = dr[k];
+    if (mode != kModeScore && R.status == kStatusOk) {
+      if (R.has_match != 1 + (k & 1)) return -3;  // layout tag
+      PairFetch f{dirs.data() + (uint64_t)(first_group + k / 2) * stride, c, lg, k & 1};
+      k1_traceback_t(f, c, R.end_i, R.end_j, P[k].dj.p0, mode == kModeFull, ops.data() + P[k].dj.ops_word, P[k].dj.ops_cap, R);
+      R.ops_start = P[k].dj.ops_word * 16 + P[k].dj.ops_cap - R.n_ops;
+    }
+    finalize_result(P[k], &R, mode, &results[k]);
+    if (results[k].status == GAMX_JOB_OK && mode == kModeFull && ops_out && ops_out[k])
+      for (uint64_t q = 0; q < results[k].n_ops && q < ops_out_cap; q++) {
+        const uint64_t gpos = results[k].ops_offset + q;
+        ops_out[k][q] = (uint8_t)((ops[gpos >> 4] >> (2 * (gpos & 15))) & 3u);
+      }
+  }
+  return n_jobs;
+}
+
+void sim_band_geometry(uint64_t band, int* c, int* lg) { geometry_for_band(band, true, c, lg); }
 
 }  // extern "C"

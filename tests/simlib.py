@@ -65,7 +65,7 @@ def lib():
         out = os.path.join(HERE, "_build", "libwarpsim.so")
         src = os.path.join(HERE, "sim", "warp_sim.cc")
         deps = [src] + [os.path.join(ROOT, "gam_ngs_b200", "csrc", f) for f in
-                        ("bsw_common.h", "bsw_warp.h", "bsw_generic.h", "bsw_traceback.h", "bsw_host.h")]
+                        ("bsw_common.h", "bsw_warp.h", "bsw_warp16.h", "bsw_generic.h", "bsw_traceback.h", "bsw_host.h")]
         if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
             os.makedirs(os.path.dirname(out), exist_ok=True)
             subprocess.run(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", "-shared", "-fPIC",
@@ -126,3 +126,39 @@ def sim_align_multi(jobs, mode=2, lane_order=0):
     L.sim_align_multi(C.c_int(n), ap, la, bp, lb, ba, ea, bb, eb, u64(jobs[0]["band"]), C.c_int64(jobs[0]["gap"]),
                       fs, fe, C.c_int(mode), C.c_int(lane_order), res, op, u64(cap))
     return [(res[k], outs[k]) if res[k].status >= 0 else None for k in range(n)]
+
+
+def sim_align_pairs(jobs, mode=2, lane_order=0, first_group=0):
+    """Runs jobs (same band and gap, no N) as 16x2 PAIRS in ONE simulated warp: jobs 2g, 2g+1 on lane
+    group first_group+g (bsw_warp16.h + PairFetch traceback).  Returns (rc, [(result, ops)])."""
+    L = lib()
+    n = len(jobs)
+    u8p, u64 = C.POINTER(C.c_uint8), C.c_uint64
+    keep = []
+    ap, bp, op = (u8p * n)(), (u8p * n)(), (u8p * n)()
+    la, lb, ba, ea, bb, eb = [(u64 * n)() for _ in range(6)]
+    fs, fe = (C.c_int * n)(), (C.c_int * n)()
+    cap = 0
+    for k, j in enumerate(jobs):
+        a = np.ascontiguousarray(j["a"], dtype=np.uint8); b = np.ascontiguousarray(j["b"], dtype=np.uint8)
+        keep += [a, b]
+        ap[k], bp[k] = a.ctypes.data_as(u8p), b.ctypes.data_as(u8p)
+        la[k], lb[k], ba[k], ea[k], bb[k], eb[k] = len(a), len(b), j["begin_a"], j["end_a"], j["begin_b"], j["end_b"]
+        fs[k], fe[k] = int(j["force_start"]), int(j["force_end"])
+        cap = max(cap, len(a) + len(b) + 2 * j["band"] + 64)
+    outs = [np.zeros(cap, dtype=np.uint8) for _ in range(n)]
+    for k in range(n):
+        op[k] = outs[k].ctypes.data_as(u8p)
+    res = (GamxResult * n)()
+    L.sim_align_pairs.restype = C.c_int
+    rc = L.sim_align_pairs(C.c_int(n), ap, la, bp, lb, ba, ea, bb, eb, u64(jobs[0]["band"]), C.c_int64(jobs[0]["gap"]),
+                           fs, fe, C.c_int(mode), C.c_int(lane_order), C.c_int(first_group), res, op, u64(cap))
+    return rc, [(res[k], outs[k]) for k in range(n)]
+
+
+def band_geometry(band):
+    """(stripe width, lanes per pair) the host picks for a band (bsw_host.h: geometry_for_band)."""
+    L = lib()
+    c, lg = C.c_int(0), C.c_int(0)
+    L.sim_band_geometry(C.c_uint64(band), C.byref(c), C.byref(lg))
+    return c.value, lg.value

@@ -145,3 +145,97 @@ def test_sim_cta_per_pair_kernel(band, force):
             job = dict(a=a, b=b, band=band, gap=-8, **w)
             cls = _check(job, oracle_expect(job), modes=(2, 0), lane_order=shape, force_class=force)
             assert cls == 3
+
+
+# ---- 16x2 pairs (bsw_warp16.h): two jobs per lane group, half-word cells, per-lane rebasing --------------
+def _shape(rng, a, b, shape):
+    la, lb = len(a), len(b)
+    if shape == 0:
+        return dict(begin_a=0, end_a=la - 1, begin_b=0, end_b=lb - 1, force_start=False, force_end=False)
+    if shape == 1:
+        return dict(begin_a=int(rng.integers(0, la // 2)), end_a=la - 1, begin_b=0, end_b=lb - 1,
+                    force_start=False, force_end=True)
+    if shape == 2:
+        return dict(begin_a=3, end_a=la + 40, begin_b=int(rng.integers(0, lb // 2)), end_b=lb + 5,
+                    force_start=True, force_end=False)
+    return dict(begin_a=int(rng.integers(0, la)), end_a=int(rng.integers(0, la + 30)), begin_b=int(rng.integers(0, lb // 2)),
+                end_b=int(rng.integers(lb // 2, lb + 9)), force_start=bool(rng.integers(0, 2)), force_end=bool(rng.integers(0, 2)))
+
+
+def _check_pairs(jobs, modes=(2, 0), lane_order=0, first_group=0):
+    for mode in modes:
+        rc, out = simlib.sim_align_pairs(jobs, mode=mode, lane_order=lane_order, first_group=first_group)
+        assert rc == len(jobs), rc
+        for n, (job, (r, ops)) in enumerate(zip(jobs, out)):
+            got = simlib.result_to_expect(r, ops if mode == 2 else None, mode)
+            assert got == simlib.project(oracle_expect(job), mode), \
+                (mode, n, {k: v for k, v in job.items() if k not in "ab"})
+
+
+@pytest.mark.parametrize("band", [0, 7, 16, 33, 47, 64, 100, 150, 256, 287])
+def test_sim_pairs_every_stripe_width(band):
+    """Every geometry the host picks (C = 2..18, LG = 4..32): pairs of different length and shape in one
+    group (masked drain per half, per-half capture windows, frozen pos < 0 cells), odd job counts,
+    idle groups in front."""
+    rng = np.random.default_rng(7000 + band)
+    c, lg = simlib.band_geometry(band)
+    G = 32 // lg
+    for rep in range(2):
+        nj = int(rng.integers(1, min(2 * G, 6) + 1))
+        first = int(rng.integers(0, G - (nj + 1) // 2 + 1))
+        jobs = []
+        for g in range(nj):
+            length = int(rng.integers(30, 300))
+            a, b = gen.make_pair(rng, length, div=float(rng.choice([0.0, 0.03, 0.2])), p_n=0.0)
+            b = b[int(rng.integers(0, min(band // 2, len(b) // 4) + 1)):]
+            jobs.append(dict(a=a, b=b, band=band, gap=-8, **_shape(rng, a, b, int(rng.integers(0, 4)))))
+        _check_pairs(jobs, lane_order=rep, first_group=first)
+
+
+@pytest.mark.parametrize("band,length", [(64, 1000), (150, 700)])
+def test_sim_pairs_rebase_and_tiles(band, length):
+    """Jobs longer than the rebase interval (256 steps) and several sequence tiles; the partner is much
+    shorter, so one half idles (keeps its registers) through most rebases."""
+    rng = np.random.default_rng(7100 + band)
+    a, b = gen.make_pair(rng, length, div=0.03, p_n=0.0)
+    a2, b2 = gen.make_pair(rng, 300, div=0.1, p_n=0.0)
+    jobs = [dict(a=a, b=b, band=band, gap=-8, **_shape(rng, a, b, 0)),
+            dict(a=a2, b=b2, band=band, gap=-8, **_shape(rng, a2, b2, 1))]
+    _check_pairs(jobs)
+    _check_pairs(jobs[::-1], lane_order=1)
+
+
+@pytest.mark.parametrize("gap", [-5, -13, -29])
+def test_sim_pairs_gap_values_and_extreme_inputs(gap):
+    """The range argument of bsw_warp16.h must hold for any input: homopolymers (every cell a match:
+    steepest rise), unrelated sequences (steepest fall), a long insertion (scores run along the band
+    edge), with the mildest and the harshest gap the fast kernels take."""
+    rng = np.random.default_rng(7200 - gap)
+    n = 400
+    homo = np.zeros(n, dtype=np.uint8)
+    r1 = rng.integers(0, 4, n).astype(np.uint8)
+    r2 = rng.integers(0, 4, n).astype(np.uint8)
+    ins = np.concatenate([r1[:150], rng.integers(0, 4, 60).astype(np.uint8), r1[150:]])
+    alt = np.tile(np.array([0, 1], dtype=np.uint8), n // 2)
+    cases = [(homo, homo.copy()), (r1, r2), (r1, ins), (ins, r1), (alt, np.roll(alt, 1)), (homo, alt)]
+    for band in (20, 64):
+        jobs = [dict(a=a, b=b, band=band, gap=gap, **_shape(rng, a, b, 0)) for a, b in cases[:4]]
+        _check_pairs(jobs[:2 * (32 // simlib.band_geometry(band)[1])])
+        jobs = [dict(a=a, b=b, band=band, gap=gap, **_shape(rng, a, b, 0)) for a, b in cases[2:]]
+        _check_pairs(jobs[:2 * (32 // simlib.band_geometry(band)[1])], lane_order=1)
+
+
+def test_sim_pairs_refuse_n():
+    """A window with an N is reported by the pre-scan (the kernel then falls back to the 32-bit body)."""
+    rng = np.random.default_rng(7300)
+    a, b = gen.make_pair(rng, 200, div=0.02, p_n=0.0)
+    a2, b2 = gen.make_pair(rng, 200, div=0.02, p_n=0.0)
+    b2 = b2.copy(); b2[57] = 4
+    jobs = [dict(a=a, b=b, band=64, gap=-8, **_shape(rng, a, b, 0)), dict(a=a2, b=b2, band=64, gap=-8, **_shape(rng, a2, b2, 0))]
+    rc, _ = simlib.sim_align_pairs(jobs, mode=1)
+    assert rc == -2
+    # an N outside the job's windows does not count
+    a3 = np.concatenate([a2, np.array([4, 4, 4], dtype=np.uint8)])
+    jobs[1] = dict(a=a3, b=b, band=64, gap=-8, begin_a=0, end_a=100, begin_b=0, end_b=30, force_start=False, force_end=False)
+    rc, out = simlib.sim_align_pairs(jobs, mode=1)
+    assert rc == 2
