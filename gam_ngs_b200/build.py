@@ -31,7 +31,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    few = ["-DGAMX_DEV_FEW_KERNELS"] if os.environ.get("GAMX_BUILD_FEW") else []  # development: a few kernel geometries only
+    few += os.environ.get("GAMX_BUILD_DEFS", "").split()  # experiments: extra -D flags ...
+    out = os.environ.get("GAMX_BUILD_OUT", LIB)            # ... into another file (load it with GAMX_LIB)
+    cmd = [nvcc] + NVCC_FLAGS + few + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES
     subprocess.run(cmd, check=True)
     return LIB
 

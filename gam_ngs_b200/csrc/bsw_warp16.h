@@ -9,52 +9,64 @@
 // (/root/reference/lib/src/alignment/banded_smith_waterman.cc:69-323); same band coordinates, lane
 // stripes, skewed wavefront and tie-breaking as bsw_warp.h (read that header first).  What differs:
 //
-// Values.  A half-word holds  V - base  with  V = ((H + beta*j) << SH) | tag,  beta = -gap (no per-row
-// offset: alpha = 0), so  diag: V + Cd,  Cd = (S << SH) | tag;  up: V + U,  U = ((2*gap) << SH) | 1;
-// left: V.  H itself grows without bound (|H| <= 5 rows), but neighbouring cells
-// cannot differ by much: for cells of one row  -8 <= H(i,j) - H(i,j-1) <= 13  and for cells of one
-// column  -4 <= H(i,j) - H(i-1,j) <= 5  (induction over the recurrence .cc:160-164 with S in [-4,5],
-// gap <= -5; the never-written region pos < 0 is identically 0 and obeys the same bounds).  So the
-// C cells of a lane stripe span at most 21*(C-1) score units, and every LANE keeps its own base:
-// every kRebaseSteps steps a lane subtracts (slot 0 - kT0) from its registers and adds it to its
-// 32-bit base; the two values a lane exchanges with its neighbours per step are translated by the
-// difference of the two bases (dL, dR; one VIADD.16x2 each).  With kT0 = 6144 and 256 steps between
-// rebases every live half-word stays inside [1700, 18000] for any band, row count and input
-// (bsw_warp16.h: "range budget"), so the 16-bit arithmetic never wraps on a value that is used.
+// Values.  Scores are stored NEGATED and the cell update is a minimum.  A half-word holds  W - base  with
+//      W = CL - ((H + beta*j) << SH)      ("clean": low SH bits all set, CL = 2^SH - 1),    beta = -gap,
+// SH = 2 with the direction store (the low bits of a fresh minimum are the direction), SH = 1 without:
+//      diag: W + Cd,  Cd = -(S << SH) - CL + tag     up: W + U,  U = -((2*gap) << SH) - CL + tagUp     left: W
+// with the tags  DIAG match 0 < DIAG mismatch 1 < UP 2 < LEFT 3 = CL: the smallest candidate wins and, on
+// equal scores, the smallest tag - exactly the reference's priority diag > up > left (.cc:272-307).  A
+// minimum is cleaned by OR-ing CL (one LOP3, needed anyway to strip the tag).  Why negated: the never-written
+// region pos < 0 must stay identically 0, i.e. those cells must reproduce themselves, which
+// takes Cd in [-CL, 0] - and PRMT can make the constants 0x0000 and 0xffff out of ANY table byte by sign
+// replication, so the selector of a position < 0 simply replicates a sign: (W + {0,-1}) | CL = W.  (With
+// maxima and AND-cleaning the constant would have to be in [0, CL]; -1 breaks it.)
 //
-// Substitution bytes.  PRMT sees 8 table bytes: 4 for job A's row (indexed by the a-base A,T,C,G), 4
-// for job B's.  The selector of a cell pair is one 16-bit shared-memory entry
+// H itself grows without bound (|H| <= 5 rows), but neighbouring cells cannot differ by much:
+// for cells of one row  -8 <= H(i,j) - H(i,j-1) <= 13  and for cells of one column  -4 <= H(i,j) - H(i-1,j) <= 5
+// (induction over the recurrence .cc:160-164 with S in [-4,5], gap <= -5; the region pos < 0 obeys the same
+// bounds).  So the C cells of a lane stripe span at most 21*(C-1) score units, and every LANE keeps its own
+// base: every kRebaseSteps steps a lane subtracts (slot 0 - kT0) from its registers and adds it to its 32-bit
+// base; the two values a lane exchanges with its neighbours per step are translated by the difference of the
+// two bases (dL, dR; one VIADD.16x2 each).  With kT0 = -6144 and 256 steps between rebases every live
+// half-word stays inside [-18000, -1700] for any band, row count and input ("range budget" below), so the
+// 16-bit arithmetic never wraps on a value that is used.
+//
+// Substitution bytes.  PRMT sees 8 table bytes: 4 for job A's row (indexed by the a-base A,T,C,G), 4 for job
+// B's.  The selector of a cell pair is one 16-bit shared-memory entry
 //      [ selA | 8+selA | 4+selB | 12+selB ]   (nibble 8+x replicates the sign of byte x)
-// so the result is the two sign-extended Cd half-words.  There is no room for N or the padding symbol:
-//   * jobs whose windows hold an N are not run here (the kernel checks the N masks of both windows of
-//     both jobs first and falls back to the 32-bit body),
-//   * the never-written region pos < 0 is kept by FREEZING those cells: while a lane
-//     still has cells with pos < 0 (steps t < -p0) the PAD step variant does not update them,
-//   * positions >= |a| are a closed region (nothing flows back into filled cells), computed with an
-//     arbitrary base; the end-cell search treats them as the never-filled zeros they are (.cc:183).
-// Band column 2B has no "up" neighbour: its U is kUpBlock16; the padding columns to its right are
-// reset at every rebase so that they cannot run away from the filled ones.
+// so the result is the two sign-extended Cd half-words; positions < 0 take [8 | 8 | 12 | 12].  There is no
+// room for N: jobs whose windows hold an N are not run here (the kernel checks the N masks of both windows of
+// both jobs first and falls back to the 32-bit body).  Positions >= |a| are a closed region (nothing flows
+// back into filled cells), computed with an arbitrary base; the end-cell search treats them as the
+// never-filled zeros they are (.cc:183).  Band column 2B has no "up" neighbour: its U is kUpBlock16; the
+// padding columns to its right are reset at every rebase so that they cannot run away from the filled ones.
+//
+// "Last column" cells (pos == end_a, .cc:197-212) sit in a different slot of a different lane every step.
+// Selecting them out of the registers would cost two compare/select pairs per cell pair on the ALU pipe, the
+// binding one; instead a lane that holds such a cell dumps its stripe to shared memory and reads the slot
+// back by index (LSU pipe, idle otherwise), only while the warp is inside the capture window.
 //
 // Directions.  A 32-bit word holds the tags of 8 consecutive steps of one band column for both jobs
-// (A: low half-word, B: high half-word, oldest tag in the top bit pair of its half); word
-// ((t>>3)*C + k)*LG + l of the PAIR's region.  A pair's region is the two per-job regions of the
-// 32-bit layout side by side, so the fallback can use them as they are.
+// (A: low half-word, B: high half-word, oldest tag in the top bit pair of its half), converted back to the
+// encoding of bsw_warp.h (LEFT 0, UP 1, DIAG 2/3 = 3 - tag) when a word is stored; word ((t>>3)*C + k)*LG + l
+// of the PAIR's region.  A pair's region is the two per-job regions of the 32-bit layout side by side, so
+// the fallback can use them as they are.
 #pragma once
 #include "bsw_common.h"
 #include "bsw_warp.h"
 
 namespace gamx {
 
-constexpr int kT0 = 6144;             // a lane's slot 0 after a rebase (multiple of 4)
+constexpr int kT0 = -6144;            // a lane's slot 0 after a rebase is kT0 + CL
 constexpr int kRebaseSteps = 256;     // steps between rebases (power of two, multiple of 8)
-constexpr int kUpBlock16 = -32768 + 4096;  // "up" addend of band column 2B: below every live value, no wrap
-constexpr uint32_t kNeg16x2 = 0x80008000u;
-// range budget (DIRS, the wider case; units of a quarter score): after a rebase slot 0 = kT0 and slot
-// k <= kT0 + 84*k; in 256 steps a cell's column drifts by [-16, +20] per step; incoming left/right
-// neighbours add 84, the intermediate up + U subtracts at most 232:
-//   live min >= 6144 - 4096 - 84 - 232 - 20 = 1712      live max <= 6144 + 1428 + 5120 + 107 = 12799
-//   padding columns (reset to kT0 at a rebase, fed by column 2B) <= 12799 + 5120 = 17919
-//   padding + kUpBlock16 in [-26960, -10753]: no wrap, below every live value.
+constexpr int kUpBlock16 = 32768 - 4096;   // "up" addend of band column 2B: above every live value, no wrap
+constexpr uint32_t kInf16x2 = 0x7fff7fffu;
+// range budget (SH = 2, the wider case; units of a quarter score, W falls as H + beta*j rises): after a
+// rebase slot 0 = kT0 + 3 and slot k >= kT0 - 84*k; in 256 steps a column drifts by [-20, +16] per step;
+// incoming left/right neighbours differ by at most 84, the intermediate up + U adds at most 232:
+//   live max <= -6141 + 4096 + 84 + 232 + 20 = -1709      live min >= -6141 - 1428 - 5120 - 107 = -12796
+//   padding columns (reset at a rebase, fed by column 2B) >= -12796 - 5120 = -17916
+//   padding + kUpBlock16 in [10756, 26963]: no wrap, above every live value.
 
 // ---- 16x2 helpers (DPX on the device; the host forms wrap exactly like the hardware) -------------
 GAMX_HD int half_lo(uint32_t v) { return (int)(int16_t)(uint16_t)(v & 0xffffu); }
@@ -74,14 +86,14 @@ GAMX_HD uint32_t vsub2w(uint32_t a, uint32_t b) {
   return ((a - b) & 0xffffu) | (((a >> 16) - (b >> 16)) << 16);
 #endif
 }
-// per half-word max(a + b, c), signed, the sum wraps
-GAMX_HD uint32_t viaddmax2(uint32_t a, uint32_t b, uint32_t c) {
+// per half-word min(a + b, c), signed, the sum wraps: one VIADDMNMX.S16x2
+GAMX_HD uint32_t viaddmin2(uint32_t a, uint32_t b, uint32_t c) {
 #if defined(__CUDA_ARCH__)
-  return __viaddmax_s16x2(a, b, c);
+  return __viaddmin_s16x2(a, b, c);
 #else
   const uint32_t s = vadd2w(a, b);
-  const int lo = half_lo(s) > half_lo(c) ? half_lo(s) : half_lo(c);
-  const int hi = half_hi(s) > half_hi(c) ? half_hi(s) : half_hi(c);
+  const int lo = half_lo(s) < half_lo(c) ? half_lo(s) : half_lo(c);
+  const int hi = half_hi(s) < half_hi(c) ? half_hi(s) : half_hi(c);
   return pack2(lo, hi);
 #endif
 }
@@ -103,14 +115,24 @@ GAMX_HD uint32_t prmt_sx(uint32_t lo, uint32_t hi, uint32_t sel) {
   return r;
 #endif
 }
+// A value the compiler must keep in a register: the per-slot "up" addends differ in one slot of one lane only,
+// and recomputing them (a compare and two selects per cell, as ptxas prefers under register pressure) costs
+// as much as the cell update itself.
+GAMX_HD uint32_t opaque(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("" : "+r"(v));
+#endif
+  return v;
+}
 // bitwise select: (a & m) | (b & ~m), one LOP3
 GAMX_HD uint32_t bitsel(uint32_t m, uint32_t a, uint32_t b) { return (a & m) | (b & ~m); }
 
 template <int C, int LG>
 struct alignas(16) GroupSmem16 {
-  uint64_t btab[(kTileSteps + LG + 7) / 8 * 8];  // rows of the tile: low word = job A's 4-byte Cd table, high word = job B's
-  uint16_t asel[kTileSteps + LG * C + 16];       // one PRMT selector per a-position of the tile (both jobs)
-  int cap[2][C * LG];                            // latched "last column" cells (true V), [job][slot][lane]
+  uint64_t btab[(kTileSteps + LG + 15) / 16 * 16];  // rows of the tile: low word = job A's 4-byte Cd table, high word = job B's (staged in runs of 16)
+  uint16_t asel[(kTileSteps + LG * C + 15) / 16 * 16 + 16];  // one PRMT selector per a-position of the tile (both jobs; runs of 16)
+  uint16_t cap[2][C * LG];                       // latched "last column" cells (half-words of the lane's frame), [job][slot][lane]
+  uint32_t dump[C * LG];                         // a lane's stripe, to read one slot back by index, [slot][lane]
 };
 template <int C, int LG>
 struct WarpSmem16 {
@@ -124,16 +146,52 @@ GAMX_HD uint64_t k1_dir_words16(int x, int c, int lg) {
   return 2 * ((steps + 15) / 16) * (uint64_t)c * lg;
 }
 
+// Tile staging reads runs of 16 view positions.  A StageView is a view prepared once per tile: the
+// pointer to the packed word that holds view position 0, so that everything after it is 32-bit
+// arithmetic on small numbers (bsw_common.h's load_codes16 works on 64-bit store indices).
+struct StageView {
+  const uint32_t* wp;  // packed word of view position 0
+  int r;               // position of view position 0 inside that word (0..15)
+  int dir;             // +1 / -1
+  uint32_t comp;       // complement: every 2-bit code ^ 1
+};
+GAMX_HD StageView stage_view(const SeqStore& s, const SeqView& v) {
+  StageView sv;
+  sv.wp = s.packed + (v.origin >> 4);
+  sv.r = (int)(v.origin & 15);
+  sv.dir = v.dir;
+  sv.comp = v.comp;
+  return sv;
+}
+// 2-bit codes of the view positions p .. p+15 (field q = position p+q, complement applied; garbage where
+// the position is outside [0, len)).  Only words that hold a position of [0, len) are touched.
+GAMX_HD uint32_t stage_codes16(const StageView& sv, int p, int len) {
+  const bool fwd = sv.dir > 0;
+  const int i0 = fwd ? sv.r + p : sv.r - p - 15;               // lowest index of the run, relative to word 0
+  const int wmin = fwd ? 0 : (sv.r - (len - 1)) >> 4, wmax = fwd ? (sv.r + len - 1) >> 4 : 0;
+  int w0 = i0 >> 4, w1 = w0 + 1;
+  w0 = imin(imax(w0, wmin), wmax);
+  w1 = imin(imax(w1, wmin), wmax);
+  const uint32_t pa = sv.wp[w0], pb = sv.wp[w1];
+  uint32_t c = funnel_r(pa, pb, 2u * (uint32_t)(i0 & 15));
+  if (!fwd) {  // the run was fetched in ascending store order = descending view order
+    const uint32_t b = brev32(c);
+    c = ((b >> 1) & 0x55555555u) | ((b & 0x55555555u) << 1);  // bit-reversed pairs back in bit order
+  }
+  return c ^ (sv.comp * 0x55555555u);
+}
+
 // Does the view range [from, to] (view positions, from <= to, inside the view) hold an N?  The lanes of
 // a group share the mask words; every lane returns its partial answer (OR-reduce over the group).
-GAMX_HD uint32_t range_n_bits(const SeqStore& s, const SeqView& v, int64_t from, int64_t to, int gl, int lg) {
+GAMX_HD uint32_t range_n_bits(const SeqStore& s, const SeqView& v, int from, int to, int gl, int lg) {
   if (to < from) return 0u;
-  const int64_t lo = v.dir > 0 ? v.origin + from : v.origin - to;
-  const int64_t hi = v.dir > 0 ? v.origin + to : v.origin - from;
-  const int64_t m0 = lo >> 5, m1 = hi >> 5;
+  const uint32_t* mp = s.nmask + (v.origin >> 5);  // mask word of view position 0
+  const int r = (int)(v.origin & 31);
+  const int lo = v.dir > 0 ? r + from : r - to, hi = v.dir > 0 ? r + to : r - from;  // bit range relative to that word
+  const int m0 = lo >> 5, m1 = hi >> 5;
   uint32_t any = 0;
-  for (int64_t m = m0 + gl; m <= m1; m += lg) {
-    uint32_t wv = s.nmask[m];
+  for (int m = m0 + gl; m <= m1; m += lg) {
+    uint32_t wv = mp[m];
     if (m == m0) wv &= 0xffffffffu << (lo & 31);
     if (m == m1) wv &= 0xffffffffu >> (31 - (hi & 31));
     any |= wv;
@@ -143,10 +201,10 @@ GAMX_HD uint32_t range_n_bits(const SeqStore& s, const SeqView& v, int64_t from,
 // N bits of both windows of a job (a: every position a cell of the band can read; b: the DP rows)
 GAMX_HD uint32_t job_n_bits(const SeqStore& s, const DevJob* J, int gl, int lg) {
   if (!J) return 0u;
-  int64_t a_lo = J->p0 < 0 ? 0 : J->p0;
-  int64_t a_hi = (int64_t)J->p0 + J->x - 1 + 2 * (int64_t)J->band;
-  if (a_hi > (int64_t)J->la - 1) a_hi = (int64_t)J->la - 1;
-  return range_n_bits(s, J->a, a_lo, a_hi, gl, lg) | range_n_bits(s, J->b, 0, (int64_t)J->x - 1, gl, lg);
+  const int a_lo = J->p0 < 0 ? 0 : J->p0;
+  const int64_t a_end = (int64_t)J->p0 + J->x - 1 + 2 * (int64_t)J->band;
+  const int a_hi = a_end > (int64_t)J->la - 1 ? J->la - 1 : (int)a_end;
+  return range_n_bits(s, J->a, a_lo, a_hi, gl, lg) | range_n_bits(s, J->b, 0, J->x - 1, gl, lg);
 }
 
 // One warp: 32/LG PAIRS.  JA / JB / outA / outB are per-lane arguments, uniform within a group of LG
@@ -160,9 +218,11 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
                           uint32_t* pair_dirs, DevResult* outA, DevResult* outB) {
   static_assert(stripe_supported(C), "lane stripe width");
   static_assert(LG == 4 || LG == 8 || LG == 16 || LG == 32, "lanes per pair");
-  constexpr int SH = DIRS ? 2 : 0;
+  constexpr int SH = DIRS ? 2 : 1;
+  constexpr int CL = (1 << SH) - 1;                         // low bits of a clean value
+  constexpr uint32_t CL2 = (uint32_t)CL * 0x00010001u;
+  constexpr uint32_t ACC0 = 0x00010001u;                    // bias of the direction accumulator (see GAMX16_STEP)
   constexpr int UF = unroll_of(C);
-  constexpr uint32_t CLEAN = DIRS ? 0xfffcfffcu : 0xffffffffu;
   const int lane = w.lane();
   const int grp = lane / LG, gl = lane % LG;
   GroupSmem16<C, LG>& sm = wsm.g[grp];
@@ -178,7 +238,6 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
   const int beta = -gap;
   const int j0 = gl * C;
   int X[2], la[2], p0[2], kc[2], tcap0[2];
-  SeqView va[2], vb[2];
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     X[h] = liveh[h] ? Jh[h]->x : 0;
@@ -186,8 +245,6 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
     p0[h] = liveh[h] ? Jh[h]->p0 : 0;
     kc[h] = liveh[h] ? Jh[h]->kc : -1;
     tcap0[h] = kc[h] - gl * (C - 1);  // step at which slot 0 holds a "last column" cell (slot k: tcap0 - k)
-    va[h].origin = vb[h].origin = 0; va[h].dir = vb[h].dir = 1; va[h].comp = vb[h].comp = 0;
-    if (liveh[h]) { va[h] = Jh[h]->a; vb[h] = Jh[h]->b; }
   }
 
   // warp-uniform extents
@@ -210,61 +267,79 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
   }
   const int T_total = t_end;
 
-  // Cd bytes (signed): match, mismatch
-  const uint32_t cdMb = (uint32_t)((kScoreMatch << SH) | (DIRS ? kTagDiagMatch : 0)) & 0xffu;
-  const uint32_t cdXb = (uint32_t)((kScoreMismatch * (1 << SH)) | (DIRS ? kTagDiagMis : 0)) & 0xffu;
+  // Cd bytes (signed): match, mismatch - see the header for the encoding
+  const int cdM = -(kScoreMatch * (1 << SH)) - (DIRS ? CL : 0) + (DIRS ? 0 : 0);   // tag DIAG match = 0
+  const int cdX = -(kScoreMismatch * (1 << SH)) - (DIRS ? CL : 0) + (DIRS ? 1 : 0); // tag DIAG mismatch = 1
+  const uint32_t cdMb = (uint32_t)cdM & 0xffu, cdXb = (uint32_t)cdX & 0xffu;
 
   uint32_t H[C], acc[C], U[C];
-  const int u_up = ((2 * gap) * (1 << SH)) | (DIRS ? kTagUp : 0);
+  const int u_up = -((2 * gap) * (1 << SH)) - (DIRS ? CL : 0) + (DIRS ? 2 : 0);    // tag UP = 2
 #pragma unroll
   for (int k = 0; k < C; k++) {
-    H[k] = 0; acc[k] = 0;
-    U[k] = (gl == ld && k == kd) ? pack2(kUpBlock16, kUpBlock16) : pack2(u_up, u_up);
+    H[k] = 0; acc[k] = ACC0;
+    U[k] = opaque((gl == ld && k == kd) ? pack2(kUpBlock16, kUpBlock16) : pack2(u_up, u_up));
   }
   const uint32_t neg1 = (uint32_t)(gap >> 31);  // -1 in a register the compiler cannot fold (FMA-pipe accumulate, see bsw_warp.h)
   // neighbour exchange: lane 0 has no left neighbour, lanes from ld on take no "up" from the right
-  const uint32_t lkeep = gl == 0 ? 0u : 0xffffffffu, lor = gl == 0 ? kNeg16x2 : 0u;
+  const uint32_t lkeep = gl == 0 ? 0u : 0xffffffffu, lor = gl == 0 ? kInf16x2 : 0u;
   const uint32_t rkeep = gl >= ld ? 0u : 0xffffffffu;
   const int kdl = gl < ld ? C - 1 : (gl == ld ? kd : -1);  // last slot of this lane that is a band column
-  int base[2] = {0, 0};     // true V = half-word + base
+  const uint32_t T02 = pack2(kT0 + CL, kT0 + CL);
+  uint32_t* const dumpp = sm.dump + gl;                      // [slot * LG]
+  uint16_t* const capp0 = sm.cap[0] + gl;
+  uint16_t* const capp1 = sm.cap[1] + gl;
+  int base[2] = {0, 0};     // true W = half-word + base
   uint32_t dL = 0, dR = 0;  // base of the left / right neighbour lane minus this lane's, per half
 
   // ---- tile staging: selectors of the a-positions, Cd tables of the b-rows ----------------------------
+  // (the views are re-read from the job records here: they are needed once per 128 steps only)
 #define GAMX16_STAGE_TILE(T0)                                                                          \
   {                                                                                                    \
     w.sync();                                                                                          \
+    StageView sa[2], sb[2];                                                                            \
+    _Pragma("unroll") for (int h = 0; h < 2; h++) {                                                    \
+      sa[h].wp = sb[h].wp = store.packed; sa[h].r = sb[h].r = 0; sa[h].dir = sb[h].dir = 1; sa[h].comp = sb[h].comp = 0; \
+      if (liveh[h]) { sa[h] = stage_view(store, Jh[h]->a); sb[h] = stage_view(store, Jh[h]->b); }      \
+    }                                                                                                  \
     const int na = kTileSteps + LG * C - (LG - 1);                                                     \
-    for (int c0 = gl * 8; c0 < na; c0 += LG * 8) {                                                     \
-      uint32_t byt[2][2];  /* [job][positions 0-3 / 4-7]: selector byte per position */               \
+    for (int c0 = gl * 16; c0 < na; c0 += LG * 16) {                                                   \
+      uint32_t byt[2][4];  /* [job][positions 4q .. 4q+3]: selector byte per position */              \
       _Pragma("unroll") for (int h = 0; h < 2; h++) {                                                  \
         const int pos0 = p0[h] + (T0) + c0;                                                            \
-        uint32_t codes = 0, nfl = 0;                                                                   \
-        if (liveh[h] && pos0 + 7 >= 0 && pos0 < la[h]) load_codes16(store, va[h], pos0, la[h], &codes, &nfl); \
-        codes = (codes ^ (va[h].comp * 0x5555u)) & 0xffffu;                                            \
-        const uint32_t nib = spread2to4(codes);            /* 8 nibbles, values 0..3 */                \
+        uint32_t codes = 0;                                                                            \
+        if (liveh[h] && pos0 + 15 >= 0 && pos0 < la[h]) codes = stage_codes16(sa[h], pos0, la[h]);     \
         const uint32_t tag = h ? 0xc4c4c4c4u : 0x80808080u;                                            \
-        _Pragma("unroll") for (int q = 0; q < 2; q++) {                                                \
-          uint32_t x = (nib >> (16 * q)) & 0xffffu;                                                    \
-          x = (x | (x << 8)) & 0x00ff00ffu;                                                            \
-          x = (x | (x << 4)) & 0x0f0f0f0fu;                /* one nibble value per byte */             \
-          byt[h][q] = (x * 0x11u) | tag;                   /* [sel | 8+sel] resp. [4+sel | 12+sel] */  \
+        const uint32_t padb = h ? 0xccccccccu : 0x88888888u;  /* pos < 0: both nibbles replicate a sign */ \
+        _Pragma("unroll") for (int q = 0; q < 4; q++) {                                                \
+          uint32_t x = (codes >> (8 * q)) & 0xffu;          /* four 2-bit codes */                     \
+          x = (x | (x << 12)) & 0x000f000fu;                                                           \
+          x = (x | (x << 6)) & 0x03030303u;                 /* one code per byte */                    \
+          x = (x * 0x11u) | tag;                            /* [sel | 8+sel] resp. [4+sel | 12+sel] */ \
+          const int nneg = -(pos0 + 4 * q);                 /* positions of this quad that are < 0 */  \
+          if (nneg > 0) {                                                                              \
+            const uint32_t mk = nneg >= 4 ? 0xffffffffu : ((1u << (8 * nneg)) - 1u);                   \
+            x = (x & ~mk) | (padb & mk);                                                               \
+          }                                                                                            \
+          byt[h][q] = x;                                                                               \
         }                                                                                              \
       }                                                                                                \
-      Quad qv;                                                                                         \
-      qv.v[0] = prmt(byt[0][0], byt[1][0], 0x5140u); qv.v[1] = prmt(byt[0][0], byt[1][0], 0x7362u);    \
-      qv.v[2] = prmt(byt[0][1], byt[1][1], 0x5140u); qv.v[3] = prmt(byt[0][1], byt[1][1], 0x7362u);    \
-      *reinterpret_cast<Quad*>(sm.asel + c0) = qv;    /* c0 % 8 == 0: 16-byte aligned */               \
+      Quad q0, q1;                                                                                     \
+      q0.v[0] = prmt(byt[0][0], byt[1][0], 0x5140u); q0.v[1] = prmt(byt[0][0], byt[1][0], 0x7362u);    \
+      q0.v[2] = prmt(byt[0][1], byt[1][1], 0x5140u); q0.v[3] = prmt(byt[0][1], byt[1][1], 0x7362u);    \
+      q1.v[0] = prmt(byt[0][2], byt[1][2], 0x5140u); q1.v[1] = prmt(byt[0][2], byt[1][2], 0x7362u);    \
+      q1.v[2] = prmt(byt[0][3], byt[1][3], 0x5140u); q1.v[3] = prmt(byt[0][3], byt[1][3], 0x7362u);    \
+      *reinterpret_cast<Quad*>(sm.asel + c0) = q0;    /* c0 % 16 == 0: 32-byte aligned */              \
+      *reinterpret_cast<Quad*>(sm.asel + c0 + 8) = q1;                                                 \
     }                                                                                                  \
     const int nb = kTileSteps + LG - 1;                                                                \
-    for (int r0 = gl * 8; r0 < nb; r0 += LG * 8) {                                                     \
+    for (int r0 = gl * 16; r0 < nb; r0 += LG * 16) {                                                   \
       const int i0 = (T0) - (LG - 1) + r0;  /* table r0+q is row i0+q */                               \
       uint32_t cds[2];                                                                                 \
       _Pragma("unroll") for (int h = 0; h < 2; h++) {                                                  \
-        uint32_t codes = 0, nfl = 0;                                                                   \
-        if (liveh[h] && i0 + 7 >= 0 && i0 < X[h]) load_codes16(store, vb[h], i0, X[h], &codes, &nfl);  \
-        cds[h] = codes ^ (vb[h].comp * 0x5555u);                                                       \
+        cds[h] = 0;                                                                                    \
+        if (liveh[h] && i0 + 15 >= 0 && i0 < X[h]) cds[h] = stage_codes16(sb[h], i0, X[h]);            \
       }                                                                                                \
-      _Pragma("unroll") for (int q = 0; q < 8; q++) {                                                  \
+      _Pragma("unroll") for (int q = 0; q < 16; q++) {                                                 \
         const uint32_t ta = (cdXb * 0x01010101u) ^ ((cdXb ^ cdMb) << (8 * ((cds[0] >> (2 * q)) & 3u))); \
         const uint32_t tb = (cdXb * 0x01010101u) ^ ((cdXb ^ cdMb) << (8 * ((cds[1] >> (2 * q)) & 3u))); \
         sm.btab[r0 + q] = ((uint64_t)tb << 32) | ta;                                                   \
@@ -273,14 +348,16 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
     w.sync();                                                                                          \
   }
 
-  // Rebase: slot 0 -> kT0; the padding columns of the lane are reset (see header); the neighbours'
-  // rebase amounts update the base differences.
+  // Rebase: slot 0 -> kT0 + CL; the padding columns of the lane are reset (see header); the latched
+  // "last column" cells follow the frame; the neighbours' rebase amounts update the base differences.
 #define GAMX16_REBASE()                                                                                \
   {                                                                                                    \
-    const uint32_t R = vsub2w(H[0], pack2(kT0, kT0));                                                  \
+    const uint32_t R = vsub2w(H[0], T02);                                                              \
     _Pragma("unroll") for (int k = 0; k < C; k++) {                                                    \
       H[k] = vsub2w(H[k], R);                                                                          \
-      if (k > kdl) H[k] = pack2(kT0, kT0);                                                             \
+      if (k > kdl) H[k] = T02;                                                                         \
+      capp0[k * LG] = (uint16_t)(capp0[k * LG] - (R & 0xffffu));                                       \
+      capp1[k * LG] = (uint16_t)(capp1[k * LG] - (R >> 16));                                           \
     }                                                                                                  \
     base[0] += half_lo(R); base[1] += half_hi(R);                                                      \
     const uint32_t Rl = (uint32_t)w.shfl_up((int)R, 1, LG), Rr = (uint32_t)w.shfl_down((int)R, 1, LG); \
@@ -294,10 +371,11 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
     const uint64_t tb = sm.btab[LG - 1];  // row 0
     const uint32_t tlo = (uint32_t)tb, thi = (uint32_t)(tb >> 32);
     const int kNone = -(1 << 28);
-    int vt[2][C];  // true V of row 0 (with tag)
+    int wt[2][C];   // clean true W of row 0
+    int tg[2][C];   // its tag
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-      int sc[C], hloc[C];
+      int sc[C], hloc[C];  // substitution score of the cell (kNone: never written), running maximum
       int run = kNone;
 #pragma unroll
       for (int k = 0; k < C; k++) {
@@ -305,8 +383,8 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
         const uint32_t cdp = prmt_sx(tlo, thi, sm.asel[gl * C + k]);
         const int cd = h ? half_hi(cdp) : half_lo(cdp);
         const bool valid = liveh[h] && pos >= 0 && pos < la[h] && j < Y;
-        sc[k] = valid ? (cd & 0xff) : -1;                 // Cd byte of the cell, -1: never written
-        const int s = cd >> SH;
+        const int s = (cd == cdM) ? kScoreMatch : kScoreMismatch;  // (no N here: the table holds two values)
+        sc[k] = valid ? s : kNone;
         if (valid) run = (pos > 0 && j > 0) ? imax(run, s) : s;
         hloc[k] = run;
       }
@@ -324,28 +402,25 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
 #pragma unroll
       for (int k = 0; k < C; k++) {
         const int j = j0 + k, pos = p0[h] + j;
-        int v;
-        if (sc[k] < 0) {
-          v = (beta * j) * (1 << SH);  // never written: 0
-        } else {
+        int hh = 0, tag = CL;  // never written: 0
+        if (sc[k] != kNone) {
           if (!(pos > 0 && j > 0)) open = false;
-          const int cds = (int)(int8_t)(uint8_t)sc[k];
-          const int s = cds >> SH;
-          const int hh = open ? imax(hloc[k], in) : hloc[k];
-          v = ((hh + beta * j) * (1 << SH)) | ((DIRS && hh == s) ? (cds & 3) : 0);
+          hh = open ? imax(hloc[k], in) : hloc[k];
+          // direction of a row-0 cell: DIAG when the cell holds its own substitution score
+          if (DIRS && hh == sc[k]) tag = sc[k] == kScoreMatch ? 0 : 1;
         }
-        vt[h][k] = v;
+        wt[h][k] = CL - (hh + beta * j) * (1 << SH);
+        tg[h][k] = tag;
       }
-      base[h] = (vt[h][0] & ~(DIRS ? 3 : 0)) - kT0;
+      base[h] = wt[h][0] - (kT0 + CL);
     }
 #pragma unroll
     for (int k = 0; k < C; k++) {
-      const int ca = vt[0][k] & ~(DIRS ? 3 : 0), cb = vt[1][k] & ~(DIRS ? 3 : 0);
-      H[k] = pack2(ca - base[0], cb - base[1]);
-      if (DIRS) acc[k] = pack2(vt[0][k] & 3, vt[1][k] & 3);
-      if (k > kdl) H[k] = pack2(kT0, kT0);
-      if (tcap0[0] - k == gl) sm.cap[0][k * LG + gl] = ca;  // "last column" cell in row 0
-      if (tcap0[1] - k == gl) sm.cap[1][k * LG + gl] = cb;
+      H[k] = pack2(wt[0][k] - base[0], wt[1][k] - base[1]);
+      if (DIRS) acc[k] = pack2(tg[0][k], tg[1][k]) + ACC0;
+      if (k > kdl) H[k] = T02;
+      if (tcap0[0] - k == gl) sm.cap[0][k * LG + gl] = (uint16_t)(H[k] & 0xffffu);  // "last column" cell in row 0
+      if (tcap0[1] - k == gl) sm.cap[1][k * LG + gl] = (uint16_t)(H[k] >> 16);
     }
     {
       const int bl0 = w.shfl_up(base[0], 1, LG), bl1 = w.shfl_up(base[1], 1, LG);
@@ -355,60 +430,72 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
     }
     if (DIRS && T_total == 1) {  // a single row on a single lane: no step will flush its directions
 #pragma unroll
-      for (int k = 0; k < C; k++) if (live) fp[k * LG] = (acc[k] & 0x00030003u) << 14;
+      for (int k = 0; k < C; k++) if (live) fp[k * LG] = ((0x00010000u - acc[k]) & 0x00030003u) << 14;
     }
   }
 
   // One step tt; PA points at the selector of this lane's slot 0, PB at its row table.
-  // KIND 0 (FAST): every lane is on a row in [1, X-1] of both jobs, no cell with pos < 0, nothing to
-  //                latch; the caller flushes.
-  // KIND 1 (SLOW): lanes outside their row range keep their registers (per job), "last column" cells
-  //                are latched, the direction flush is decided per step.
-  // KIND 2 (PAD):  SLOW, and cells with pos < 0 are frozen (they hold the never-written zeros).
+  // KIND 0 (FAST): every lane is on a row in [1, X-1] of both jobs, nothing to latch; the caller flushes.
+  //                Without the direction store minima need no cleaning, except while cells with pos < 0
+  //                are around (their Cd is 0 or -1): KIND 3 is FAST with the cleaning OR.
+  // KIND 4       : FAST inside the capture window: lanes that hold a "last column" cell latch it.
+  // KIND 1 (SLOW): lanes outside their row range keep their registers (per job; pipeline drain, jobs of
+  //                different length), capture, the direction flush is decided per step.
+  // KIND 2       : SLOW while lanes are still waiting for their first row (pipeline fill, t < LG).
+  // Direction accumulator: acc holds (tags so far) + ACC0, because a step adds  v - (v | CL)  = tag - CL
+  // per half instead of the tag: the constant keeps the recurrence  acc = 4*acc + v - hc  exact (two IMAD on
+  // the FMA pipe); a stored word is ~(acc - ACC0) = 0x10000 - acc, which also turns the tags into the
+  // LEFT 0 / UP 1 / DIAG 2,3 encoding of bsw_warp.h.  acc restarts at ACC0 after every 8-step word (the low
+  // half must not shift into the high one).
+#define GAMX16_CAPTURE(TT)                                                                             \
+  {                                                                                                    \
+    const int dcap0 = tcap0[0] - (TT), dcap1 = tcap0[1] - (TT);  /* the slot that is on a "last column" cell */ \
+    if ((unsigned)dcap0 < (unsigned)C || (unsigned)dcap1 < (unsigned)C) {                              \
+      _Pragma("unroll") for (int k = 0; k < C; k++) dumpp[k * LG] = H[k];                              \
+      if ((unsigned)dcap0 < (unsigned)C) capp0[dcap0 * LG] = (uint16_t)(dumpp[dcap0 * LG] & 0xffffu);  \
+      if ((unsigned)dcap1 < (unsigned)C) capp1[dcap1 * LG] = (uint16_t)(dumpp[dcap1 * LG] >> 16);      \
+    }                                                                                                  \
+  }
 #define GAMX16_STEP(KIND, TT, PA, PB)                                                                  \
   {                                                                                                    \
+    constexpr bool kSlow = (KIND) == 1 || (KIND) == 2;                                                 \
     const int tt = (TT);                                                                               \
     const uint64_t tb = *(PB);                                                                         \
     const uint32_t tlo = (uint32_t)tb, thi = (uint32_t)(tb >> 32);                                     \
     uint32_t left = (vadd2w((uint32_t)w.shfl_up((int)H[C - 1], 1, LG), dL) & lkeep) | lor;             \
-    const bool started = (KIND) == 0 || (tt - gl >= 1);                                                \
+    const bool started = (KIND) != 2 || (tt - gl >= 1);                                                \
     uint32_t keep = 0xffffffffu;                                                                       \
-    int q0 = 0, q1 = 0;                                                                                \
-    if ((KIND) != 0) {                                                                                 \
+    if (kSlow)                                                                                         \
       keep = ((started && tt - gl < X[0]) ? 0xffffu : 0u) | ((started && tt - gl < X[1]) ? 0xffff0000u : 0u); \
-      q0 = -p0[0] - gl * (C - 1) - tt;  /* slots k < q are cells with pos < 0 */                       \
-      q1 = -p0[1] - gl * (C - 1) - tt;                                                                 \
-    }                                                                                                  \
-    const int dcap0 = tcap0[0] - tt, dcap1 = tcap0[1] - tt;                                            \
-    uint32_t capv0 = 0, capv1 = 0;                                                                     \
     uint32_t right = 0;                                                                                \
     _Pragma("unroll") for (int k = 0; k < C; k++) {                                                    \
       const uint32_t cd = prmt_sx(tlo, thi, (PA)[k]);                                                  \
       const uint32_t up = (k == C - 1) ? right : H[(k + 1) % C];                                       \
-      const uint32_t m = viaddmax2(up, U[k], left);                                                    \
-      const uint32_t v = viaddmax2(H[k], cd, m);                                                       \
-      const uint32_t hc = v & CLEAN;                                                                   \
+      const uint32_t m = viaddmin2(up, U[k], left);                                                    \
+      const uint32_t v = viaddmin2(H[k], cd, m);                                                       \
+      const uint32_t hc = (DIRS || (KIND) != 0) ? (v | CL2) : v;                                       \
       if (DIRS && started) acc[k] = (acc[k] * 4u + v) + neg1 * hc;                                     \
-      if ((KIND) == 0) {                                                                               \
-        H[k] = hc;                                                                                     \
-      } else {                                                                                         \
-        uint32_t kk = keep;                                                                            \
-        if ((KIND) == 2) kk &= (k >= q0 ? 0xffffu : 0u) | (k >= q1 ? 0xffff0000u : 0u);                \
-        H[k] = bitsel(kk, hc, H[k]);                                                                   \
-        capv0 = (dcap0 == k) ? H[k] : capv0;                                                           \
-        capv1 = (dcap1 == k) ? H[k] : capv1;                                                           \
-      }                                                                                                \
+      H[k] = kSlow ? bitsel(keep, hc, H[k]) : hc;                                                      \
       left = H[k];                                                                                     \
       if (k == 0) right = vadd2w((uint32_t)w.shfl_down((int)H[0], 1, LG), dR) & rkeep;                 \
     }                                                                                                  \
-    if ((KIND) != 0) {                                                                                 \
-      if ((unsigned)dcap0 < (unsigned)C) sm.cap[0][dcap0 * LG + gl] = half_lo(capv0) + base[0];        \
-      if ((unsigned)dcap1 < (unsigned)C) sm.cap[1][dcap1 * LG + gl] = half_hi(capv1) + base[1];        \
+    if ((KIND) == 4) GAMX16_CAPTURE(tt)                                                                \
+    if (kSlow) {                                                                                       \
+      if (tt >= win_lo && tt <= win_hi) GAMX16_CAPTURE(tt)                                             \
       if (DIRS && ((tt & 7) == 7 || tt == T_total - 1)) {                                              \
-        const int sh = 2 * (7 - (tt & 7));                                                             \
-        _Pragma("unroll") for (int k = 0; k < C; k++) {                                                \
-          if (live) fp[k * LG] = ((acc[k] << sh) & 0xffffu) | (((acc[k] >> 16) << sh) << 16);          \
-          if (tt - gl >= 0) acc[k] = 0;  /* (a lane still before its row 0 keeps that row's tags) */    \
+        if (live) {                                                                                    \
+          if ((tt & 7) == 7) {                                                                         \
+            _Pragma("unroll") for (int k = 0; k < C; k++) fp[k * LG] = 0x00010000u - acc[k];           \
+          } else {  /* the last word of the job, partly filled: the tags move to the top of their half */ \
+            const int sh = 2 * (7 - (tt & 7));                                                         \
+            _Pragma("unroll") for (int k = 0; k < C; k++) {                                            \
+              const uint32_t wd = 0x00010000u - acc[k];                                                \
+              fp[k * LG] = ((wd << sh) & 0xffffu) | (((wd >> 16) << sh) << 16);                        \
+            }                                                                                          \
+          }                                                                                            \
+        }                                                                                              \
+        if (tt - gl >= 0) {  /* (a lane still before its row 0 keeps that row's tags) */               \
+          _Pragma("unroll") for (int k = 0; k < C; k++) acc[k] = ACC0;                                 \
         }                                                                                              \
         fp += C * LG;                                                                                  \
       }                                                                                                \
@@ -424,29 +511,44 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
     const int stop = imin(t0 + kTileSteps, T_total);       // first step this tile does not cover
     while (t < stop) {
       // steps [t, fast_hi) are steady state: every lane has started (t >= LG) and is on a row < X of
-      // both jobs, no cell with pos < 0 is left (t >= pad_end), the last step (partial flush) is
-      // excluded, no lane meets its "last column" cells
+      // both jobs, the last step (partial flush) is excluded.  The variant is fixed per run of groups:
+      // capture window or not, cells with pos < 0 around or not (score only).
       int fast_hi = imin(stop, imin(x_min, T_total - 1));
-      if (t <= win_hi) fast_hi = imin(fast_hi, win_lo);
-      int nf = (t >= LG && t >= pad_end && (t & (UF - 1)) == 0) ? (fast_hi - t) / UF : 0;
+      const bool capture = t + UF > win_lo && t <= win_hi;  // some step of the next group may meet a "last column" cell
+      if (!capture && t <= win_hi) fast_hi = imin(fast_hi, win_lo & ~(UF - 1));
+      const bool padding = !DIRS && t < pad_end;  // cells with pos < 0 around: minima need the cleaning OR
+      if (padding && !capture) fast_hi = imin(fast_hi, (pad_end + UF - 1) & ~(UF - 1));
+      int nf = (t >= LG && (t & (UF - 1)) == 0) ? (fast_hi - t) / UF : 0;
       if (nf > 0) {
         const uint16_t* pa_t = pa + t;
         const uint64_t* pb_t = pb + t;
         do {
+          if (capture) {
 #pragma unroll
-          for (int u = 0; u < UF; u++) GAMX16_STEP(0, t + u, pa_t + u, pb_t + u)
+            for (int u = 0; u < UF; u++) GAMX16_STEP(4, t + u, pa_t + u, pb_t + u)
+          } else if (padding) {
+#pragma unroll
+            for (int u = 0; u < UF; u++) GAMX16_STEP(3, t + u, pa_t + u, pb_t + u)
+          } else {
+#pragma unroll
+            for (int u = 0; u < UF; u++) GAMX16_STEP(0, t + u, pa_t + u, pb_t + u)
+          }
           t += UF; pa_t += UF; pb_t += UF;
           if (DIRS && (t & 7) == 0) {
+            if (live) {  // (an idle group owns no scratch)
 #pragma unroll
-            for (int k = 0; k < C; k++) { if (live) fp[k * LG] = acc[k]; acc[k] = 0; }  // (an idle group owns no scratch)
+              for (int k = 0; k < C; k++) fp[k * LG] = 0x00010000u - acc[k];
+            }
+#pragma unroll
+            for (int k = 0; k < C; k++) acc[k] = ACC0;
             fp += C * LG;
           }
           if ((t & (kRebaseSteps - 1)) == 0) GAMX16_REBASE()
-        } while (--nf > 0);
+        } while (--nf > 0 && (!capture || t <= win_hi));
       } else {
         const int slow_stop = imin(stop, (t & ~(UF - 1)) + UF);  // up to the next group boundary
         do {
-          if (t < pad_end) GAMX16_STEP(2, t, pa + t, pb + t)
+          if (t < LG) GAMX16_STEP(2, t, pa + t, pb + t)
           else GAMX16_STEP(1, t, pa + t, pb + t)
           t++;
           if ((t & (kRebaseSteps - 1)) == 0) GAMX16_REBASE()
@@ -454,6 +556,7 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
       }
     }
   }
+#undef GAMX16_CAPTURE
 #undef GAMX16_STEP
 #undef GAMX16_REBASE
 #undef GAMX16_STAGE_TILE
@@ -469,8 +572,8 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
       for (int k = 0; k < C; k++) {
         const int j = j0 + k;
         if (j >= Jp->jlo && j <= Jp->jhi) {
-          const int vtrue = (h ? half_hi(H[k]) : half_lo(H[k])) + base[h];
-          const int val = (j < Jp->jfill) ? ((vtrue >> SH) - beta * j) : 0;
+          const int wtrue = (h ? half_hi(H[k]) : half_lo(H[k])) + base[h];
+          const int val = (j < Jp->jfill) ? (((CL - wtrue) >> SH) - beta * j) : 0;
           best.consider(val, j);
         }
       }
@@ -479,7 +582,8 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
         for (int k = 0; k < C; k++) {
           const int j = j0 + k, i = tcap0[h] - k - gl;  // the row this slot was on when it met pos == end_a
           if (i >= 0 && i < X[h] && j <= 2 * B && i >= Jp->col_imin) {
-            const int val = Jp->col_zero ? 0 : ((sm.cap[h][k * LG + gl] >> SH) - beta * j);
+            const int wtrue = (int)(int16_t)sm.cap[h][k * LG + gl] + base[h];
+            const int val = Jp->col_zero ? 0 : (((CL - wtrue) >> SH) - beta * j);
             best.consider(val, Y + i);
           }
         }

@@ -66,7 +66,7 @@ struct DevWarp {
 // shuffle / dependent-chain latencies and the leader-only traceback.  Measured +4..16 % across bands
 // against an unconstrained build in the same run (profiles/r1c_geometry_probe.txt).
 #ifndef GAMX_K1_MIN_BLOCKS
-#define GAMX_K1_MIN_BLOCKS(C) ((C) <= 6 ? 8 : ((C) <= 10 ? 5 : 4))
+#define GAMX_K1_MIN_BLOCKS(C) ((C) <= 6 ? 8 : ((C) <= 9 ? 6 : ((C) <= 10 ? 5 : 4)))
 #endif
 template <int C, int LG, bool DIRS>
 __global__ void __launch_bounds__(warps_per_block(LG) * 32, GAMX_K1_MIN_BLOCKS(C) * 4 / warps_per_block(LG))
@@ -89,6 +89,15 @@ k1_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counter
     uint32_t* my_dirs = DIRS ? dirs + (uint64_t)j * group_stride : nullptr;
     warp_align<C, LG, DIRS, false>(w, Jp, store, sm[warp], my_dirs, group_stride, ops, results + (mine < n_jobs ? mine : 0));
   }
+}
+
+// The 32-bit body as a function of its own (not inlined): k1s_kernel needs it rarely, and inlined twice it
+// would share the register allocation of the half-word body and push that one into spills.
+template <int C, int LG, bool DIRS>
+__device__ __noinline__ void fallback32(const DevJob* Jp, const SeqStore& store, WarpSmem<C, LG>& sm, uint32_t* dirs,
+                                        uint64_t stride, uint32_t* ops, DevResult* out) {
+  DevWarp w;
+  warp_align<C, LG, DIRS, false>(w, Jp, store, sm, dirs, stride, ops, out);
 }
 
 // K1s: the 16x2 form (bsw_warp16.h).  A lane group takes TWO consecutive jobs of the launch and runs them as
@@ -124,10 +133,10 @@ k1s_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counte
                                 results + (JA ? ma : 0), results + (JB ? mb : 0));
     } else {
       // (warp_align adds grp * stride to the pointer it is given)
-      warp_align<C, LG, DIRS, false>(w, JA, store, sm[warp].s32, DIRS ? dirs + (uint64_t)(ma - grp) * stride : nullptr, stride, ops,
-                                     results + (JA ? ma : 0));
-      warp_align<C, LG, DIRS, false>(w, JB, store, sm[warp].s32, DIRS ? dirs + (uint64_t)(mb - grp) * stride : nullptr, stride, ops,
-                                     results + (JB ? mb : 0));
+      fallback32<C, LG, DIRS>(JA, store, sm[warp].s32, DIRS ? dirs + (uint64_t)(ma - grp) * stride : nullptr, stride, ops,
+                              results + (JA ? ma : 0));
+      fallback32<C, LG, DIRS>(JB, store, sm[warp].s32, DIRS ? dirs + (uint64_t)(mb - grp) * stride : nullptr, stride, ops,
+                              results + (JB ? mb : 0));
     }
   }
 }
@@ -942,8 +951,12 @@ int occupancy_k1_t(int* blocks_per_sm) {
   return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k1_kernel<C, LG, DIRS>, warps_per_block(LG) * 32, 0);
 }
 
+#ifdef GAMX_DEV_FEW_KERNELS  // development builds (GAMX_BUILD_FEW=1): only the stripe widths of bands 64, 150 and 256
+#define GAMX_FOR_EACH_C(M, LG) M(9, LG) M(10, LG) M(18, LG)
+#else
 #define GAMX_FOR_EACH_C(M, LG) M(2, LG) M(3, LG) M(4, LG) M(5, LG) M(6, LG) M(7, LG) M(8, LG) M(9, LG) M(10, LG) \
   M(11, LG) M(12, LG) M(13, LG) M(14, LG) M(15, LG) M(16, LG) M(17, LG) M(18, LG)
+#endif
 
 template <int LG>
 int k1_blocks_per_sm_lg(int c, bool dirs) {
@@ -1031,7 +1044,11 @@ template <int C, int LG, bool DIRS>
 int occupancy_k2_t(int* blocks_per_sm) {
   return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k2_kernel<C, LG, DIRS>, LG, 0);
 }
+#ifdef GAMX_DEV_FEW_KERNELS
+#define GAMX_FOR_EACH_WIDE_C(M, LG) M(18, LG)
+#else
 #define GAMX_FOR_EACH_WIDE_C(M, LG) M(10, LG) M(11, LG) M(12, LG) M(13, LG) M(14, LG) M(15, LG) M(16, LG) M(17, LG) M(18, LG)
+#endif
 
 int k2_blocks_per_sm(int c, int lg, bool dirs) {
   int b = 0;

@@ -343,7 +343,8 @@ int sim_align_multi(int n_jobs, const uint8_t* const* a, const uint64_t* la, con
 int sim_align_pairs(int n_jobs, const uint8_t* const* a, const uint64_t* la, const uint8_t* const* b,
                     const uint64_t* lb, const uint64_t* begin_a, const uint64_t* end_a, const uint64_t* begin_b,
                     const uint64_t* end_b, uint64_t band, int64_t gap, const int* fs, const int* fe, int mode,
-                    int lane_order, int first_group, gamx_result* results, uint8_t* const* ops_out, uint64_t ops_out_cap) {
+                    int lane_order, int first_group, int rc, gamx_result* results, uint8_t* const* ops_out, uint64_t ops_out_cap) {
+  // rc: bit 0 / bit 1 = the jobs see the reverse complement of the stored a / b contigs
   HostStore hs;
   std::vector<Prepared> P(n_jobs);
   std::vector<DevResult> dr(n_jobs);
@@ -351,7 +352,7 @@ int sim_align_pairs(int n_jobs, const uint8_t* const* a, const uint64_t* la, con
   uint64_t xmax = 0, ops_words = 0;
   for (int k = 0; k < n_jobs; k++) {
     const int64_t ia = hs.add(a[k], la[k]), ib = hs.add(b[k], lb[k]);
-    prepare_job(P[k], nullptr, make_view(hs.start[ia], la[k], false, 0), la[k], make_view(hs.start[ib], lb[k], false, 0),
+    prepare_job(P[k], nullptr, make_view(hs.start[ia], la[k], (rc & 1) != 0, 0), la[k], make_view(hs.start[ib], lb[k], (rc & 2) != 0, 0),
                 lb[k], begin_a[k], end_a[k], begin_b[k], end_b[k], band, gap, fs[k] != 0, fe[k] != 0, mode);
     memset(&dr[k], 0, sizeof(DevResult));
     if (P[k].cls != kClassWarp) return -1;

@@ -128,7 +128,7 @@ def sim_align_multi(jobs, mode=2, lane_order=0):
     return [(res[k], outs[k]) if res[k].status >= 0 else None for k in range(n)]
 
 
-def sim_align_pairs(jobs, mode=2, lane_order=0, first_group=0):
+def sim_align_pairs(jobs, mode=2, lane_order=0, first_group=0, rc=0):
     """Runs jobs (same band and gap, no N) as 16x2 PAIRS in ONE simulated warp: jobs 2g, 2g+1 on lane
     group first_group+g (bsw_warp16.h + PairFetch traceback).  Returns (rc, [(result, ops)])."""
     L = lib()
@@ -152,7 +152,7 @@ def sim_align_pairs(jobs, mode=2, lane_order=0, first_group=0):
     res = (GamxResult * n)()
     L.sim_align_pairs.restype = C.c_int
     rc = L.sim_align_pairs(C.c_int(n), ap, la, bp, lb, ba, ea, bb, eb, u64(jobs[0]["band"]), C.c_int64(jobs[0]["gap"]),
-                           fs, fe, C.c_int(mode), C.c_int(lane_order), C.c_int(first_group), res, op, u64(cap))
+                           fs, fe, C.c_int(mode), C.c_int(lane_order), C.c_int(first_group), C.c_int(rc), res, op, u64(cap))
     return rc, [(res[k], outs[k]) for k in range(n)]
 
 

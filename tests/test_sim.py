@@ -172,7 +172,7 @@ def _check_pairs(jobs, modes=(2, 0), lane_order=0, first_group=0):
                 (mode, n, {k: v for k, v in job.items() if k not in "ab"})
 
 
-@pytest.mark.parametrize("band", [0, 7, 16, 33, 47, 64, 100, 150, 256, 287])
+@pytest.mark.parametrize("band", [0, 1, 7, 16, 33, 47, 64, 100, 130, 150, 200, 256, 271, 287])
 def test_sim_pairs_every_stripe_width(band):
     """Every geometry the host picks (C = 2..18, LG = 4..32): pairs of different length and shape in one
     group (masked drain per half, per-half capture windows, frozen pos < 0 cells), odd job counts,
@@ -180,7 +180,7 @@ def test_sim_pairs_every_stripe_width(band):
     rng = np.random.default_rng(7000 + band)
     c, lg = simlib.band_geometry(band)
     G = 32 // lg
-    for rep in range(2):
+    for rep in range(3):
         nj = int(rng.integers(1, min(2 * G, 6) + 1))
         first = int(rng.integers(0, G - (nj + 1) // 2 + 1))
         jobs = []
@@ -192,7 +192,7 @@ def test_sim_pairs_every_stripe_width(band):
         _check_pairs(jobs, lane_order=rep, first_group=first)
 
 
-@pytest.mark.parametrize("band,length", [(64, 1000), (150, 700)])
+@pytest.mark.parametrize("band,length", [(64, 1000), (16, 900), (150, 1300), (256, 700)])
 def test_sim_pairs_rebase_and_tiles(band, length):
     """Jobs longer than the rebase interval (256 steps) and several sequence tiles; the partner is much
     shorter, so one half idles (keeps its registers) through most rebases."""
@@ -239,3 +239,22 @@ def test_sim_pairs_refuse_n():
     jobs[1] = dict(a=a3, b=b, band=64, gap=-8, begin_a=0, end_a=100, begin_b=0, end_b=30, force_start=False, force_end=False)
     rc, out = simlib.sim_align_pairs(jobs, mode=1)
     assert rc == 2
+
+
+@pytest.mark.parametrize("rc", [1, 2, 3])
+def test_sim_pairs_reverse_complement_views(rc):
+    """The stored contigs hold the reverse complement of what the jobs must see (PctgBuilder.cc:1443):
+    the tile staging of bsw_warp16.h reads such views backwards and complements them."""
+    rng = np.random.default_rng(7400 + rc)
+    jobs, stored = [], []
+    for _ in range(4):
+        a, b = gen.make_pair(rng, int(rng.integers(100, 500)), div=0.04, p_n=0.0)
+        job = dict(a=a, b=b, band=64, gap=-8, **_shape(rng, a, b, int(rng.integers(0, 3))))
+        jobs.append(job)
+        stored.append(dict(job, a=gen.revcomp(a) if rc & 1 else a, b=gen.revcomp(b) if rc & 2 else b))
+    for mode in (2, 0):
+        n, out = simlib.sim_align_pairs(stored, mode=mode, rc=rc)
+        assert n == len(jobs)
+        for job, (r, ops) in zip(jobs, out):
+            got = simlib.result_to_expect(r, ops if mode == 2 else None, mode)
+            assert got == simlib.project(oracle_expect(job), mode)
