@@ -52,7 +52,10 @@ GAMX_HD void generic_align(const GenJob& J, const SeqStore& S, int64_t* rows, ui
   bool col_found = false;
   int64_t col_best = 0, col_i = 0, col_j = 0;
   const int64_t kc = (int64_t)(end_a - begin_a + band);  // i + j of those cells (may wrap: checked below)
-  const bool kc_valid = end_a + band >= begin_a && (end_a - begin_a + band) < (uint64_t)1 << 40;
+  // (end_a < 2^40 first, like the fast path's guard in bsw_host.h: with end_a near 2^64 - e.g. UINT64_MAX from
+  //  m_at + mlen - 1 with mlen = 0 - the sums below wrap into the valid range, but the reference has no
+  //  last-column cell then: int_type(end_a) is negative, .cc:197)
+  const bool kc_valid = end_a < ((uint64_t)1 << 40) && end_a + band >= begin_a && (end_a - begin_a + band) < (uint64_t)1 << 40;
 
   for (uint64_t i = 0; i < x_size; i++) {
     // columns whose pos = begin_a + i + j - band lies in [0, la)

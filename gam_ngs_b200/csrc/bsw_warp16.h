@@ -27,7 +27,8 @@
 // bounds).  So the C cells of a lane stripe span at most 21*(C-1) score units, and every LANE keeps its own
 // base: every kRebaseSteps steps a lane subtracts (slot 0 - kT0) from its registers and adds it to its 32-bit
 // base; the two values a lane exchanges with its neighbours per step are translated by the difference of the
-// two bases (dL, dR; one VIADD.16x2 each).  With kT0 = -6144 and 256 steps between rebases every live
+// two bases ("left": one VIADD.16x2 with dL; "up" from the right: folded into the addend of the last slot, no
+// instruction).  With kT0 = -6144 and 256 steps between rebases every live
 // half-word stays inside [-18000, -1700] for any band, row count and input ("range budget" below), so the
 // 16-bit arithmetic never wraps on a value that is used.
 //
@@ -36,7 +37,7 @@
 //      [ selA | 8+selA | 4+selB | 12+selB ]   (nibble 8+x replicates the sign of byte x)
 // so the result is the two sign-extended Cd half-words; positions < 0 take [8 | 8 | 12 | 12].  There is no
 // room for N: jobs whose windows hold an N are not run here (the kernel checks the N masks of both windows of
-// both jobs first and falls back to the 32-bit body).  Positions >= |a| are a closed region (nothing flows
+// both jobs first and leaves such jobs to the 32-bit kernel, gamx.cu: k1s_kernel's retry list).  Positions >= |a| are a closed region (nothing flows
 // back into filled cells), computed with an arbitrary base; the end-cell search treats them as the
 // never-filled zeros they are (.cc:183).  Band column 2B has no "up" neighbour: its U is kUpBlock16; the
 // padding columns to its right are reset at every rebase so that they cannot run away from the filled ones.
@@ -47,9 +48,9 @@
 // back by index (LSU pipe, idle otherwise), only while the warp is inside the capture window.
 //
 // Directions.  A 32-bit word holds the tags of 8 consecutive steps of one band column for both jobs
-// (A: low half-word, B: high half-word, oldest tag in the top bit pair of its half), converted back to the
-// encoding of bsw_warp.h (LEFT 0, UP 1, DIAG 2/3 = 3 - tag) when a word is stored; word ((t>>3)*C + k)*LG + l
-// of the PAIR's region.  A pair's region is the two per-job regions of the 32-bit layout side by side, so
+// (A: low half-word, B: high half-word, oldest tag in the top bit pair of its half); it is stored as the step
+// loop accumulates it and converted back to the encoding of bsw_warp.h (LEFT 0, UP 1, DIAG 2/3 = 3 - tag) by
+// the traceback (pair_word16); word ((t>>3)*C + k)*LG + l of the PAIR's region.  A pair's region is the two per-job regions of the 32-bit layout side by side, so
 // the fallback can use them as they are.
 #pragma once
 #include "bsw_common.h"
@@ -60,7 +61,6 @@ namespace gamx {
 constexpr int kT0 = -6144;            // a lane's slot 0 after a rebase is kT0 + CL
 constexpr int kRebaseSteps = 256;     // steps between rebases (power of two, multiple of 8)
 constexpr int kUpBlock16 = 32768 - 4096;   // "up" addend of band column 2B: above every live value, no wrap
-constexpr uint32_t kInf16x2 = 0x7fff7fffu;
 // range budget (SH = 2, the wider case; units of a quarter score, W falls as H + beta*j rises): after a
 // rebase slot 0 = kT0 + 3 and slot k >= kT0 - 84*k; in 256 steps a column drifts by [-20, +16] per step;
 // incoming left/right neighbours differ by at most 84, the intermediate up + U adds at most 232:
@@ -139,7 +139,7 @@ struct WarpSmem16 {
   GroupSmem16<C, LG> g[LG >= 32 ? 1 : 32 / LG];
 };
 
-// words of a PAIR's direction region (8 steps per word; an even number of 8-step blocks so that the
+// words of a PAIR's direction region (8 steps per word, the stored form is the step loop's accumulator; an even number of 8-step blocks so that the
 // traceback can always read two consecutive blocks as one 16-step word)
 GAMX_HD uint64_t k1_dir_words16(int x, int c, int lg) {
   const uint64_t steps = (uint64_t)x + lg + 16;
@@ -230,7 +230,10 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
   const bool liveh[2] = {JA != nullptr, JB != nullptr};
   const DevJob* J0 = JA ? JA : JB;   // band and gap are common to the pair
   const bool live = J0 != nullptr;
-  uint32_t* fp = DIRS ? pair_dirs + gl : nullptr;  // running flush pointer
+  // running flush pointer.  An idle group flushes like the others (no predicate in the step loop): its
+  // pair_dirs is a sink of C * LG words that it does not advance in.
+  uint32_t* fp = DIRS ? pair_dirs + gl : nullptr;
+  const int fp_step = live ? C * LG : 0;
 
   const int B = live ? J0->band : 0, Y = 2 * B + 1;
   const int ld = (Y - 1) / C, kd = (Y - 1) - ld * C;  // lane/slot of band column 2B
@@ -280,16 +283,19 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
     U[k] = opaque((gl == ld && k == kd) ? pack2(kUpBlock16, kUpBlock16) : pack2(u_up, u_up));
   }
   const uint32_t neg1 = (uint32_t)(gap >> 31);  // -1 in a register the compiler cannot fold (FMA-pipe accumulate, see bsw_warp.h)
-  // neighbour exchange: lane 0 has no left neighbour, lanes from ld on take no "up" from the right
-  const uint32_t lkeep = gl == 0 ? 0u : 0xffffffffu, lor = gl == 0 ? kInf16x2 : 0u;
-  const uint32_t rkeep = gl >= ld ? 0u : 0xffffffffu;
+  // Neighbour exchange.  The value a lane receives is in the SENDER's frame.  "left" (from lane gl-1) is
+  // translated by dL, one VIADD.16x2 per step; lane 0 has no left neighbour: its dL is the blocking constant
+  // (the shuffle hands it its own last slot, + kUpBlock16 is above every live value, no wrap).  "up" of the
+  // last slot (from lane gl+1) needs no instruction of its own: the translation is folded into that slot's
+  // "up" addend U[C-1]; lanes from ld on take no "up" from the right: their U[C-1] is the blocking addend.
+  const bool has_left = gl != 0, has_right = gl < ld;
   const int kdl = gl < ld ? C - 1 : (gl == ld ? kd : -1);  // last slot of this lane that is a band column
   const uint32_t T02 = pack2(kT0 + CL, kT0 + CL);
   uint32_t* const dumpp = sm.dump + gl;                      // [slot * LG]
   uint16_t* const capp0 = sm.cap[0] + gl;
   uint16_t* const capp1 = sm.cap[1] + gl;
   int base[2] = {0, 0};     // true W = half-word + base
-  uint32_t dL = 0, dR = 0;  // base of the left / right neighbour lane minus this lane's, per half
+  uint32_t dL = 0;          // base of the left neighbour lane minus this lane's, per half (lane 0: the block)
 
   // ---- tile staging: selectors of the a-positions, Cd tables of the b-rows ----------------------------
   // (the views are re-read from the job records here: they are needed once per 128 steps only)
@@ -361,8 +367,8 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
     }                                                                                                  \
     base[0] += half_lo(R); base[1] += half_hi(R);                                                      \
     const uint32_t Rl = (uint32_t)w.shfl_up((int)R, 1, LG), Rr = (uint32_t)w.shfl_down((int)R, 1, LG); \
-    dL = vsub2w(vadd2w(dL, Rl), R);                                                                    \
-    dR = vsub2w(vadd2w(dR, Rr), R);                                                                    \
+    if (has_left) dL = vsub2w(vadd2w(dL, Rl), R);                                                      \
+    if (has_right) U[C - 1] = vsub2w(vadd2w(U[C - 1], Rr), R);                                         \
   }
 
   // ---- first row, banded_smith_waterman.cc:112-132 (see bsw_warp.h), one job after the other ---------
@@ -425,12 +431,12 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
     {
       const int bl0 = w.shfl_up(base[0], 1, LG), bl1 = w.shfl_up(base[1], 1, LG);
       const int br0 = w.shfl_down(base[0], 1, LG), br1 = w.shfl_down(base[1], 1, LG);
-      dL = pack2(bl0 - base[0], bl1 - base[1]);
-      dR = pack2(br0 - base[0], br1 - base[1]);
+      dL = has_left ? pack2(bl0 - base[0], bl1 - base[1]) : pack2(kUpBlock16, kUpBlock16);
+      U[C - 1] = has_right ? pack2(u_up + br0 - base[0], u_up + br1 - base[1]) : pack2(kUpBlock16, kUpBlock16);
     }
     if (DIRS && T_total == 1) {  // a single row on a single lane: no step will flush its directions
 #pragma unroll
-      for (int k = 0; k < C; k++) if (live) fp[k * LG] = ((0x00010000u - acc[k]) & 0x00030003u) << 14;
+      for (int k = 0; k < C; k++) if (live) fp[k * LG] = 0x00010000u - (((0x00010000u - acc[k]) & 0x00030003u) << 14);
     }
   }
 
@@ -444,9 +450,10 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
   // KIND 2       : SLOW while lanes are still waiting for their first row (pipeline fill, t < LG).
   // Direction accumulator: acc holds (tags so far) + ACC0, because a step adds  v - (v | CL)  = tag - CL
   // per half instead of the tag: the constant keeps the recurrence  acc = 4*acc + v - hc  exact (two IMAD on
-  // the FMA pipe); a stored word is ~(acc - ACC0) = 0x10000 - acc, which also turns the tags into the
-  // LEFT 0 / UP 1 / DIAG 2,3 encoding of bsw_warp.h.  acc restarts at ACC0 after every 8-step word (the low
-  // half must not shift into the high one).
+  // the FMA pipe).  The accumulator is stored as it is; the word of tags is ~(acc - ACC0) = 0x10000 - acc,
+  // which also turns the tags into the LEFT 0 / UP 1 / DIAG 2,3 encoding of bsw_warp.h - the traceback does
+  // that subtraction on the few words it reads (pair_word16).  acc restarts at ACC0 after every 8-step word
+  // (the low half must not shift into the high one).
 #define GAMX16_CAPTURE(TT)                                                                             \
   {                                                                                                    \
     const int dcap0 = tcap0[0] - (TT), dcap1 = tcap0[1] - (TT);  /* the slot that is on a "last column" cell */ \
@@ -462,7 +469,7 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
     const int tt = (TT);                                                                               \
     const uint64_t tb = *(PB);                                                                         \
     const uint32_t tlo = (uint32_t)tb, thi = (uint32_t)(tb >> 32);                                     \
-    uint32_t left = (vadd2w((uint32_t)w.shfl_up((int)H[C - 1], 1, LG), dL) & lkeep) | lor;             \
+    uint32_t left = vadd2w((uint32_t)w.shfl_up((int)H[C - 1], 1, LG), dL);                             \
     const bool started = (KIND) != 2 || (tt - gl >= 1);                                                \
     uint32_t keep = 0xffffffffu;                                                                       \
     if (kSlow)                                                                                         \
@@ -477,30 +484,47 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
       if (DIRS && started) acc[k] = (acc[k] * 4u + v) + neg1 * hc;                                     \
       H[k] = kSlow ? bitsel(keep, hc, H[k]) : hc;                                                      \
       left = H[k];                                                                                     \
-      if (k == 0) right = vadd2w((uint32_t)w.shfl_down((int)H[0], 1, LG), dR) & rkeep;                 \
+      if (k == 0) right = (uint32_t)w.shfl_down((int)H[0], 1, LG);                                     \
     }                                                                                                  \
     if ((KIND) == 4) GAMX16_CAPTURE(tt)                                                                \
     if (kSlow) {                                                                                       \
       if (tt >= win_lo && tt <= win_hi) GAMX16_CAPTURE(tt)                                             \
       if (DIRS && ((tt & 7) == 7 || tt == T_total - 1)) {                                              \
-        if (live) {                                                                                    \
-          if ((tt & 7) == 7) {                                                                         \
-            _Pragma("unroll") for (int k = 0; k < C; k++) fp[k * LG] = 0x00010000u - acc[k];           \
-          } else {  /* the last word of the job, partly filled: the tags move to the top of their half */ \
-            const int sh = 2 * (7 - (tt & 7));                                                         \
-            _Pragma("unroll") for (int k = 0; k < C; k++) {                                            \
-              const uint32_t wd = 0x00010000u - acc[k];                                                \
-              fp[k * LG] = ((wd << sh) & 0xffffu) | (((wd >> 16) << sh) << 16);                        \
-            }                                                                                          \
+        if ((tt & 7) == 7) {                                                                           \
+          _Pragma("unroll") for (int k = 0; k < C; k++) fp[k * LG] = acc[k];                           \
+        } else {  /* the last word of the job, partly filled: the tags move to the top of their half */ \
+          const int sh = 2 * (7 - (tt & 7));                                                           \
+          _Pragma("unroll") for (int k = 0; k < C; k++) {                                              \
+            const uint32_t wd = 0x00010000u - acc[k];                                                  \
+            fp[k * LG] = 0x00010000u - (((wd << sh) & 0xffffu) | (((wd >> 16) << sh) << 16));          \
           }                                                                                            \
         }                                                                                              \
         if (tt - gl >= 0) {  /* (a lane still before its row 0 keeps that row's tags) */               \
           _Pragma("unroll") for (int k = 0; k < C; k++) acc[k] = ACC0;                                 \
         }                                                                                              \
-        fp += C * LG;                                                                                  \
+        fp += fp_step;                                                                                 \
       }                                                                                                \
     }                                                                                                  \
   }
+
+  // Steady state runs in BLOCKS of 8 steps that start at multiples of 8 (= one direction word per slot, and
+  // tile and rebase boundaries are block boundaries): UF steps unrolled, 8 / UF times, then the flush -
+  // no per-step tests.  KIND is fixed per run of blocks.
+#define GAMX16_BLOCKS(KIND)                                                                            \
+  do {                                                                                                 \
+    const uint16_t* const pa_end = pa_t + 8;                                                           \
+    int tq = t;                                                                                        \
+    _Pragma("unroll 1") do {                                                                           \
+      _Pragma("unroll") for (int u = 0; u < UF; u++) GAMX16_STEP(KIND, tq + u, pa_t + u, pb_t + u)     \
+      pa_t += UF; pb_t += UF; tq += UF;                                                                \
+    } while (pa_t != pa_end);                                                                          \
+    t += 8;                                                                                            \
+    if (DIRS) {                                                                                        \
+      _Pragma("unroll") for (int k = 0; k < C; k++) { fp[k * LG] = acc[k]; acc[k] = ACC0; }            \
+      fp += fp_step;                                                                                   \
+    }                                                                                                  \
+    if ((t & (kRebaseSteps - 1)) == 0) GAMX16_REBASE()                                                 \
+  } while (--nb > 0 && ((KIND) != 4 || t <= win_hi));
 
   int t = 1;  // row 0 is done; lane gl starts its row 1 at step gl + 1
   int t0 = 0;
@@ -511,42 +535,22 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
     const int stop = imin(t0 + kTileSteps, T_total);       // first step this tile does not cover
     while (t < stop) {
       // steps [t, fast_hi) are steady state: every lane has started (t >= LG) and is on a row < X of
-      // both jobs, the last step (partial flush) is excluded.  The variant is fixed per run of groups:
+      // both jobs, the last step (partial flush) is excluded.  The variant is fixed per run of blocks:
       // capture window or not, cells with pos < 0 around or not (score only).
       int fast_hi = imin(stop, imin(x_min, T_total - 1));
-      const bool capture = t + UF > win_lo && t <= win_hi;  // some step of the next group may meet a "last column" cell
-      if (!capture && t <= win_hi) fast_hi = imin(fast_hi, win_lo & ~(UF - 1));
+      const bool capture = t + 8 > win_lo && t <= win_hi;  // some step of the next block may meet a "last column" cell
+      if (!capture && t <= win_hi) fast_hi = imin(fast_hi, win_lo & ~7);
       const bool padding = !DIRS && t < pad_end;  // cells with pos < 0 around: minima need the cleaning OR
-      if (padding && !capture) fast_hi = imin(fast_hi, (pad_end + UF - 1) & ~(UF - 1));
-      int nf = (t >= LG && (t & (UF - 1)) == 0) ? (fast_hi - t) / UF : 0;
-      if (nf > 0) {
+      if (padding && !capture) fast_hi = imin(fast_hi, (pad_end + 7) & ~7);
+      int nb = (t >= LG && (t & 7) == 0) ? (fast_hi - t) >> 3 : 0;
+      if (nb > 0) {
         const uint16_t* pa_t = pa + t;
         const uint64_t* pb_t = pb + t;
-        do {
-          if (capture) {
-#pragma unroll
-            for (int u = 0; u < UF; u++) GAMX16_STEP(4, t + u, pa_t + u, pb_t + u)
-          } else if (padding) {
-#pragma unroll
-            for (int u = 0; u < UF; u++) GAMX16_STEP(3, t + u, pa_t + u, pb_t + u)
-          } else {
-#pragma unroll
-            for (int u = 0; u < UF; u++) GAMX16_STEP(0, t + u, pa_t + u, pb_t + u)
-          }
-          t += UF; pa_t += UF; pb_t += UF;
-          if (DIRS && (t & 7) == 0) {
-            if (live) {  // (an idle group owns no scratch)
-#pragma unroll
-              for (int k = 0; k < C; k++) fp[k * LG] = 0x00010000u - acc[k];
-            }
-#pragma unroll
-            for (int k = 0; k < C; k++) acc[k] = ACC0;
-            fp += C * LG;
-          }
-          if ((t & (kRebaseSteps - 1)) == 0) GAMX16_REBASE()
-        } while (--nf > 0 && (!capture || t <= win_hi));
+        if (capture) GAMX16_BLOCKS(4)
+        else if (padding) GAMX16_BLOCKS(3)
+        else GAMX16_BLOCKS(0)
       } else {
-        const int slow_stop = imin(stop, (t & ~(UF - 1)) + UF);  // up to the next group boundary
+        const int slow_stop = imin(stop, (t & ~7) + 8);  // up to the next block boundary
         do {
           if (t < LG) GAMX16_STEP(2, t, pa + t, pb + t)
           else GAMX16_STEP(1, t, pa + t, pb + t)
@@ -556,6 +560,7 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
       }
     }
   }
+#undef GAMX16_BLOCKS
 #undef GAMX16_CAPTURE
 #undef GAMX16_STEP
 #undef GAMX16_REBASE
@@ -611,6 +616,9 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
         R.score = best.val; R.end_i = ei; R.end_j = ej;
         if (p0[h] + ei + ej >= la[h]) R.status = kStatusOutOfRange;  // first traceback step reads a.at(pos), .cc:231/:265
       }
+#ifdef GAMX_DEBUG_PATH2
+      printf("  half %d: found %d val %d ord %d status %d X %d la %d p0 %d kc %d jlo %d jhi %d jfill %d base %d H0 %d\n", h, best.found, best.val, best.ord, R.status, X[h], la[h], p0[h], kc[h], Jp->jlo, Jp->jhi, Jp->jfill, base[h], h ? half_hi(H[0]) : half_lo(H[0]));
+#endif
       *(h ? outB : outA) = R;
     }
   }
@@ -619,13 +627,18 @@ GAMX_HD void warp_align16(W& w, const DevJob* JA, const DevJob* JB, const SeqSto
 
 // Traceback fetcher for half `half` of a pair region: two consecutive 8-step blocks make the 16-step
 // word k1_traceback_t expects (oldest tag on top).
+// a0, a1: the stored accumulators of the two blocks (see GAMX16_STEP: word of tags = 0x10000 - accumulator)
+GAMX_HD uint32_t pair_word16(uint32_t a0, uint32_t a1, int half) {
+  const uint32_t w0 = 0x00010000u - a0, w1 = 0x00010000u - a1;
+  return half ? ((w0 & 0xffff0000u) | (w1 >> 16)) : ((w0 << 16) | (w1 & 0xffffu));
+}
 struct PairFetch {
   const uint32_t* dirs;
   int C, LG, half;
   GAMX_HD uint32_t operator()(int blk, int k, int l) const {
-    const uint32_t w0 = dirs[((uint32_t)(2 * blk) * (uint32_t)C + (uint32_t)k) * (uint32_t)LG + (uint32_t)l];
-    const uint32_t w1 = dirs[((uint32_t)(2 * blk + 1) * (uint32_t)C + (uint32_t)k) * (uint32_t)LG + (uint32_t)l];
-    return half ? ((w0 & 0xffff0000u) | (w1 >> 16)) : ((w0 << 16) | (w1 & 0xffffu));
+    const uint32_t a0 = dirs[((uint32_t)(2 * blk) * (uint32_t)C + (uint32_t)k) * (uint32_t)LG + (uint32_t)l];
+    const uint32_t a1 = dirs[((uint32_t)(2 * blk + 1) * (uint32_t)C + (uint32_t)k) * (uint32_t)LG + (uint32_t)l];
+    return pair_word16(a0, a1, half);
   }
 };
 

@@ -1,8 +1,12 @@
 // libgamx.so - sm_100a kernels and the C-ABI host layer (include/gamx.h).
 //
 // Kernels
-//   k1_kernel<C, LG, DIRS>  warp-level banded DP (body: bsw_warp.h), LG = 4/8/16/32 lanes per pair, persistent
-//                        warps pulling jobs from a device counter; DIRS adds the 2-bit direction store.
+//   k1s_kernel<C, LG, DIRS> warp-level banded DP with 16x2 SIMD cells (body: bsw_warp16.h): two jobs per group of
+//                        LG = 4/8/16/32 lanes, persistent warps pulling jobs from a device counter; DIRS adds the
+//                        2-bit direction store.  Job runs it cannot take (an N in a window, mixed band / gap) go
+//                        on the launch's retry list.
+//   k1_kernel<C, LG, DIRS, RETRY>  the 32-bit form (body: bsw_warp.h), one job per lane group: the retry pass behind
+//                        every k1s launch, or all jobs (GAMX_NO_S16).
 //   k2_kernel<C, LG, DIRS>  the same body, one pair per CTA of 64/128/256 threads (wide bands, few long pairs).
 //   tb_kernel / tbw_kernel  traceback of a fill wave: one job per thread / per warp (long jobs); coordinates,
 //                        op counts, first/last match and - FULL mode - the edit string.
@@ -68,9 +72,18 @@ struct DevWarp {
 #ifndef GAMX_K1_MIN_BLOCKS
 #define GAMX_K1_MIN_BLOCKS(C) ((C) <= 6 ? 8 : ((C) <= 9 ? 6 : ((C) <= 10 ? 5 : 4)))
 #endif
-template <int C, int LG, bool DIRS>
+// counters of one fill launch (zeroed before the run): [0] next job of the launch, [1] entries of the retry
+// list, [2] next entry of the retry list
+constexpr int kCountersPerLaunch = 3;
+
+// K1, the 32-bit warp kernel.  RETRY = false: all jobs of the launch, G per visit of the job counter.
+// RETRY = true: the second pass behind a k1s_kernel launch - only the job runs that kernel put on its retry list
+// (windows with an N, or a pair that mixes bands or gaps): entry e = first job of a run of 2 * G jobs, which this
+// kernel takes in two rounds of G; the same direction regions and result slots as the pair kernel would have
+// used (job m of the launch owns words [m * stride, (m+1) * stride)).
+template <int C, int LG, bool DIRS, bool RETRY>
 __global__ void __launch_bounds__(warps_per_block(LG) * 32, GAMX_K1_MIN_BLOCKS(C) * 4 / warps_per_block(LG))
-k1_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counter, SeqStore store,
+k1_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counters, const int* __restrict__ retry_list, SeqStore store,
           uint32_t* __restrict__ dirs, uint64_t group_stride, uint32_t* __restrict__ ops,
           DevResult* __restrict__ results) {
   constexpr int G = 32 / LG;  // pairs per warp
@@ -78,49 +91,53 @@ k1_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counter
   DevWarp w;
   const int warp = (int)(threadIdx.x >> 5);
   const int grp = w.lane() / LG;
+  const int n_retry = RETRY ? counters[1] : 0;
   for (;;) {
     int j = 0;
-    if (w.lane() == 0) j = atomicAdd(counter, G);
+    if (w.lane() == 0) j = RETRY ? atomicAdd(counters + 2, 1) : atomicAdd(counters, G);
     j = __shfl_sync(0xffffffffu, j, 0);
-    if (j >= n_jobs) break;
-    const int mine = j + grp;  // jobs are sorted by cost: the groups of a warp get similar work
-    const DevJob* Jp = mine < n_jobs ? jobs + mine : nullptr;
-    // direction words of job `mine` of this launch: dirs + mine * group_stride (read back by tb_kernel)
-    uint32_t* my_dirs = DIRS ? dirs + (uint64_t)j * group_stride : nullptr;
-    warp_align<C, LG, DIRS, false>(w, Jp, store, sm[warp], my_dirs, group_stride, ops, results + (mine < n_jobs ? mine : 0));
+    if (RETRY) {
+      if (j >= n_retry) break;
+      j = retry_list[j];
+    } else if (j >= n_jobs) {
+      break;
+    }
+#pragma unroll 1
+    for (int round = 0; round < (RETRY ? 2 : 1); round++) {
+      const int first = j + round * G;
+      const int mine = first + grp;  // jobs are sorted by cost: the groups of a warp get similar work
+      const DevJob* Jp = mine < n_jobs ? jobs + mine : nullptr;
+      // direction words of job `mine` of this launch: dirs + mine * group_stride (read back by tb_kernel;
+      // warp_align adds grp * group_stride to the pointer it is given)
+      uint32_t* my_dirs = DIRS ? dirs + (uint64_t)first * group_stride : nullptr;
+      warp_align<C, LG, DIRS, false>(w, Jp, store, sm[warp], my_dirs, group_stride, ops, results + (mine < n_jobs ? mine : 0));
+    }
   }
 }
 
-// The 32-bit body as a function of its own (not inlined): k1s_kernel needs it rarely, and inlined twice it
-// would share the register allocation of the half-word body and push that one into spills.
-template <int C, int LG, bool DIRS>
-__device__ __noinline__ void fallback32(const DevJob* Jp, const SeqStore& store, WarpSmem<C, LG>& sm, uint32_t* dirs,
-                                        uint64_t stride, uint32_t* ops, DevResult* out) {
-  DevWarp w;
-  warp_align<C, LG, DIRS, false>(w, Jp, store, sm, dirs, stride, ops, out);
-}
+// where the idle lane groups of a k1s warp flush their (meaningless) direction words
+__device__ uint32_t g_dir_sink[kMaxC * 32];
 
 // K1s: the 16x2 form (bsw_warp16.h).  A lane group takes TWO consecutive jobs of the launch and runs them as
 // the two half-words of one register set.  The pair form needs what the half-word arithmetic and its 4-entry
 // substitution tables cannot express to be absent: both jobs must take the same band and gap, and no window
 // may hold an N (checked here on the store's N masks, every lane a share of the words).  When any pair of
-// the warp fails the test the whole warp runs its jobs through the 32-bit body instead, one job per group
-// and round (the groups of a warp share their step loop) - same results, same direction regions: job m of
-// the launch owns words [m * stride, (m+1) * stride), a pair the two regions of its jobs together.
+// the warp fails the test the warp puts its run of 2 * G jobs on the launch's retry list instead, and the 32-bit
+// kernel (k1_kernel<.., RETRY>, launched right behind this one) computes them - same results, same direction
+// regions.  (The 32-bit body used to be called from here; as a second kernel it costs this one neither
+// registers nor instruction cache.)
 template <int C, int LG, bool DIRS>
 __global__ void __launch_bounds__(warps_per_block(LG) * 32, GAMX_K1_MIN_BLOCKS(C) * 4 / warps_per_block(LG))
-k1s_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counter, SeqStore store,
-           uint32_t* __restrict__ dirs, uint64_t stride, uint32_t* __restrict__ ops,
-           DevResult* __restrict__ results) {
+k1s_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counters, int* __restrict__ retry_list, SeqStore store,
+           uint32_t* __restrict__ dirs, uint64_t stride, DevResult* __restrict__ results) {
   constexpr int G = 32 / LG;  // pairs per warp
-  union Smem { WarpSmem<C, LG> s32; WarpSmem16<C, LG> s16; };
-  __shared__ Smem sm[warps_per_block(LG)];
+  __shared__ WarpSmem16<C, LG> sm[warps_per_block(LG)];
   DevWarp w;
   const int warp = (int)(threadIdx.x >> 5);
   const int grp = w.lane() / LG, gl = w.lane() % LG;
   for (;;) {
     int j = 0;
-    if (w.lane() == 0) j = atomicAdd(counter, 2 * G);
+    if (w.lane() == 0) j = atomicAdd(counters, 2 * G);
     j = __shfl_sync(0xffffffffu, j, 0);
     if (j >= n_jobs) break;
     const int ma = j + 2 * grp, mb = ma + 1;  // jobs are sorted by cost: the jobs of a warp get similar work
@@ -129,14 +146,10 @@ k1s_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counte
     bool ok = !(JA && JB) || (JA->band == JB->band && JA->gap == JB->gap);
     ok = ok && (job_n_bits(store, JA, gl, LG) | job_n_bits(store, JB, gl, LG)) == 0u;
     if (__all_sync(0xffffffffu, ok)) {
-      warp_align16<C, LG, DIRS>(w, JA, JB, store, sm[warp].s16, DIRS ? dirs + (uint64_t)ma * stride : nullptr,
+      warp_align16<C, LG, DIRS>(w, JA, JB, store, sm[warp], DIRS ? (JA ? dirs + (uint64_t)ma * stride : g_dir_sink) : nullptr,
                                 results + (JA ? ma : 0), results + (JB ? mb : 0));
-    } else {
-      // (warp_align adds grp * stride to the pointer it is given)
-      fallback32<C, LG, DIRS>(JA, store, sm[warp].s32, DIRS ? dirs + (uint64_t)(ma - grp) * stride : nullptr, stride, ops,
-                              results + (JA ? ma : 0));
-      fallback32<C, LG, DIRS>(JB, store, sm[warp].s32, DIRS ? dirs + (uint64_t)(mb - grp) * stride : nullptr, stride, ops,
-                              results + (JB ? mb : 0));
+    } else if (w.lane() == 0) {
+      retry_list[atomicAdd(counters + 1, 1)] = j;
     }
   }
 }
@@ -250,7 +263,7 @@ struct WarpFetch16 {
       if (b >= 0) {
         const uint32_t w0 = dirs[((uint32_t)(2 * b) * (uint32_t)C + (uint32_t)k) * (uint32_t)LG + (uint32_t)l];
         const uint32_t w1 = dirs[((uint32_t)(2 * b + 1) * (uint32_t)C + (uint32_t)k) * (uint32_t)LG + (uint32_t)l];
-        mine = half ? ((w0 & 0xffff0000u) | (w1 >> 16)) : ((w0 << 16) | (w1 & 0xffffu));
+        mine = pair_word16(w0, w1, half);
       }
     }
     return __shfl_sync(0xffffffffu, mine, cb - blk);
@@ -527,8 +540,9 @@ struct Slot {
   // previous wave drain (no idle tail at a wave boundary); ev_ready = inputs of the run are on the device
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_ready = nullptr;
-  DevBuf jobs, gjobs, results, dirs, ops, grows, gdirs, counters;
+  DevBuf jobs, gjobs, results, dirs, ops, grows, gdirs, counters, retry;  // retry: the k1s launches' retry lists
   PinBuf h_jobs, h_gjobs, h_results, h_ops;
+  uint64_t generation = 0;  // bumped by every plan_upload into this slot: a plan whose stamp is older has lost its buffers
 };
 
 struct Device {
@@ -607,6 +621,7 @@ struct gamx_ctx {
   PinBuf h_meta;                  // roff[n+1], sgroup[n+1] of the upload in flight (pinned, shared by the devices)
   uint64_t pipeline_chunk = 65536;  // gamx_set_pipeline_chunk
   uint64_t piece_bytes = 128u << 20;  // raw bytes per upload piece; 128 MB measured 2-3 ms per 2.1 GB faster than 64 MB (GAMX_UPLOAD_PIECE_BYTES)
+  bool up_unsettled = false;      // an asynchronous upload may still read the caller's `codes` (settle_uploads)
   std::mutex mu;
   std::string err;
 };
@@ -844,6 +859,7 @@ int store_upload(gamx_ctx* ctx, const uint8_t* raw, size_t first, size_t n, bool
     d.store_groups = groups_end;
   }
   u.active = true;
+  ctx->up_unsettled = !wait;
   if (wait) {
     if (int rc = upload_advance(ctx, SIZE_MAX)) return rc;
     for (Device& d : ctx->devs) {
@@ -851,6 +867,21 @@ int store_upload(gamx_ctx* ctx, const uint8_t* raw, size_t first, size_t n, bool
       CU(cudaStreamSynchronize(d.up_stream));
     }
   }
+  return GAMX_OK;
+}
+
+// gamx_add_contigs_async's contract (gamx.h): `codes` stays valid until the next batch / plan call on the
+// context returns.  Every such entry point therefore ends here, on every path (errors and fallbacks included):
+// all pieces are enqueued and the copies out of the caller's buffer have completed.
+int settle_uploads(gamx_ctx* ctx) {
+  if (!ctx->up_unsettled) return GAMX_OK;
+  if (int rc = upload_advance(ctx, SIZE_MAX)) return rc;
+  for (Device& d : ctx->devs) {
+    if (d.up_events.empty()) continue;
+    CU(cudaSetDevice(d.id));
+    CU(cudaEventSynchronize(d.up_events[0]));
+  }
+  ctx->up_unsettled = false;
   return GAMX_OK;
 }
 
@@ -897,6 +928,7 @@ struct DevPlan {
   bool two_halves = false;  // the direction scratch has a second half (some group takes several waves)
   bool two_halves_ok = false;  // splitting a group that fits one half into waves is allowed (not for pipelined chunks)
   float last_ms = 0.f;
+  uint64_t generation = 0;  // Slot::generation at plan_upload
 };
 
 }  // namespace
@@ -933,13 +965,18 @@ bool use_s16() {
 uint64_t k1_jobs_per_block(int lg) { return (uint64_t)warps_per_block(lg) * (32 / lg) * (use_s16() ? 2 : 1); }
 
 template <int C, int LG, bool DIRS>
-int launch_k1_t(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, int n_jobs, const DevJob* jobs, int* counter, uint32_t* dirs,
-                uint64_t stride, uint32_t* ops, DevResult* results) {
+int launch_k1_t(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, int n_jobs, const DevJob* jobs, int* counters, int* retry_list,
+                uint32_t* dirs, uint64_t stride, uint32_t* ops, DevResult* results) {
   SeqStore st{(const uint32_t*)d.packed.p, (const uint32_t*)d.nmask.p};
-  if (use_s16())
-    k1s_kernel<C, LG, DIRS><<<g.grid, warps_per_block(LG) * 32, 0, stream>>>(jobs, n_jobs, counter, st, dirs, stride, ops, results);
-  else
-    k1_kernel<C, LG, DIRS><<<g.grid, warps_per_block(LG) * 32, 0, stream>>>(jobs, n_jobs, counter, st, dirs, stride, ops, results);
+  const int threads = warps_per_block(LG) * 32;
+  if (use_s16()) {
+    k1s_kernel<C, LG, DIRS><<<g.grid, threads, 0, stream>>>(jobs, n_jobs, counters, retry_list, st, dirs, stride, results);
+    CU(cudaGetLastError());
+    // the retry pass (normally an empty list: its blocks read the count and leave)
+    k1_kernel<C, LG, DIRS, true><<<g.grid, threads, 0, stream>>>(jobs, n_jobs, counters, retry_list, st, dirs, stride, ops, results);
+  } else {
+    k1_kernel<C, LG, DIRS, false><<<g.grid, threads, 0, stream>>>(jobs, n_jobs, counters, nullptr, st, dirs, stride, ops, results);
+  }
   CU(cudaGetLastError());
   return GAMX_OK;
 }
@@ -948,11 +985,15 @@ template <int C, int LG, bool DIRS>
 int occupancy_k1_t(int* blocks_per_sm) {
   if (use_s16())
     return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k1s_kernel<C, LG, DIRS>, warps_per_block(LG) * 32, 0);
-  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k1_kernel<C, LG, DIRS>, warps_per_block(LG) * 32, 0);
+  return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k1_kernel<C, LG, DIRS, false>, warps_per_block(LG) * 32, 0);
 }
 
 #ifdef GAMX_DEV_FEW_KERNELS  // development builds (GAMX_BUILD_FEW=1): only the stripe widths of bands 64, 150 and 256
+#ifdef GAMX_DEV_C  // ... or one stripe width: -DGAMX_DEV_C=14
+#define GAMX_FOR_EACH_C(M, LG) M(GAMX_DEV_C, LG)
+#else
 #define GAMX_FOR_EACH_C(M, LG) M(9, LG) M(10, LG) M(18, LG)
+#endif
 #else
 #define GAMX_FOR_EACH_C(M, LG) M(2, LG) M(3, LG) M(4, LG) M(5, LG) M(6, LG) M(7, LG) M(8, LG) M(9, LG) M(10, LG) \
   M(11, LG) M(12, LG) M(13, LG) M(14, LG) M(15, LG) M(16, LG) M(17, LG) M(18, LG)
@@ -977,22 +1018,22 @@ int k1_blocks_per_sm(int c, int lg, bool dirs) {
 }
 
 template <int LG>
-int launch_k1_lg(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, int n_jobs, const DevJob* jobs, int* counter, uint32_t* dirs,
+int launch_k1_lg(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, int n_jobs, const DevJob* jobs, int* counter, int* retry_list, uint32_t* dirs,
                  uint64_t stride, uint32_t* ops, DevResult* results) {
   switch (g.c) {
-#define M(N, L) case N: return g.dirs ? launch_k1_t<N, L, true>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results) \
-                                       : launch_k1_t<N, L, false>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results);
+#define M(N, L) case N: return g.dirs ? launch_k1_t<N, L, true>(ctx, d, stream, g, n_jobs, jobs, counter, retry_list, dirs, stride, ops, results) \
+                                       : launch_k1_t<N, L, false>(ctx, d, stream, g, n_jobs, jobs, counter, retry_list, dirs, stride, ops, results);
     GAMX_FOR_EACH_C(M, LG)
 #undef M
     default: ctx->err = "internal: bad stripe width"; return GAMX_ERR_INVALID;
   }
 }
-int launch_k1(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, int n_jobs, const DevJob* jobs, int* counter, uint32_t* dirs,
+int launch_k1(gamx_ctx* ctx, Device& d, cudaStream_t stream, const Group& g, int n_jobs, const DevJob* jobs, int* counter, int* retry_list, uint32_t* dirs,
               uint64_t stride, uint32_t* ops, DevResult* results) {
-  if (g.lg == 32) return launch_k1_lg<32>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results);
-  if (g.lg == 16) return launch_k1_lg<16>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results);
-  if (g.lg == 8) return launch_k1_lg<8>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results);
-  return launch_k1_lg<4>(ctx, d, stream, g, n_jobs, jobs, counter, dirs, stride, ops, results);
+  if (g.lg == 32) return launch_k1_lg<32>(ctx, d, stream, g, n_jobs, jobs, counter, retry_list, dirs, stride, ops, results);
+  if (g.lg == 16) return launch_k1_lg<16>(ctx, d, stream, g, n_jobs, jobs, counter, retry_list, dirs, stride, ops, results);
+  if (g.lg == 8) return launch_k1_lg<8>(ctx, d, stream, g, n_jobs, jobs, counter, retry_list, dirs, stride, ops, results);
+  return launch_k1_lg<4>(ctx, d, stream, g, n_jobs, jobs, counter, retry_list, dirs, stride, ops, results);
 }
 
 // stable LSD radix sort of job indices by descending cost
@@ -1155,7 +1196,7 @@ void gamx_destroy(gamx_ctx* ctx) {
     PinBuf* pbs[] = {&d.h_stage, &d.h_stage2};
     for (PinBuf* b : pbs) if (b->p) cudaFreeHost(b->p);
     for (Slot& sl : d.s) {
-      DevBuf* sd[] = {&sl.jobs, &sl.gjobs, &sl.results, &sl.dirs, &sl.ops, &sl.grows, &sl.gdirs, &sl.counters};
+      DevBuf* sd[] = {&sl.jobs, &sl.gjobs, &sl.results, &sl.dirs, &sl.ops, &sl.grows, &sl.gdirs, &sl.counters, &sl.retry};
       for (DevBuf* b : sd) if (b->p) cudaFree(b->p);
       PinBuf* sp[] = {&sl.h_jobs, &sl.h_gjobs, &sl.h_results, &sl.h_ops};
       for (PinBuf* b : sp) if (b->p) cudaFreeHost(b->p);
@@ -1179,7 +1220,14 @@ void gamx_destroy(gamx_ctx* ctx) {
 }
 
 int gamx_device_count(const gamx_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
-const char* gamx_last_error(const gamx_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+const char* gamx_last_error(const gamx_ctx* ctx) {
+  if (!ctx) return "null context";
+  // a per-thread copy: another thread's call on the context may rewrite the message at any time
+  static thread_local std::string copy;
+  std::lock_guard<std::mutex> lk(const_cast<gamx_ctx*>(ctx)->mu);
+  copy = ctx->err;
+  return copy.c_str();
+}
 
 int64_t gamx_add_contig(gamx_ctx* ctx, const uint8_t* codes, uint64_t len) {
   if (!ctx || (!codes && len)) return GAMX_ERR_INVALID;
@@ -1255,8 +1303,13 @@ static int64_t add_contigs_impl(gamx_ctx* ctx, const uint8_t* codes, const uint6
   return (int64_t)first;
 }
 
+static uint64_t contig_length_locked(const gamx_ctx* ctx, uint32_t id) {
+  return id < ctx->store.length.size() ? ctx->store.length[id] : 0;
+}
 uint64_t gamx_contig_length(const gamx_ctx* ctx, uint32_t id) {
-  return (ctx && id < ctx->store.length.size()) ? ctx->store.length[id] : 0;
+  if (!ctx) return 0;
+  std::lock_guard<std::mutex> lk(const_cast<gamx_ctx*>(ctx)->mu);  // (gamx_add_contig may reallocate the index)
+  return contig_length_locked(ctx, id);
 }
 
 int gamx_clear_contigs(gamx_ctx* ctx) {
@@ -1285,6 +1338,7 @@ int gamx_set_pipeline_chunk(gamx_ctx* ctx, uint64_t jobs_per_chunk) {
 
 uint64_t gamx_ops_capacity(const gamx_ctx* ctx, const gamx_job* jobs, uint64_t n) {
   if (!ctx || !jobs) return 0;
+  std::lock_guard<std::mutex> lk(const_cast<gamx_ctx*>(ctx)->mu);  // (reads the contig index)
   uint64_t total = 0;
   for (uint64_t i = 0; i < n; i++) {
     if (jobs[i].mode != GAMX_MODE_FULL) continue;
@@ -1529,12 +1583,8 @@ static int blocks_per_sm_cached(int c, int lg, bool dirs) {
   if (v == 0) {
     const int b = lg > 32 ? k2_blocks_per_sm(c, lg, dirs) : k1_blocks_per_sm(c, lg, dirs);
     v = b > 0 ? b : -1;
-    if (getenv("GAMX_TIMING")) {
-      cudaFuncAttributes fa = {};
-      if (c == 9 && lg == 16) cudaFuncGetAttributes(&fa, dirs ? (const void*)k1_kernel<9, 16, true> : (const void*)k1_kernel<9, 16, false>);
-      fprintf(stderr, "[gamx] kernel family C=%d LG=%d dirs=%d: %d resident blocks per SM (numRegs %d, static smem %zu)\n", c, lg,
-              (int)dirs, b, fa.numRegs, fa.sharedSizeBytes);
-    }
+    if (getenv("GAMX_TIMING"))
+      fprintf(stderr, "[gamx] kernel family C=%d LG=%d dirs=%d: %d resident blocks per SM\n", c, lg, (int)dirs, b);
   }
   return v > 0 ? v : 0;
 }
@@ -1553,6 +1603,11 @@ static int plan_upload(gamx_plan* pl) {
     Slot& sl = d.s[pl->slot];
     if (dp.n_jobs == 0) continue;
     CU(cudaSetDevice(d.id));
+    // The descriptors, results and scratch of a plan live in the slot's buffers.  A plan that is not a chunk
+    // of a pipelined batch (those order their own reuse) waits for whatever still uses the slot - e.g. the
+    // descriptor copy of an earlier plan out of the pinned h_jobs - and takes the slot over.
+    if (!pl->chunked) CU(cudaStreamSynchronize(sl.stream));
+    dp.generation = ++sl.generation;
     lap(5);
     // the kernels read the contig store: stream-ordered behind the upload pieces they need
     if (int rc = store_ready(ctx, d, sl.stream, pl->max_contig)) return rc;
@@ -1643,7 +1698,10 @@ static int plan_upload(gamx_plan* pl) {
       }
     dp.dirs_words = dp.two_halves ? std::min(half_words, used_words) : (want_words ? half_words : 0);
     if (int rc = ensure_dev(ctx, sl.dirs, dp.dirs_words * (dp.two_halves ? 8 : 4) + 64)) return rc;
-    if (int rc = ensure_dev(ctx, sl.counters, sizeof(int) * (dp.n_launches + 1))) return rc;
+    if (int rc = ensure_dev(ctx, sl.counters, sizeof(int) * kCountersPerLaunch * (dp.n_launches + 1))) return rc;
+    // retry lists of the pair kernels: a launch of nw jobs needs at most nw / 2 + 1 entries (one per visit of the
+    // job counter, at least two jobs each); the launches of a run take consecutive regions
+    if (int rc = ensure_dev(ctx, sl.retry, sizeof(int) * ((size_t)dp.n_dev_jobs / 2 + dp.n_launches + 1))) return rc;
     lap(2);
     DevJob* hj = (DevJob*)sl.h_jobs.p;
     GenJob* hg = (GenJob*)sl.h_gjobs.p;
@@ -1685,8 +1743,11 @@ int gamx_plan_create(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan*
   std::lock_guard<std::mutex> lk(ctx->mu);
   *out = nullptr;
   gamx_plan* pl = nullptr;
-  if (int rc = plan_build_checked(ctx, jobs, n, &pl)) return rc;
-  if (int rc = plan_upload(pl)) { delete pl; return rc; }
+  int rc = plan_build_checked(ctx, jobs, n, &pl);
+  if (!rc) rc = plan_upload(pl);
+  const int rc_up = settle_uploads(ctx);
+  if (!rc) rc = rc_up;
+  if (rc) { delete pl; return rc; }
   *out = pl;
   return GAMX_OK;
 }
@@ -1700,10 +1761,11 @@ static int plan_run_locked(gamx_plan* pl) {
     Slot& sl = d.s[pl->slot];
     CU(cudaSetDevice(d.id));
     CU(cudaEventRecord(sl.ev0, sl.stream));
-    CU(cudaMemsetAsync(sl.counters.p, 0, sizeof(int) * (dp.n_launches + 1), sl.stream));
+    CU(cudaMemsetAsync(sl.counters.p, 0, sizeof(int) * kCountersPerLaunch * (dp.n_launches + 1), sl.stream));
     CU(cudaEventRecord(sl.ev_ready, sl.stream));
     CU(cudaStreamWaitEvent(sl.stream2, sl.ev_ready, 0));
     uint32_t launch = 0, wave = 0;
+    uint64_t retry_off = 0;  // next free entry of sl.retry
     bool half_used[2] = {false, false};
     for (size_t gi = 0; gi < dp.groups.size(); gi++) {
       const Group& g = dp.groups[gi];
@@ -1729,11 +1791,13 @@ static int plan_run_locked(gamx_plan* pl) {
         gw.c = g.c; gw.lg = g.lg; gw.dirs = g.dirs;
         const uint64_t pairs_per_block = g.lg > 32 ? 1 : k1_jobs_per_block(g.lg);
         gw.grid = (int)std::min<uint64_t>((uint64_t)g.grid, (nw + pairs_per_block - 1) / pairs_per_block);
-        const int rc = g.lg > 32 ? launch_k2(ctx, d, fs, gw, (int)nw, dj + w0, (int*)sl.counters.p + launch, half,
+        int* const counters = (int*)sl.counters.p + (size_t)kCountersPerLaunch * launch;
+        const int rc = g.lg > 32 ? launch_k2(ctx, d, fs, gw, (int)nw, dj + w0, counters, half,
                                              g.max_dir_words, (uint32_t*)sl.ops.p, res + w0)
-                                 : launch_k1(ctx, d, fs, gw, (int)nw, dj + w0, (int*)sl.counters.p + launch, half,
+                                 : launch_k1(ctx, d, fs, gw, (int)nw, dj + w0, counters, (int*)sl.retry.p + retry_off, half,
                                              g.max_dir_words, (uint32_t*)sl.ops.p, res + w0);
         if (rc) return rc;
+        if (g.lg <= 32) { retry_off += nw / 2 + 1; if (use_s16()) pl->launches++; }
         pl->launches++; launch++;
         if (walk) {
           CU(cudaEventRecord(sl.ev_fill[h], fs));
@@ -1765,9 +1829,25 @@ static int plan_run_locked(gamx_plan* pl) {
   return GAMX_OK;
 }
 
+// A plan owns no device memory of its own: a later batch, merge round or plan on the same context reuses the
+// slot's buffers.  The public plan entry points refuse a plan whose stamp is stale instead of running on (or
+// returning) another batch's data.
+static int plan_check_owner(gamx_plan* pl) {
+  gamx_ctx* ctx = pl->ctx;
+  for (const DevPlan& dp : pl->dps) {
+    if (dp.n_jobs == 0) continue;
+    if (ctx->devs[dp.dev].s[pl->slot].generation != dp.generation) {
+      ctx->err = "plan invalidated: a later batch or plan on this context took over its device buffers";
+      return GAMX_ERR_INVALID;
+    }
+  }
+  return GAMX_OK;
+}
+
 int gamx_plan_run(gamx_plan* pl) {
   if (!pl) return GAMX_ERR_INVALID;
   std::lock_guard<std::mutex> lk(pl->ctx->mu);
+  if (int rc = plan_check_owner(pl)) return rc;
   return plan_run_locked(pl);
 }
 
@@ -1849,6 +1929,7 @@ static int plan_fetch_locked(gamx_plan* pl, gamx_result* results, uint8_t* ops_b
 int gamx_plan_fetch(gamx_plan* pl, gamx_result* results, uint8_t* ops_buf, uint64_t ops_cap) {
   if (!pl) return GAMX_ERR_INVALID;
   std::lock_guard<std::mutex> lk(pl->ctx->mu);
+  if (int rc = plan_check_owner(pl)) return rc;
   if (int rc = plan_sync_locked(pl)) return rc;
   return plan_fetch_locked(pl, results, ops_buf, ops_cap);
 }
@@ -1980,10 +2061,18 @@ static int align_batch_pipelined(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n
   return rc;
 }
 
+static int align_batch_locked(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_result* results, uint8_t* ops_buf, uint64_t ops_cap);
+
 int gamx_align_batch(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_result* results, uint8_t* ops_buf,
                      uint64_t ops_cap) {
   if (!ctx || (!jobs && n) || (!results && n)) return GAMX_ERR_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
+  const int rc = align_batch_locked(ctx, jobs, n, results, ops_buf, ops_cap);
+  const int rc_up = settle_uploads(ctx);  // (also for n == 0, errors and the single-plan fallback)
+  return rc ? rc : rc_up;
+}
+
+static int align_batch_locked(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_result* results, uint8_t* ops_buf, uint64_t ops_cap) {
   static const bool timing = getenv("GAMX_TIMING") != nullptr;  // prints a host-side phase breakdown
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {

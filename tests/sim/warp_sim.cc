@@ -11,6 +11,7 @@
 // product (bsw_host.h), so those are exercised on the CPU too.  Nothing here is used by the
 // product path; the -m gpu tests exercise the real kernels through the C ABI.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 #include <ucontext.h>
 
@@ -24,7 +25,9 @@
 
 using namespace gamx;
 
-namespace {
+// (a named namespace: the build may split the template instantiations over several translation units,
+// SIM_PART below)
+namespace simns {
 
 struct Sched;
 struct SimWarp {
@@ -92,7 +95,7 @@ struct Sched {
   }
 };
 
-int SimWarp::exchange(int v, int src) {
+inline int SimWarp::exchange(int v, int src) {
   s->slot[lane_] = v;
   s->barrier(lane_);
   const int r = s->slot[src];
@@ -123,7 +126,7 @@ void body_c(SimWarp& w, void* p) {
 
 template <int C, int LG>
 void dispatch(WarpArgs& a, bool desc) {
-  std::vector<uint64_t> smem((sizeof(WarpSmem<C, LG>) + 7) / 8);
+  std::vector<uint64_t> smem((sizeof(WarpSmem<C, LG>) + 7) / 8, 0x9e3779b97f4a7c15ull);  // (garbage, like a reused block)
   a.smem = smem.data();
   Sched* s = new Sched();
   s->run(body_c<C, LG>, &a, desc, LG > 32 ? LG : 32);
@@ -140,6 +143,32 @@ void run_warp_lg(WarpArgs& a, bool desc) {
     default: break;
   }
 }
+// Parallel build (tests/simlib.py): part 0 holds the glue and only DECLARES the per-LG instantiations, parts
+// 1..11 define one of them each.  Without SIM_PART everything is one translation unit.
+#if defined(SIM_PART) && SIM_PART == 0
+extern template void run_warp_lg<4>(WarpArgs&, bool);
+extern template void run_warp_lg<8>(WarpArgs&, bool);
+extern template void run_warp_lg<16>(WarpArgs&, bool);
+extern template void run_warp_lg<32>(WarpArgs&, bool);
+extern template void run_warp_lg<64>(WarpArgs&, bool);
+extern template void run_warp_lg<128>(WarpArgs&, bool);
+extern template void run_warp_lg<256>(WarpArgs&, bool);
+#elif defined(SIM_PART) && SIM_PART == 1
+template void run_warp_lg<4>(WarpArgs&, bool);
+#elif defined(SIM_PART) && SIM_PART == 2
+template void run_warp_lg<8>(WarpArgs&, bool);
+#elif defined(SIM_PART) && SIM_PART == 3
+template void run_warp_lg<16>(WarpArgs&, bool);
+#elif defined(SIM_PART) && SIM_PART == 4
+template void run_warp_lg<32>(WarpArgs&, bool);
+#elif defined(SIM_PART) && SIM_PART == 5
+template void run_warp_lg<64>(WarpArgs&, bool);
+#elif defined(SIM_PART) && SIM_PART == 6
+template void run_warp_lg<128>(WarpArgs&, bool);
+#elif defined(SIM_PART) && SIM_PART == 7
+template void run_warp_lg<256>(WarpArgs&, bool);
+#endif
+#if !defined(SIM_PART) || SIM_PART == 0
 void run_warp(WarpArgs& a, bool desc) {
   if (a.lg == 32) run_warp_lg<32>(a, desc);
   else if (a.lg == 16) run_warp_lg<16>(a, desc);
@@ -149,6 +178,7 @@ void run_warp(WarpArgs& a, bool desc) {
   else if (a.lg == 128) run_warp_lg<128>(a, desc);
   else run_warp_lg<256>(a, desc);
 }
+#endif
 
 
 // ---- 16x2 pairs (bsw_warp16.h) -------------------------------------------------------------------
@@ -184,6 +214,11 @@ void body_pair(SimWarp& w, void* p) {
 template <int C, int LG>
 void dispatch_pair(PairArgs& a, bool desc) {
   std::vector<uint64_t> smem((sizeof(WarpSmem16<C, LG>) + 7) / 8);
+  {  // garbage, like a reused block (SIM_SMEM_SEED varies it)
+    const char* e = getenv("SIM_SMEM_SEED");
+    uint64_t x = 0x9e3779b97f4a7c15ull * (uint64_t)(e ? atoll(e) + 1 : 1);
+    for (auto& v : smem) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; v = x; }
+  }
   a.smem = smem.data();
   Sched* s = new Sched();
   s->run(body_pair<C, LG>, &a, desc, 32);
@@ -199,15 +234,33 @@ void run_pair_lg(PairArgs& a, bool desc) {
     default: break;
   }
 }
+#if defined(SIM_PART) && SIM_PART == 0
+extern template void run_pair_lg<4>(PairArgs&, bool);
+extern template void run_pair_lg<8>(PairArgs&, bool);
+extern template void run_pair_lg<16>(PairArgs&, bool);
+extern template void run_pair_lg<32>(PairArgs&, bool);
+#elif defined(SIM_PART) && SIM_PART == 8
+template void run_pair_lg<4>(PairArgs&, bool);
+#elif defined(SIM_PART) && SIM_PART == 9
+template void run_pair_lg<8>(PairArgs&, bool);
+#elif defined(SIM_PART) && SIM_PART == 10
+template void run_pair_lg<16>(PairArgs&, bool);
+#elif defined(SIM_PART) && SIM_PART == 11
+template void run_pair_lg<32>(PairArgs&, bool);
+#endif
+#if !defined(SIM_PART) || SIM_PART == 0
 void run_pair(PairArgs& a, bool desc) {
   if (a.lg == 32) run_pair_lg<32>(a, desc);
   else if (a.lg == 16) run_pair_lg<16>(a, desc);
   else if (a.lg == 8) run_pair_lg<8>(a, desc);
   else run_pair_lg<4>(a, desc);
 }
+#endif
 
-}  // namespace
+}  // namespace simns
+using namespace simns;
 
+#if !defined(SIM_PART) || SIM_PART == 0
 extern "C" {
 
 // One job through packing -> prepare_job -> kernel body (simulated warp or generic thread)
@@ -373,8 +426,8 @@ int sim_align_pairs(int n_jobs, const uint8_t* const* a, const uint64_t* la, con
     const int g = first_group + k / 2;
     if (k & 1) { pa.jb[g] = &P[k].dj; pa.ob[g] = &dr[k]; }
     else { pa.ja[g] = &P[k].dj; pa.oa[g] = &dr[k]; }
-    pa.pdirs[g] = dirs.data() + (uint64_t)g * stride;
   }
+  for (int g = 0; g < G; g++) pa.pdirs[g] = dirs.data() + (uint64_t)g * stride;  // (idle groups: their sink)
   pa.store = st; pa.c = c; pa.lg = lg; pa.dirs_on = mode != kModeScore;
   run_pair(pa, (lane_order & 1) != 0);
   for (int g = 0; g < G; g++) if (pa.nbits[g]) return -2;
@@ -399,3 +452,4 @@ int sim_align_pairs(int n_jobs, const uint8_t* const* a, const uint64_t* la, con
 void sim_band_geometry(uint64_t band, int* c, int* lg) { geometry_for_band(band, true, c, lg); }
 
 }  // extern "C"
+#endif  // glue part

@@ -68,8 +68,13 @@ def lib():
                         ("bsw_common.h", "bsw_warp.h", "bsw_warp16.h", "bsw_generic.h", "bsw_traceback.h", "bsw_host.h")]
         if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
             os.makedirs(os.path.dirname(out), exist_ok=True)
-            subprocess.run(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", "-shared", "-fPIC",
-                            "-o", out, src], check=True)
+            # twelve translation units in parallel (warp_sim.cc: SIM_PART), then one link
+            flags = ["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", "-fPIC"]
+            objs = [os.path.join(HERE, "_build", f"warp_sim_{p}.o") for p in range(12)]
+            procs = [subprocess.Popen(flags + [f"-DSIM_PART={p}", "-c", "-o", o, src]) for p, o in enumerate(objs)]
+            if any(pr.wait() != 0 for pr in procs):
+                raise RuntimeError("simulator build failed")
+            subprocess.run(["g++", "-shared", "-o", out] + objs, check=True)
         _lib = C.CDLL(out)
         u8p, u64 = C.POINTER(C.c_uint8), C.c_uint64
         _lib.sim_align.argtypes = [u8p, u64, C.c_int, u64, u64, u8p, u64, C.c_int, u64, u64,

@@ -258,3 +258,20 @@ def test_sim_pairs_reverse_complement_views(rc):
         for job, (r, ops) in zip(jobs, out):
             got = simlib.result_to_expect(r, ops if mode == 2 else None, mode)
             assert got == simlib.project(oracle_expect(job), mode)
+
+
+@pytest.mark.parametrize("gap", [-3, -8])
+def test_generic_body_end_a_wraps(gap):
+    """end_a near 2^64 (m_at + mlen - 1 with mlen = 0): the reference has no "last column" cell then
+    (int_type(end_a) < 0, banded_smith_waterman.cc:197-212) - the generic body must not invent one out of
+    wrapped sums.  Sequences chosen so that every last-row score is negative."""
+    rng = np.random.default_rng(77)
+    a = rng.integers(0, 4, 90).astype(np.uint8)
+    b = ((a[:60] + 1 + rng.integers(0, 3, 60)) % 4).astype(np.uint8)  # mismatch at every diagonal position
+    for end_a in (2**64 - 1, 2**64 - 5, 2**63 + 7):
+        for begin_a in (0, 3, 40):
+            job = dict(a=a, b=b, band=20, gap=gap, begin_a=begin_a, end_a=end_a, begin_b=0, end_b=len(b) - 1,
+                       force_start=False, force_end=False)
+            exp = oracle_expect(job)
+            _check(job, exp, modes=(2, 0), force_class=2)
+            _check(job, exp, modes=(2, 0))
