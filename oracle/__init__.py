@@ -54,6 +54,18 @@ class RefResult(C.Structure):
     ]
 
 
+class MergeBlockRec(C.Structure):
+    """oracle/pctg_shim.cc: gamref_block (= include/gamx.h gamx_block)"""
+    _fields_ = [("num_reads", C.c_int32), ("m_strand", C.c_uint8), ("s_strand", C.c_uint8), ("reserved_", C.c_uint8 * 2),
+                ("m_begin", C.c_int32), ("m_end", C.c_int32), ("s_begin", C.c_int32), ("s_end", C.c_int32)]
+
+
+class MergeRefResult(C.Structure):
+    """oracle/pctg_shim.cc: gamref_merge_result"""
+    _fields_ = [("status", C.c_int32), ("align_ok", C.c_int32), ("align_rev", C.c_int32), ("coords_set", C.c_int32),
+                ("m_start", C.c_int32), ("m_end", C.c_int32), ("s_start", C.c_int32), ("s_end", C.c_int32)]
+
+
 class OracleResult(C.Structure):
     _fields_ = RefResult._fields_ + [
         ("n_match", C.c_uint64),
@@ -205,6 +217,33 @@ class Reference:
         self.lib.gamref_contig_free(ha)
         self.lib.gamref_contig_free(hb)
         return hits[: min(n, cap)].copy()
+
+    def align_merge_block(self, master, slave, blocks, tails=(1, 1, 1, 1)):
+        """PctgBuilder::alignMergeBlock (PctgBuilder.cc:726-844, the unmodified bodies compiled by pctg_shim.cc) on
+        one merge block.  blocks: dicts with num_reads, m_strand, s_strand (0 '+', 1 '-'), m_begin, m_end, s_begin,
+        s_end.  Returns a dict shaped like tests/merge_util.result_dict."""
+        if not hasattr(self.lib, "gamref_align_merge_block"):
+            raise RuntimeError("libgamref.so predates the PctgBuilder shim: rebuild with `make -C oracle ref`")
+        m, pm = _u8(master)
+        s_, ps = _u8(slave)
+        blk = (MergeBlockRec * len(blocks))()
+        for k, b in enumerate(blocks):
+            blk[k].num_reads = b["num_reads"]; blk[k].m_strand = b["m_strand"]; blk[k].s_strand = b["s_strand"]
+            blk[k].m_begin, blk[k].m_end, blk[k].s_begin, blk[k].s_end = b["m_begin"], b["m_end"], b["s_begin"], b["s_end"]
+        r = MergeRefResult()
+        f = self.lib.gamref_align_merge_block
+        f.restype = C.c_int
+        rc = f(pm, C.c_uint64(len(m)), ps, C.c_uint64(len(s_)), blk, C.c_uint32(len(blocks)), C.c_int(int(tails[0])),
+               C.c_int(int(tails[1])), C.c_int(int(tails[2])), C.c_int(int(tails[3])), C.byref(r))
+        if rc != 0:
+            raise ValueError("merge block without blocks")
+        d = dict(status=int(r.status))
+        if d["status"]:
+            return d
+        d.update(align_ok=int(r.align_ok), coords_set=int(r.coords_set))
+        if d["coords_set"]:
+            d.update(align_rev=int(r.align_rev), m_start=int(r.m_start), m_end=int(r.m_end), s_start=int(r.s_start), s_end=int(r.s_end))
+        return d
 
     def bench(self, a_list, b_list, band, n_threads):
         """Times full-window alignments of the pairs on n_threads host threads.

@@ -9,10 +9,13 @@ Follows, statement by statement and on plain Python structures,
 with Frame / Block / MergeBlock reduced to the fields those functions read
 (lib/include/assembly/Frame.hpp:53-60, Block.hpp:68-71, pctg/MergeDescriptor.hpp:40-69).
 
-Parity status: every alignment and every findHits call goes through a checker that IS pinned to
-the reference (oracle.restatement() / oracle.reference()); the control flow above them is
-"parity unpinned": PctgBuilder.cc cannot be compiled here (it needs Boost.Graph and sparsehash,
-SURVEY.md 8c), so this file is a careful restatement only.
+Parity status: PINNED.  Every alignment and every findHits call goes through a checker that is pinned to the
+reference (oracle.restatement() / oracle.reference()), and the control flow above them is pinned to the reference's
+own caller code: PctgBuilder.cc cannot be compiled whole (Boost.Graph, sparsehash, BamTools), but the bodies of
+the four functions above are copied out of it at build time (oracle/pctg_extract.py) and compiled unmodified
+against small stand-ins for Block / Frame / the graph (oracle/pctg_shim.cc -> oracle/_ref/libgamref.so:
+gamref_align_merge_block).  tests/test_merge_oracle.py compares this file with that build on adversarial merge
+blocks and with the golden vectors generated from it (tests/golden/merge_golden.json).
 """
 from __future__ import annotations
 

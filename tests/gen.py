@@ -235,3 +235,62 @@ def make_assembly(rng, genome_len=200_000, master_mean=60_000, slave_mean=40_000
             if blocks:
                 merge_blocks.append(dict(m=mi, s=si, blocks=blocks))
     return masters, slaves, merge_blocks
+
+
+def perturb_merge_blocks(rng, masters, slaves, merge_blocks, n_extra=12):
+    """Adversarial variants of an assembly's merge blocks for the caller-side parity tests (the control flow of
+    PctgBuilder.cc:726-844,1361-1730 beyond the happy path): random tail flags, blocks listed in reverse order,
+    shifted / empty / out-of-contig frames, wrong strand evidence on some blocks only, unrelated contig pairs and
+    pairs whose slave was damaged after the blocks were laid out.  Returns (slaves', merge_blocks')."""
+    slaves = [s.copy() for s in slaves]
+    out = []
+    for mb in merge_blocks:
+        blocks = [dict(b) for b in mb["blocks"]]
+        kind = int(rng.integers(0, 10))
+        if kind == 0 and len(blocks) > 1:
+            blocks = blocks[::-1]                                   # processed in reverse order (.cc:1677-1706)
+        elif kind == 1:
+            for b in blocks:                                        # frames that no longer match: chained starts drift
+                d = int(rng.integers(-300, 300))
+                b["m_begin"] += d; b["m_end"] += d
+        elif kind == 2 and len(blocks) > 2:
+            blocks = blocks[len(blocks) // 2:len(blocks) // 2 + 1]  # one frame in the middle: two long tails
+        elif kind == 3:
+            b = blocks[int(rng.integers(0, len(blocks)))]
+            b["m_end"] = b["m_begin"] - 1                           # empty master frame: end_a = m_at + 0 - 1
+        elif kind == 4:
+            b = blocks[-1]
+            b["s_end"] += 5000; b["m_end"] += 5000                  # frame beyond both contigs
+        elif kind == 5:
+            for b in blocks[::2]:
+                b["s_strand"] ^= 1                                  # mixed strand evidence
+        elif kind == 6:
+            s = slaves[mb["s"]]                                     # a damaged stretch inside the slave
+            lo = int(rng.integers(0, max(1, len(s) - 400)))
+            s[lo:lo + 400] = rng.integers(0, 4, min(400, len(s) - lo)).astype(np.uint8)
+        elif kind == 7:
+            s = slaves[mb["s"]]                                     # damaged slave tails (tail alignments fail)
+            s[:300] = rng.integers(0, 4, min(300, len(s))).astype(np.uint8)
+            s[-300:] = rng.integers(0, 4, min(300, len(s))).astype(np.uint8)
+        elif kind == 8 and len(blocks) > 2:
+            b = blocks[len(blocks) // 2]                            # one good frame, the slave damaged right beside it:
+            blocks = [b]                                            # the chained part passes, a tail alignment fails
+            s = slaves[mb["s"]]
+            for lo in (b["s_begin"] - 450, b["s_end"] + 50):
+                lo = max(0, min(len(s) - 1, lo))
+                hi = min(len(s), lo + 400)
+                s[lo:hi] = rng.integers(0, 4, hi - lo).astype(np.uint8)
+        tails = tuple(int(x) for x in rng.integers(0, 2, 4)) if rng.random() < 0.5 else (1, 1, 1, 1)
+        out.append(dict(m=mb["m"], s=mb["s"], blocks=blocks, tails=tails))
+    for _ in range(n_extra):                                        # unrelated pairs
+        m, s = int(rng.integers(0, len(masters))), int(rng.integers(0, len(slaves)))
+        lm, ls = len(masters[m]), len(slaves[s])
+        n = int(rng.integers(1, 4))
+        blocks = []
+        for k in range(n):
+            mb_, sb_ = int(rng.integers(0, lm // 2)), int(rng.integers(0, ls // 2))
+            ln = int(rng.integers(50, 1500))
+            blocks.append(dict(num_reads=int(rng.integers(1, 40)), m_strand=0, s_strand=int(rng.integers(0, 2)),
+                               m_begin=mb_, m_end=min(lm - 1, mb_ + ln), s_begin=sb_, s_end=min(ls - 1, sb_ + ln)))
+        out.append(dict(m=m, s=s, blocks=blocks, tails=tuple(int(x) for x in rng.integers(0, 2, 4))))
+    return slaves, out

@@ -42,3 +42,36 @@ def test_merge_stage_matches_oracle(ctx, seed, kw):
     assert stats["cells"] == ostats.cells
     # rounds are bounded by the longest chain (two orientations) plus the two tail rounds
     assert stats["rounds"] <= 2 * max(len(m["blocks"]) for m in MB) + 2
+
+
+def test_merge_stage_matches_golden_from_reference_caller(ctx):
+    """gamx_merge_align against tests/golden/merge_golden.json: vectors generated from the UNMODIFIED bodies of
+    PctgBuilder::alignMergeBlock & co. (tests/golden/make_merge_golden.py), all four outcome classes."""
+    from util import load_merge_golden
+    n = 0
+    for M, S, mbs in load_merge_golden():
+        arr, blk = to_arrays(g, M, S, mbs, ctx)
+        res, _ = ctx.merge_align(arr, blk)
+        for k, mb in enumerate(mbs):
+            assert result_dict(res[k]) == mb["expect"], (k, mb["m"], mb["s"], len(mb["blocks"]), mb["tails"])
+            n += 1
+    assert n >= 50
+
+
+@pytest.mark.parametrize("seed", [21, 22, 23])
+def test_merge_stage_matches_compiled_reference_caller(ctx, seed):
+    """The same without any restatement in between: gamx_merge_align against oracle/_ref/libgamref.so
+    (the reference's caller code compiled by oracle/pctg_shim.cc; the prebuilt library travels to the GPU box)."""
+    import oracle
+    if not oracle.reference_available():
+        pytest.skip("reference build not present")
+    ref = oracle.reference()
+    rng = np.random.default_rng(seed)
+    M, S, MB = gen.make_assembly(rng, genome_len=60_000, master_mean=12_000, slave_mean=9_000, trim_prob=0.5,
+                                 wrong_strand_prob=0.3, p_n=0.002)
+    S, MB = gen.perturb_merge_blocks(rng, M, S, MB)
+    arr, blk = to_arrays(g, M, S, MB, ctx)
+    res, _ = ctx.merge_align(arr, blk)
+    for k, mb in enumerate(MB):
+        want = ref.align_merge_block(M[mb["m"]], S[mb["s"]], mb["blocks"], mb["tails"])
+        assert result_dict(res[k]) == want, (k, mb["m"], mb["s"], len(mb["blocks"]), mb["tails"])

@@ -543,3 +543,31 @@ def test_config2_full_size_properties():
         case = dict(a=A, b=B, begin_a=0, end_a=len(A) - 1, begin_b=0, end_b=len(B) - 1, band=64, gap=-8,
                     force_start=False, force_end=False)
         assert result_to_expect(None, r[k], None, capi.MODE_ENDPOINTS) == project(oracle_expect(case), capi.MODE_ENDPOINTS), k
+
+
+def test_gpu_matches_compiled_reference_directly(ctx):
+    """No restatement in between: the CUDA path against oracle/_ref/libgamref.so (the UNMODIFIED reference aligner;
+    the prebuilt library travels to the GPU box) on fuzz cases of every clamp plus config-2 / config-3 shaped
+    pairs, all three modes."""
+    import oracle
+    if not oracle.reference_available():
+        pytest.skip("reference build not present")
+    ref = oracle.reference()
+    rng = np.random.default_rng(4242)
+    cases = []
+    while len(cases) < 240:
+        job = gen.fuzz_case(rng)
+        x = x_size_of(job)
+        if x is None or x == 0 or x > 3000:
+            continue  # (x == 0: the reference's behaviour is undefined, .cc:102-122)
+        cases.append(job)
+    for length, band in ((1000, 64), (700, 16), (2500, 256), (1500, 150)):
+        for _ in range(8):
+            a, b = gen.make_pair(rng, length, div=float(rng.choice([0.0, 0.02, 0.08])), p_n=float(rng.choice([0.0, 0.002])))
+            cases.append(dict(a=a, b=b, begin_a=0, end_a=len(a) - 1, begin_b=0, end_b=len(b) - 1, band=band, gap=-8,
+                              force_start=False, force_end=False))
+    exps = [oracle_expect(c, ref) for c in cases]
+    for mode in (capi.MODE_FULL, capi.MODE_ENDPOINTS, capi.MODE_SCORE):
+        got = run_batch(ctx, cases, mode)
+        for k in range(len(cases)):
+            assert got[k] == project(exps[k], mode), (k, mode, {a: b for a, b in cases[k].items() if a not in "ab"})

@@ -53,3 +53,37 @@ def test_merge_oracle_same_with_reference_aligner():
 
     b, _ = oracle_merge(M, S, MB, RefChecker())
     assert a == b
+
+
+# ---- the restated control flow pinned to the reference's own caller code ------------------------------------
+# (PctgBuilder::alignMergeBlock / findBestAlignment / alignBlocks / is_good, PctgBuilder.cc:726-844,1361-1730:
+#  the unmodified bodies compiled by oracle/pctg_shim.cc, or the golden vectors generated from them)
+
+def test_merge_oracle_matches_golden_from_reference_caller():
+    from util import load_merge_golden
+    n, classes = 0, set()
+    for M, S, mbs in load_merge_golden():
+        got, _ = oracle_merge(M, S, mbs)
+        for mb, r in zip(mbs, got):
+            assert r == mb["expect"], (mb["m"], mb["s"], len(mb["blocks"]), mb["tails"])
+            classes.add((r["status"], r.get("align_ok"), r.get("coords_set")))
+            n += 1
+    assert n >= 50
+    # merged, refused by the chained alignments, refused by a tail alignment, reference throws
+    assert {(0, 1, 1), (0, 0, 0), (0, 0, 1), (2, None, None)} <= classes
+
+
+@pytest.mark.skipif(not oracle.reference_available(), reason="reference build not present")
+@pytest.mark.parametrize("seed", [10, 11, 12, 13, 14, 15])
+def test_merge_oracle_pinned_to_reference_caller(seed):
+    """Adversarial merge blocks (reverse block order, shifted / empty / out-of-contig frames, mixed strand
+    evidence, damaged slaves, unrelated pairs, random tail flags): restatement == compiled reference."""
+    ref = oracle.reference()
+    rng = np.random.default_rng(seed)
+    M, S, MB = gen.make_assembly(rng, genome_len=60_000, master_mean=12_000, slave_mean=9_000, trim_prob=0.5,
+                                 wrong_strand_prob=0.3, p_n=0.002)
+    S, MB = gen.perturb_merge_blocks(rng, M, S, MB)
+    got, _ = oracle_merge(M, S, MB)
+    for mb, r in zip(MB, got):
+        want = ref.align_merge_block(M[mb["m"]], S[mb["s"]], mb["blocks"], mb["tails"])
+        assert r == want, (mb["m"], mb["s"], len(mb["blocks"]), mb["tails"])

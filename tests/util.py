@@ -29,6 +29,22 @@ def load_golden():
     return cases
 
 
+def load_merge_golden():
+    """tests/golden/merge_golden.json (made by tests/golden/make_merge_golden.py from the compiled reference
+    caller): [(masters, slaves, [merge block dicts with m, s, blocks, tails, expect])] per assembly."""
+    with open(os.path.join(HERE, "golden", "merge_golden.json")) as f:
+        g = json.load(f)
+    code = {c: i for i, c in enumerate("ATCGN")}
+    out = []
+    for k, asm in enumerate(g["assemblies"]):
+        M = [np.array([code[c] for c in m], dtype=np.uint8) for m in asm["masters"]]
+        S = [np.array([code[c] for c in s], dtype=np.uint8) for s in asm["slaves"]]
+        mbs = [dict(m=c["m"], s=c["s"], blocks=c["blocks"], tails=tuple(c["tails"]), expect=c["expect"])
+               for c in g["cases"] if c["assembly"] == k]
+        out.append((M, S, mbs))
+    return out
+
+
 def x_size_of(job):
     """banded_smith_waterman.cc:90-95 with the reference's unsigned wrap-around; None when
     the reference returns before sizing the matrix."""
