@@ -46,12 +46,17 @@ WORKLOADS = {
     "cfg3_long_band256_full": dict(pairs=4000, len_lo=10000, len_hi=50000, band=256, div=0.02, mode=2),
 }
 DEFAULT_WORKLOAD = "cfg2_1M_1kb_band64_endpoints"
-ALGO_LANE_OPS_PER_CELL = 4      # select + add + max + fused add-max in 32-bit
+# SURVEY.md 8(d), algorithmic integer lane-ops per cell: 4 in 32-bit (select + add + max + fused add-max), 2 with
+# 16x2 SIMD - the form the warp-level kernels run in since round 2 (k1s_kernel, two cells per lane-op).  Pairs whose
+# windows hold an N take the 32-bit retry kernel; the synthetic workloads have none.
+ALGO_LANE_OPS_PER_CELL_S16 = 2
+ALGO_LANE_OPS_PER_CELL_S32 = 4
 DIR_BYTES_PER_CELL = 0.25       # 2 direction bits per cell
 # dram__bytes_read.sum + dram__bytes_write.sum of the fill kernel + traceback kernel per DP cell, from the
-# `ncu --set full` capture of 100k config-2 pairs (12.9e9 cells) in profiles/r1f_k1_c18_lg8_fill_tb_100k.csv:
-# 3.63 GB written + 0.14 GB read by the fill kernel, 0.86 GB read by the traceback kernel
-NCU_DRAM_BYTES_PER_CELL = 0.36
+# `ncu --set full` capture of 100k config-2 pairs (12.9e9 cells) in profiles/r2o_k1s_c18_lg8_dirs_100k.csv
+# (3.63 GB written + 0.27 GB read by the fill kernel) and profiles/r1f_k1_c18_lg8_fill_tb_100k.csv (0.86 GB read
+# by the traceback kernel)
+NCU_DRAM_BYTES_PER_CELL = 0.37
 
 
 def env_int(name, default):
@@ -181,13 +186,23 @@ def cpu_baseline(spec, a, al, b, bl, seconds_target=12.0, threads=None):
             "seconds": sec, "score_sum": int(ssum)}
 
 
+def config_of(workload, spec, pairs_per_gpu):
+    """The `config` object of both arms (same keys and values: the reference arm times a bounded sample of it)."""
+    return {"workload": workload, "pairs_per_gpu": int(pairs_per_gpu), "band": spec["band"], "divergence": spec["div"],
+            "mode": ["score", "endpoints", "full"][spec["mode"]],
+            "l2": "inputs_larger_than_l2 (packed contigs + job/result records > 126 MB per step)",
+            "timing": "CUDA events on the launching stream per step, max over ranks"}
+
+
 def run_reference(args, spec, rank, world):
     """--impl reference: the reference's own CPU implementation on the host cores (rank 0 only)."""
     if rank != 0:
         return
+    # the same seeded workload as rank 0 of the GPU arm; the CPU arm times a bounded prefix of it per step
+    from gam_ngs_b200.dist import shard_seed
     sub = dict(spec)
-    sub["pairs"] = min(spec["pairs"], 200_000)
-    a, al, b, bl = make_workload(sub, 1000)
+    sub["pairs"] = min(spec["pairs"], 250_000)  # (a prefix: the generator emits pairs in blocks of 32768, same stream)
+    a, al, b, bl = make_workload(sub, shard_seed(1000, 0))
     vals = []
     for _ in range(args.warmup):
         cpu_baseline(spec, a, al, b, bl, seconds_target=1.0)
@@ -204,10 +219,92 @@ def run_reference(args, spec, rank, world):
     line = {"impl": "reference", "metric": "alignment_gcups", "value": v, "unit": "GCUPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / max(1, args.steps) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": args.workload, "band": spec["band"], "note": "bounded sample per step"},
+            "config": config_of(args.workload, spec, spec["pairs"]),
             "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def timed_plan(ctx, jobs, steps=3, warmup=1):
+    """Kernel-only rate of a job batch whose contigs are resident: (GCUPS, ms per step, cells, launches per step)."""
+    plan = ctx.plan(jobs)
+    for _ in range(warmup):
+        plan.run(); plan.sync()
+    ms = 0.0
+    for _ in range(steps):
+        plan.run(); plan.sync()
+        ms += plan.last_ms
+    cells, launches = plan.cells, plan.kernel_launches
+    plan.close()
+    return cells * steps / (ms * 1e-3) / 1e9, ms / steps, int(cells), int(launches)
+
+
+def other_configs(ctx, g, capi, jobs_cfg2, int_peak32, int_peak16):
+    """Short kernel-only measurements of the BASELINE.json configs the headline is not quoted on (bounded samples,
+    a few steps each): config 2 score-only on the resident batch, a config 3 sample (10-50 kb, band 256, full
+    traceback + edit strings), config 5 sweep points (mixed lengths; band and divergence), and the config 1 merge
+    stage (gamx_merge_align on a 2.9 Mb synthetic assembly pair)."""
+    import gen
+    from merge_util import to_arrays
+    out = []
+
+    def frac(gcups, band, mode):
+        geo = capi.band_geometry(band) or (0, 64)
+        s16 = geo[1] <= 32 and os.environ.get("GAMX_NO_S16") is None
+        peak = int_peak16 if s16 else int_peak32
+        return gcups * 1e9 * (ALGO_LANE_OPS_PER_CELL_S16 if s16 else ALGO_LANE_OPS_PER_CELL_S32) / peak if peak else None
+
+    def entry(name, jobs, band, mode, note, steps=3):
+        v, ms, cells, launches = timed_plan(ctx, jobs, steps=steps)
+        out.append({"workload": name, "value": v, "unit": "GCUPS", "ms_per_step": ms, "cells": cells, "pairs": int(len(jobs)),
+                    "band": band, "mode": ["score", "endpoints", "full"][mode], "steps": steps, "launches_per_step": launches,
+                    "roofline_frac_int_alu": frac(v, band, mode), "note": note})
+
+    # config 2, score only: the batch that is resident already
+    j = jobs_cfg2.copy(); j["mode"] = capi.MODE_SCORE
+    entry("cfg2_1M_1kb_band64_score", j, 64, 0, "same contigs and jobs as the headline, score only")
+    # config 3 sample
+    rng = np.random.default_rng(3)
+    n3 = 1500
+    a, al, b, bl = gen.bulk_pairs(rng, n3, 0, div=0.02, len_lo=10000, len_hi=50000)
+    ctx.clear_contigs()
+    ctx.add_contigs(np.concatenate([a, b]), np.concatenate([al, bl]))
+    j = g.make_jobs(n3)
+    j["a_id"] = np.arange(n3); j["b_id"] = np.arange(n3, 2 * n3)
+    j["end_a"] = al - 1; j["end_b"] = bl - 1; j["band"] = 256; j["mode"] = capi.MODE_FULL
+    entry("cfg3_long_band256_full", j, 256, 2, f"{n3}-pair sample of the 100000 pairs of config 3 (10-50 kb, full traceback + edit strings)", steps=2)
+    # config 5 sweep points: mixed lengths (log-uniform 256..16384), band sweep at 2 %, divergence sweep at band 64
+    rng = np.random.default_rng(5)
+    n5 = 40000
+    lengths = np.exp(rng.uniform(np.log(256), np.log(16384), n5)).astype(np.int64)
+    for div in (0.02, 0.0, 0.10):
+        a, al, b, bl = gen.bulk_pairs(rng, n5, 0, div=div, lengths=lengths)
+        ctx.clear_contigs()
+        ctx.add_contigs(np.concatenate([a, b]), np.concatenate([al, bl]))
+        for band in ((16, 64, 256, 1024) if div == 0.02 else (64,)):
+            j = g.make_jobs(n5)
+            j["a_id"] = np.arange(n5); j["b_id"] = np.arange(n5, 2 * n5)
+            j["end_a"] = al - 1; j["end_b"] = bl - 1; j["band"] = band; j["mode"] = capi.MODE_ENDPOINTS
+            entry(f"cfg5_mixed_lengths_band{band}_div{int(div * 100)}", j, band, 1,
+                  f"{n5}-pair sample of config 5 (lengths log-uniform 256..16384), divergence {div:.2f}, endpoints")
+    # config 1: the merge stage on a 2.9 Mb assembly pair
+    rng = np.random.default_rng(1)
+    M, S, MB = gen.make_assembly(rng, genome_len=2_900_000, master_mean=60_000, slave_mean=40_000, div=0.01,
+                                 trim_prob=0.5, wrong_strand_prob=0.1)
+    mbs, blk = to_arrays(g, M, S, MB, ctx)
+    ctx.merge_align(mbs[:4], blk)
+    best, stats = None, None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        res, stats = ctx.merge_align(mbs, blk)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    out.append({"workload": "cfg1_merge_alignment_stage_2.9Mb", "value": stats["cells"] / best / 1e9, "unit": "GCUPS",
+                "ms_per_step": best * 1e3, "cells": int(stats["cells"]), "merge_blocks": len(MB), "rounds": int(stats["rounds"]),
+                "alignments": int(stats["alignments"]), "hits_calls": int(stats["hits_calls"]), "band": 150, "mode": "endpoints",
+                "align_ok": int(res["align_ok"].sum()),
+                "note": "gamx_merge_align end to end (host wall clock): chained block alignments, orientation retry, findHits-seeded tails"})
+    return out
 
 
 def main():
@@ -220,6 +317,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=0, help="override pairs per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -358,19 +456,27 @@ def main():
                "pipeline": "chunks of 65536 jobs over 4 buffer slots/streams; upload pieces of 128 MB on their own stream"}
     # ---- roofline --------------------------------------------------------------------------------
     geo = capi.band_geometry(spec["band"]) or (0, 0)
-    kernel_name = f"{'k1' if geo[1] <= 32 else 'k2'}_kernel<{geo[0]},{geo[1]},{'true' if spec['mode'] else 'false'}>" + \
+    s16 = geo[1] <= 32 and os.environ.get("GAMX_NO_S16") is None   # warp-level launches run the 16x2 pair kernel
+    kernel_name = f"{('k1s' if s16 else 'k1') if geo[1] <= 32 else 'k2'}_kernel<{geo[0]},{geo[1]},{'true' if spec['mode'] else 'false'}>" + \
                   (" (+ tb_kernel)" if spec["mode"] else "")
     peaks, peak_src = load_peaks()
     kernel_s = dev_s / args.steps
     cells_rank = float(cells)
-    ach_int = cells_rank / (dev_ms * 1e-3 / args.steps) * ALGO_LANE_OPS_PER_CELL / 1e12
-    roofline = {"bound": "int_alu", "achieved": ach_int, "peak": int_peak / 1e12, "unit": "Tlaneop/s",
-                "frac": ach_int / (int_peak / 1e12) if int_peak else None,
+    ops_per_cell = ALGO_LANE_OPS_PER_CELL_S16 if s16 else ALGO_LANE_OPS_PER_CELL_S32
+    int_peak_used = (ctx.measure_int_peak(2) if s16 else int_peak) or int_peak   # VIADDMNMX.S16x2 / VIADDMNMX issue rate
+    cells_per_s = cells_rank / (dev_ms * 1e-3 / args.steps)
+    ach_int = cells_per_s * ops_per_cell / 1e12
+    roofline = {"bound": "int_alu", "achieved": ach_int, "peak": int_peak_used / 1e12, "unit": "Tlaneop/s",
+                "frac": ach_int / (int_peak_used / 1e12) if int_peak_used else None,
                 "traffic": NCU_DRAM_BYTES_PER_CELL * cells_rank if spec["mode"] else None,
                 "traffic_note": "DRAM bytes per step = ncu dram bytes per cell (profiles/, 100k-pair --set full capture) x cells",
                 "kernel": kernel_name,
-                "algorithmic": f"{ALGO_LANE_OPS_PER_CELL} int32 lane-ops per cell (SURVEY 8d) x {int(cells_rank)} cells per launch",
-                "peak_source": "VIADDMNMX issue rate measured live by gamx_measure_int_peak (register-only kernel)"}
+                "algorithmic": f"{ops_per_cell} integer lane-ops per cell ({'16x2 SIMD' if s16 else '32-bit'} form, SURVEY 8d) x "
+                               f"{int(cells_rank)} cells per step",
+                # the round-1 figure for comparison: the same cell rate counted as 4 lane-ops per cell (32-bit form)
+                "frac_int32_form": cells_per_s * ALGO_LANE_OPS_PER_CELL_S32 / int_peak if int_peak else None,
+                "peak_source": "issue rate of the DPX instruction the kernel uses, measured live by gamx_measure_int_peak "
+                               "(register-only kernel)"}
     seq_bytes = total_bases * 3 / 8
     algo_bytes = (cells_rank * DIR_BYTES_PER_CELL if spec["mode"] else 0.0) + seq_bytes + n * (96 + 104)
     ach_hbm = algo_bytes / (dev_ms * 1e-3 / args.steps) / 1e9
@@ -385,16 +491,18 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         cpu = cpu_baseline(spec, a, al, b, bl)
 
+    # ---- the other BASELINE.json configs, briefly (single-GPU runs only; the headline above is unaffected) -----
+    others = None
+    if world == 1 and not args.no_other_configs and args.workload == DEFAULT_WORKLOAD:
+        others = other_configs(ctx, g, capi, jobs, int_peak, int_peak_used)
+
     if rank == 0:
         line = {"metric": "alignment_gcups", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": kernel_s * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-                "config": {"workload": args.workload, "pairs_per_gpu": n, "band": spec["band"],
-                           "divergence": spec["div"], "mode": ["score", "endpoints", "full"][spec["mode"]],
-                           "l2": "inputs_larger_than_l2 (packed contigs + job/result records > 126 MB per step)",
-                           "timing": "CUDA events on the launching stream per step, max over ranks"},
+                "config": config_of(args.workload, spec, n),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-                "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
+                "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu, "other_configs": others,
                 "wall_ms_per_step": wall_s / args.steps * 1e3, "jobs_ok": ok, "parity_checked": checked,
                 "gen_seconds": t_gen}
         print(json.dumps(line), flush=True)
