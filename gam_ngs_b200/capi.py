@@ -87,7 +87,8 @@ assert RESULT_DTYPE.itemsize == C.sizeof(GamxResult), (RESULT_DTYPE.itemsize, C.
 EXPORTS = [
     "gamx_abi_version", "gamx_create", "gamx_destroy", "gamx_device_count", "gamx_last_error",
     "gamx_add_contig", "gamx_add_contig_ascii", "gamx_add_contigs", "gamx_add_contigs_async", "gamx_contig_length", "gamx_clear_contigs",
-    "gamx_ops_capacity", "gamx_set_pipeline_chunk", "gamx_align_batch", "gamx_unpack_ops", "gamx_cigar_rle",
+    "gamx_add_fasta", "gamx_contig_name",
+    "gamx_ops_capacity", "gamx_set_pipeline_chunk", "gamx_align_batch", "gamx_align_batch_cigar", "gamx_unpack_ops", "gamx_cigar_rle",
     "gamx_plan_create", "gamx_plan_run", "gamx_plan_sync", "gamx_plan_fetch", "gamx_plan_last_ms",
     "gamx_plan_cells", "gamx_plan_kernel_launches", "gamx_plan_destroy", "gamx_measure_int_peak",
     "gamx_shard_by_cost", "gamx_find_hits_batch", "gamx_merge_align", "gamx_band_geometry",
@@ -139,6 +140,12 @@ def load_library(build_if_missing: bool = True):
     L.gamx_set_pipeline_chunk.restype = C.c_int
     L.gamx_align_batch.argtypes = [vp, vp, u64, vp, vp, u64]
     L.gamx_align_batch.restype = C.c_int
+    L.gamx_align_batch_cigar.argtypes = [vp, vp, u64, vp, vp, vp, u64, vp]
+    L.gamx_align_batch_cigar.restype = C.c_int
+    L.gamx_add_fasta.argtypes = [vp, C.c_char_p, vp]
+    L.gamx_add_fasta.restype = C.c_int64
+    L.gamx_contig_name.argtypes = [vp, C.c_uint32]
+    L.gamx_contig_name.restype = C.c_char_p
     L.gamx_unpack_ops.argtypes = [vp, u64, u64, vp]
     L.gamx_unpack_ops.restype = None
     L.gamx_cigar_rle.argtypes = [vp, u64, u64, vp, u64]
@@ -295,6 +302,9 @@ class Context:
     def clear_contigs(self):
         self._check(self.lib.gamx_clear_contigs(self._h))
 
+    def contig_length(self, cid: int) -> int:
+        return int(self.lib.gamx_contig_length(self._h, cid))
+
     def ops_capacity(self, jobs: np.ndarray) -> int:
         jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
         return int(self.lib.gamx_ops_capacity(self._h, jobs.ctypes.data, len(jobs)))
@@ -324,6 +334,34 @@ class Context:
             rc = self.lib.gamx_align_batch(self._h, jobs.ctypes.data, n, results.ctypes.data, ops.ctypes.data, cap)
         self._check(rc)
         return results, ops
+
+    def align_batch_cigar(self, jobs: np.ndarray):
+        """FULL-mode batch with the edit strings returned as run-length CIGARs built on the device:
+        (results, run_offsets[n + 1], runs) with runs[k] = length << 2 | op."""
+        jobs = np.ascontiguousarray(jobs, dtype=JOB_DTYPE)
+        n = len(jobs)
+        results = np.empty(n, dtype=RESULT_DTYPE)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        need = np.zeros(1, dtype=np.uint64)
+        runs = np.zeros(max(1024, 64 * n), dtype=np.uint32)
+        rc = self.lib.gamx_align_batch_cigar(self._h, jobs.ctypes.data, n, results.ctypes.data, offs.ctypes.data,
+                                             runs.ctypes.data, len(runs), need.ctypes.data)
+        if rc == ERR_OPS_CAPACITY:
+            runs = np.zeros(int(need[0]), dtype=np.uint32)
+            rc = self.lib.gamx_align_batch_cigar(self._h, jobs.ctypes.data, n, results.ctypes.data, offs.ctypes.data,
+                                                 runs.ctypes.data, len(runs), need.ctypes.data)
+        self._check(rc)
+        return results, offs, runs[: int(offs[n])]
+
+    def add_fasta(self, path: str):
+        """Loads every record of a FASTA file; returns (first contig id, number of contigs)."""
+        n = np.zeros(1, dtype=np.uint64)
+        first = int(self.lib.gamx_add_fasta(self._h, path.encode(), n.ctypes.data))
+        self._check(first if first < 0 else 0)
+        return first, int(n[0])
+
+    def contig_name(self, cid: int) -> str:
+        return self.lib.gamx_contig_name(self._h, cid).decode()
 
     def find_hits_batch(self, jobs: np.ndarray) -> np.ndarray:
         """ABlast::findHits for a batch of (a window, b window) jobs (HITS_JOB_DTYPE)."""

@@ -192,16 +192,31 @@ class BandedSmithWaterman {
   template <class SeqT>
   MyAlignment find_alignment(const SeqT& a, size_type begin_a, size_type end_a, const SeqT& b, size_type begin_b,
                              size_type end_b, bool force_start = false, bool force_end = false) const {
-    gamx_ctx* ctx = nullptr;
-    if (gamx_create(&ctx, nullptr, 1) != GAMX_OK)
-      throw std::runtime_error("gamx: no usable CUDA device (this aligner has no CPU fallback)");
-    struct Guard { gamx_ctx* c; ~Guard() { gamx_destroy(c); } } guard{ctx};
+    if (_band_size > 0xffffffffull || _gap_score < INT32_MIN || _gap_score > INT32_MAX)
+      throw std::invalid_argument("gamx: band or gap score outside the 32-bit range of gamx_job");
+    // One context per calling thread, created on first use and reused: the legacy call pattern is N host threads
+    // each issuing synchronous calls (ThreadedBuildPctg.cc:159-169) - a call costs two small uploads and one
+    // batch, not the creation of streams and buffers.  The context holds just the two sequences of the call.
+    gamx_ctx* ctx = call_context();
+    if (gamx_clear_contigs(ctx) != GAMX_OK) throw std::runtime_error(gamx_last_error(ctx));
     AlignBatch batch(ctx);
     const uint32_t ia = batch.add_contig(a), ib = batch.add_contig(b);
     batch.add(ia, false, 0, UINT64_MAX, begin_a, end_a, ib, false, 0, UINT64_MAX, begin_b, end_b,
               (uint32_t)_band_size, (int32_t)_gap_score, force_start, force_end, GAMX_MODE_FULL);
     batch.run();
     return batch.alignment(0);
+  }
+
+  // the calling thread's context (first visible GPU), destroyed when the thread ends
+  static gamx_ctx* call_context() {
+    struct Holder {
+      gamx_ctx* c = nullptr;
+      ~Holder() { if (c) gamx_destroy(c); }
+    };
+    static thread_local Holder h;
+    if (!h.c && gamx_create(&h.c, nullptr, 1) != GAMX_OK)
+      throw std::runtime_error("gamx: no usable CUDA device (this aligner has no CPU fallback)");
+    return h.c;
   }
 
  private:

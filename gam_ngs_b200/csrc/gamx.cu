@@ -23,11 +23,13 @@
 // if CUDA is not usable every entry point fails.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -295,6 +297,91 @@ tbw_kernel(const DevJob* __restrict__ jobs, int n_jobs, const uint32_t* __restri
   }
 }
 
+// ---- run-length CIGAR on the device ------------------------------------------------------------------
+// The traceback kernels leave a job's edit string packed 2 bits per op in the device ops buffer (op g of the
+// buffer at bits [2*(g&15), +2) of word g>>4; a job's ops are [ops_start, ops_start + n_ops)).  One warp per job
+// turns it into (length << 2 | op) runs: a lane looks at one 16-op word per round, run starts are the positions
+// whose op differs from the one before (XOR with the word shifted by one op, the previous word supplying the
+// carry-in).  Pass 1 counts the runs, an exclusive scan places the jobs, pass 2 writes the runs.
+struct CigarWord {
+  uint32_t starts;  // bit 2p set: a run starts at op p of this word
+  uint32_t word;
+};
+__device__ __forceinline__ CigarWord cigar_word(const uint32_t* __restrict__ ops, uint64_t w, uint64_t first, uint64_t end) {
+  // word w holds buffer positions [16w, 16w + 16); the job's ops are [first, end)
+  CigarWord c;
+  c.word = ops[w];
+  const uint32_t prev = w ? ops[w - 1] >> 30 : 0u;                       // last op of the previous word
+  const uint32_t x = c.word ^ ((c.word << 2) | prev);
+  uint32_t m = (x | (x >> 1)) & 0x55555555u;
+  const uint64_t base = w << 4;
+  if (first >= base) m |= 1u << (2 * (uint32_t)(first - base));         // the first op always starts a run
+  const uint32_t lo = first > base ? (uint32_t)(first - base) : 0u, hi = end - base < 16 ? (uint32_t)(end - base) : 16u;
+  uint32_t valid = hi >= 16 ? 0xffffffffu : ((1u << (2 * hi)) - 1u);
+  valid &= ~((1u << (2 * lo)) - 1u);
+  c.starts = m & valid & 0x55555555u;
+  return c;
+}
+
+constexpr int kCigarThreads = 128;
+__global__ void __launch_bounds__(kCigarThreads)
+cigar_count_kernel(const DevResult* __restrict__ results, const uint8_t* __restrict__ want, int n, const uint32_t* __restrict__ ops,
+                   unsigned long long* __restrict__ counts) {
+  const int j = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31);
+  if (j >= n) return;
+  const DevResult R = results[j];
+  uint32_t cnt = 0;
+  if (want[j] && R.status == kStatusOk && R.n_ops) {
+    const uint64_t first = R.ops_start, end = first + R.n_ops;
+    for (uint64_t w = (first >> 4) + lane; w <= ((end - 1) >> 4); w += 32) cnt += __popc(cigar_word(ops, w, first, end).starts);
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  if (lane == 0) counts[j] = cnt;
+}
+
+// offsets: the exclusive scan of the counts (n + 1 entries).  starts: scratch of total-runs words.
+__global__ void __launch_bounds__(kCigarThreads)
+cigar_emit_kernel(const DevResult* __restrict__ results, const uint8_t* __restrict__ want, int n, const uint32_t* __restrict__ ops,
+                  const unsigned long long* __restrict__ offsets, uint32_t* __restrict__ starts, uint32_t* __restrict__ runs) {
+  const int j = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = (int)(threadIdx.x & 31);
+  if (j >= n) return;
+  const DevResult R = results[j];
+  if (!(want[j] && R.status == kStatusOk && R.n_ops)) return;
+  const uint64_t first = R.ops_start, end = first + R.n_ops;
+  const unsigned long long out0 = offsets[j], n_runs = offsets[j + 1] - out0;
+  unsigned long long done = 0;  // runs of the words before this round (warp-uniform)
+  const uint64_t w_last = (end - 1) >> 4;
+  for (uint64_t w0 = first >> 4; w0 <= w_last; w0 += 32) {
+    const uint64_t w = w0 + lane;
+    CigarWord c;
+    c.starts = 0; c.word = 0;
+    if (w <= w_last) c = cigar_word(ops, w, first, end);
+    const uint32_t mine = __popc(c.starts);
+    uint32_t incl = mine;  // inclusive prefix over the lanes
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    unsigned long long k = out0 + done + (incl - mine);
+    uint32_t m = c.starts;
+    while (m) {
+      const int p = (__ffs((int)m) - 1) >> 1;
+      m &= m - 1;
+      starts[k++] = (uint32_t)(((w << 4) + p - first) << 2) | ((c.word >> (2 * p)) & 3u);  // (position in the job, op)
+    }
+    done += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  __threadfence_block();
+  __syncwarp();
+  for (unsigned long long r = lane; r < n_runs; r += 32) {
+    const uint32_t s0 = starts[out0 + r];
+    const uint32_t nxt = r + 1 < n_runs ? (starts[out0 + r + 1] >> 2) : R.n_ops;
+    runs[out0 + r] = ((nxt - (s0 >> 2)) << 2) | (s0 & 3u);
+  }
+}
+
 __global__ void __launch_bounds__(64)
 generic_kernel(const GenJob* __restrict__ jobs, int n_jobs, SeqStore store, int64_t* __restrict__ rows,
                uint32_t* __restrict__ dirs, uint32_t* __restrict__ ops, DevResult* __restrict__ results) {
@@ -543,6 +630,8 @@ struct Slot {
   DevBuf jobs, gjobs, results, dirs, ops, grows, gdirs, counters, retry;  // retry: the k1s launches' retry lists
   PinBuf h_jobs, h_gjobs, h_results, h_ops;
   uint64_t generation = 0;  // bumped by every plan_upload into this slot: a plan whose stamp is older has lost its buffers
+  DevBuf cig_want, cig_counts, cig_offsets, cig_starts, cig_runs, cig_temp;  // device CIGAR stage (gamx_align_batch_cigar)
+  PinBuf h_cig_offsets, h_cig_runs;
 };
 
 struct Device {
@@ -622,6 +711,7 @@ struct gamx_ctx {
   uint64_t pipeline_chunk = 65536;  // gamx_set_pipeline_chunk
   uint64_t piece_bytes = 128u << 20;  // raw bytes per upload piece; 128 MB measured 2-3 ms per 2.1 GB faster than 64 MB (GAMX_UPLOAD_PIECE_BYTES)
   bool up_unsettled = false;      // an asynchronous upload may still read the caller's `codes` (settle_uploads)
+  std::vector<std::string> names; // names of the contigs that came from gamx_add_fasta (by contig id)
   std::mutex mu;
   std::string err;
 };
@@ -1196,9 +1286,10 @@ void gamx_destroy(gamx_ctx* ctx) {
     PinBuf* pbs[] = {&d.h_stage, &d.h_stage2};
     for (PinBuf* b : pbs) if (b->p) cudaFreeHost(b->p);
     for (Slot& sl : d.s) {
-      DevBuf* sd[] = {&sl.jobs, &sl.gjobs, &sl.results, &sl.dirs, &sl.ops, &sl.grows, &sl.gdirs, &sl.counters, &sl.retry};
+      DevBuf* sd[] = {&sl.jobs, &sl.gjobs, &sl.results, &sl.dirs, &sl.ops, &sl.grows, &sl.gdirs, &sl.counters, &sl.retry,
+                      &sl.cig_want, &sl.cig_counts, &sl.cig_offsets, &sl.cig_starts, &sl.cig_runs, &sl.cig_temp};
       for (DevBuf* b : sd) if (b->p) cudaFree(b->p);
-      PinBuf* sp[] = {&sl.h_jobs, &sl.h_gjobs, &sl.h_results, &sl.h_ops};
+      PinBuf* sp[] = {&sl.h_jobs, &sl.h_gjobs, &sl.h_results, &sl.h_ops, &sl.h_cig_offsets, &sl.h_cig_runs};
       for (PinBuf* b : sp) if (b->p) cudaFreeHost(b->p);
       cudaEventDestroy(sl.ev0);
       cudaEventDestroy(sl.ev1);
@@ -1237,14 +1328,109 @@ int64_t gamx_add_contig(gamx_ctx* ctx, const uint8_t* codes, uint64_t len) {
   return index_add(ctx, len);
 }
 
+// character -> base code as a table (nucleotide.code.hpp:47-75 via ascii_to_code): the conversion loops below
+// are plain byte gathers the compiler vectorises, run over slices on the host threads
+static const uint8_t* ascii_table() {
+  static const std::array<uint8_t, 256> t = [] {
+    std::array<uint8_t, 256> a{};
+    for (int c = 0; c < 256; c++) a[c] = ascii_to_code((char)c);
+    return a;
+  }();
+  return t.data();
+}
+
 int64_t gamx_add_contig_ascii(gamx_ctx* ctx, const char* seq, uint64_t len) {
   if (!ctx || (!seq && len)) return GAMX_ERR_INVALID;
   std::vector<uint8_t> codes(len);
-  for (uint64_t i = 0; i < len; i++) codes[i] = ascii_to_code(seq[i]);
+  const uint8_t* tab = ascii_table();
+  uint8_t* out = codes.data();
+  parallel_for(len, [&](uint64_t b, uint64_t e) {
+    for (uint64_t i = b; i < e; i++) out[i] = tab[(uint8_t)seq[i]];
+  });
   return gamx_add_contig(ctx, codes.data(), len);
 }
 
 static int64_t add_contigs_impl(gamx_ctx* ctx, const uint8_t* codes, const uint64_t* lengths, uint64_t n, bool wait);
+
+// FASTA -> contig store (the load-time half of SURVEY 8 row f4).  Record structure as the reference reads it
+// (io_contig.code.hpp:540-565): a '>' starts a header that runs to the end of the line, the name is its first
+// word; every following character except '\n', ' ' and '>' is a base (so a stray '\r' or tab becomes N, like
+// there), converted by the Nucleotide(char) table (nucleotide.code.hpp:47-75).
+int64_t gamx_add_fasta(gamx_ctx* ctx, const char* path, uint64_t* n_contigs) {
+  if (!ctx || !path) return GAMX_ERR_INVALID;
+  if (n_contigs) *n_contigs = 0;
+  std::vector<char> buf;
+  {
+    FILE* f = fopen(path, "rb");
+    if (!f) { std::lock_guard<std::mutex> lk(ctx->mu); ctx->err = std::string("cannot open ") + path; return GAMX_ERR_INVALID; }
+    fseek(f, 0, SEEK_END);
+    const long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    buf.resize(sz > 0 ? (size_t)sz : 0);
+    const size_t got = buf.empty() ? 0 : fread(buf.data(), 1, buf.size(), f);
+    fclose(f);
+    if (got != buf.size()) { std::lock_guard<std::mutex> lk(ctx->mu); ctx->err = std::string("short read of ") + path; return GAMX_ERR_INVALID; }
+  }
+  // records: [header start, sequence start, sequence end)
+  struct Rec { size_t hdr, seq, end; };
+  std::vector<Rec> recs;
+  const size_t N = buf.size();
+  for (size_t i = 0; i < N;) {
+    if (buf[i] != '>') { i++; continue; }  // (anything before the first '>' is skipped)
+    Rec r; r.hdr = i + 1;
+    size_t j = i + 1;
+    while (j < N && buf[j] != '\n') j++;
+    r.seq = j < N ? j + 1 : N;
+    const char* nxt = r.seq < N ? (const char*)memchr(buf.data() + r.seq, '>', N - r.seq) : nullptr;
+    r.end = nxt ? (size_t)(nxt - buf.data()) : N;
+    recs.push_back(r);
+    i = r.end;
+  }
+  if (recs.empty()) { std::lock_guard<std::mutex> lk(ctx->mu); ctx->err = std::string("no FASTA record in ") + path; return GAMX_ERR_INVALID; }
+  const size_t n = recs.size();
+  std::vector<uint64_t> lengths(n), offs(n + 1, 0);
+  parallel_for(n, [&](uint64_t b, uint64_t e) {
+    for (uint64_t k = b; k < e; k++) {
+      uint64_t len = 0;
+      for (size_t i = recs[k].seq; i < recs[k].end; i++) len += buf[i] != '\n' && buf[i] != ' ';
+      lengths[k] = len;
+    }
+  });
+  for (size_t k = 0; k < n; k++) offs[k + 1] = offs[k] + lengths[k];
+  std::vector<uint8_t> codes(offs[n] ? offs[n] : 1);
+  const uint8_t* tab = ascii_table();
+  parallel_for(n, [&](uint64_t b, uint64_t e) {
+    for (uint64_t k = b; k < e; k++) {
+      uint8_t* out = codes.data() + offs[k];
+      for (size_t i = recs[k].seq; i < recs[k].end; i++) {
+        const char c = buf[i];
+        if (c != '\n' && c != ' ') *out++ = tab[(uint8_t)c];
+      }
+    }
+  });
+  const int64_t first = add_contigs_impl(ctx, codes.data(), lengths.data(), n, true);
+  if (first < 0) return first;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->names.size() < (size_t)first + n) ctx->names.resize((size_t)first + n);
+    for (size_t k = 0; k < n; k++) {
+      size_t e = recs[k].hdr;
+      const size_t lim = recs[k].seq ? recs[k].seq - 1 : 0;  // (the newline that ends the header)
+      while (e < lim && buf[e] != ' ' && buf[e] != '\t' && buf[e] != '\r' && buf[e] != '\n') e++;
+      ctx->names[(size_t)first + k].assign(buf.data() + recs[k].hdr, e - recs[k].hdr);
+    }
+  }
+  if (n_contigs) *n_contigs = n;
+  return first;
+}
+
+const char* gamx_contig_name(const gamx_ctx* ctx, uint32_t id) {
+  if (!ctx) return "";
+  static thread_local std::string copy;
+  std::lock_guard<std::mutex> lk(const_cast<gamx_ctx*>(ctx)->mu);
+  copy = id < ctx->names.size() ? ctx->names[id] : std::string();
+  return copy.c_str();
+}
 
 int64_t gamx_add_contigs(gamx_ctx* ctx, const uint8_t* codes, const uint64_t* lengths, uint64_t n) {
   return add_contigs_impl(ctx, codes, lengths, n, true);
@@ -1326,6 +1512,7 @@ int gamx_clear_contigs(gamx_ctx* ctx) {
   ctx->store.n_bases = 0;
   ctx->pending.clear();
   ctx->pending_first = 0;
+  ctx->names.clear();
   return GAMX_OK;
 }
 
@@ -2114,6 +2301,114 @@ static int align_batch_locked(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, g
     fprintf(stderr, "[gamx] align_batch n=%llu: build %.1f ms, upload %.1f ms, run+sync %.1f ms, fetch %.1f ms, free %.1f ms\n",
             (unsigned long long)n, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, now()));
   return rc;
+}
+
+// FULL-mode batch whose edit strings are turned into run-length CIGARs ON THE DEVICE (cigar_count_kernel, an
+// exclusive scan, cigar_emit_kernel): the packed ops never leave the device, only the runs are copied back.
+int gamx_align_batch_cigar(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_result* results, uint64_t* run_offsets,
+                           uint32_t* runs, uint64_t runs_cap, uint64_t* runs_needed) {
+  if (!ctx || (!jobs && n) || (!results && n) || !run_offsets) return GAMX_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (runs_needed) *runs_needed = 0;
+  gamx_plan* pl = nullptr;
+  int rc = plan_build_checked(ctx, jobs, n, &pl);
+  if (!rc) rc = plan_upload(pl);
+  if (!rc) rc = plan_run_locked(pl);
+  // per device: count, scan, emit on the plan's stream (behind the traceback kernels)
+  std::vector<std::vector<uint64_t>> dev_off(pl ? pl->dps.size() : 0);
+  uint64_t total_all = 0;
+  if (!rc) {
+    // which result records are FULL-mode jobs
+    std::vector<std::vector<uint8_t>> want(pl->dps.size());
+    for (size_t di = 0; di < pl->dps.size(); di++) want[di].assign(pl->dps[di].n_jobs, 0);
+    for (uint64_t i = 0; i < n; i++)
+      if (pl->job_dev[i] >= 0 && pl->modes[i] == GAMX_MODE_FULL) want[pl->job_dev[i]][pl->job_res[i]] = 1;
+    for (size_t di = 0; di < pl->dps.size() && !rc; di++) {
+      DevPlan& dp = pl->dps[di];
+      if (dp.n_jobs == 0) continue;
+      Device& d = ctx->devs[dp.dev];
+      Slot& sl = d.s[pl->slot];
+      const int nj = (int)dp.n_jobs;
+      CU(cudaSetDevice(d.id));
+      if ((rc = ensure_dev(ctx, sl.cig_want, nj))) break;
+      if ((rc = ensure_dev(ctx, sl.cig_counts, sizeof(unsigned long long) * ((size_t)nj + 1)))) break;
+      if ((rc = ensure_dev(ctx, sl.cig_offsets, sizeof(unsigned long long) * ((size_t)nj + 1)))) break;
+      if ((rc = ensure_pin(ctx, sl.h_cig_offsets, sizeof(unsigned long long) * ((size_t)nj + 1)))) break;
+      CU(cudaMemcpyAsync(sl.cig_want.p, want[di].data(), nj, cudaMemcpyHostToDevice, sl.stream));
+      CU(cudaMemsetAsync((unsigned long long*)sl.cig_counts.p + nj, 0, sizeof(unsigned long long), sl.stream));
+      const unsigned blocks = (unsigned)(((size_t)nj * 32 + kCigarThreads - 1) / kCigarThreads);
+      cigar_count_kernel<<<blocks, kCigarThreads, 0, sl.stream>>>((const DevResult*)sl.results.p, (const uint8_t*)sl.cig_want.p, nj,
+                                                                  (const uint32_t*)sl.ops.p, (unsigned long long*)sl.cig_counts.p);
+      CU(cudaGetLastError());
+      size_t temp_bytes = 0;
+      CU(cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, (const unsigned long long*)sl.cig_counts.p, (unsigned long long*)sl.cig_offsets.p,
+                                       nj + 1, sl.stream));
+      if ((rc = ensure_dev(ctx, sl.cig_temp, temp_bytes + 16))) break;
+      CU(cub::DeviceScan::ExclusiveSum(sl.cig_temp.p, temp_bytes, (const unsigned long long*)sl.cig_counts.p,
+                                       (unsigned long long*)sl.cig_offsets.p, nj + 1, sl.stream));
+      CU(cudaMemcpyAsync(sl.h_cig_offsets.p, sl.cig_offsets.p, sizeof(unsigned long long) * ((size_t)nj + 1), cudaMemcpyDeviceToHost, sl.stream));
+      CU(cudaStreamSynchronize(sl.stream));  // (the host copy below reads want[di]; the run total sizes the buffers)
+      const unsigned long long* ho = (const unsigned long long*)sl.h_cig_offsets.p;
+      dev_off[di].assign(ho, ho + nj + 1);
+      const uint64_t total = ho[nj];
+      total_all += total;
+      if (total) {
+        if ((rc = ensure_dev(ctx, sl.cig_starts, total * 4))) break;
+        if ((rc = ensure_dev(ctx, sl.cig_runs, total * 4))) break;
+        if ((rc = ensure_pin(ctx, sl.h_cig_runs, total * 4))) break;
+        cigar_emit_kernel<<<blocks, kCigarThreads, 0, sl.stream>>>((const DevResult*)sl.results.p, (const uint8_t*)sl.cig_want.p, nj,
+                                                                   (const uint32_t*)sl.ops.p, (const unsigned long long*)sl.cig_offsets.p,
+                                                                   (uint32_t*)sl.cig_starts.p, (uint32_t*)sl.cig_runs.p);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(sl.h_cig_runs.p, sl.cig_runs.p, total * 4, cudaMemcpyDeviceToHost, sl.stream));
+        pl->launches += 2;
+      }
+    }
+  }
+  if (!rc) rc = plan_sync_locked(pl);
+  if (runs_needed) *runs_needed = total_all;
+  if (!rc && total_all > runs_cap) {
+    ctx->err = "runs buffer too small: need " + std::to_string(total_all) + " runs";
+    rc = GAMX_ERR_OPS_CAPACITY;
+  }
+  if (!rc && total_all && !runs) rc = GAMX_ERR_INVALID;
+  if (!rc) {
+    // results without the packed ops (they stay on the device)
+    for (DevPlan& dp : pl->dps) {
+      if (dp.n_jobs == 0) continue;
+      Device& d = ctx->devs[dp.dev];
+      Slot& sl = d.s[pl->slot];
+      CU(cudaSetDevice(d.id));
+      CU(cudaMemcpyAsync(sl.h_results.p, sl.results.p, (size_t)dp.n_jobs * sizeof(DevResult), cudaMemcpyDeviceToHost, sl.stream));
+      CU(cudaStreamSynchronize(sl.stream));
+    }
+    // the caller's order: job i's runs are runs[run_offsets[i] .. run_offsets[i + 1])
+    uint64_t at = 0;
+    for (uint64_t i = 0; i < n; i++) {
+      run_offsets[i] = at;
+      if (pl->job_dev[i] >= 0) { const auto& o = dev_off[pl->job_dev[i]]; at += o[pl->job_res[i] + 1] - o[pl->job_res[i]]; }
+    }
+    run_offsets[n] = at;
+    parallel_for(n, [&](uint64_t b, uint64_t e) {
+      for (uint64_t i = b; i < e; i++) {
+        const Prepared& P = pl->preps[i];
+        const DevResult* dr = nullptr;
+        if (pl->job_dev[i] >= 0) {
+          const DevPlan& dp = pl->dps[pl->job_dev[i]];
+          const Slot& sl = ctx->devs[dp.dev].s[pl->slot];
+          dr = (const DevResult*)sl.h_results.p + pl->job_res[i];
+          const auto& o = dev_off[pl->job_dev[i]];
+          const uint64_t cnt = o[pl->job_res[i] + 1] - o[pl->job_res[i]];
+          if (cnt) memcpy(runs + run_offsets[i], (const uint32_t*)sl.h_cig_runs.p + o[pl->job_res[i]], cnt * 4);
+        }
+        finalize_result(P, dr, pl->modes[i], &results[i]);
+        results[i].ops_offset = 0;  // (no packed ops are returned by this entry point)
+      }
+    });
+  }
+  delete pl;
+  const int rc_up = settle_uploads(ctx);
+  return rc ? rc : rc_up;
 }
 
 void gamx_unpack_ops(const uint8_t* ops_buf, uint64_t ops_offset, uint64_t n_ops, uint8_t* out) {

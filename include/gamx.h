@@ -145,6 +145,13 @@ GAMX_API int gamx_abi_version(void);
 GAMX_API int64_t gamx_add_contig(gamx_ctx* ctx, const uint8_t* codes, uint64_t len);
 /* Same, from FASTA characters (ACGTacgt, everything else -> N). */
 GAMX_API int64_t gamx_add_contig_ascii(gamx_ctx* ctx, const char* seq, uint64_t len);
+/* Loads every record of a FASTA file as a contig (the record structure and the character table of the
+ * reference's reader: io_contig.code.hpp:540-565 readNextSequence, nucleotide.code.hpp:47-75).  Returns the id
+ * of the first contig (the records get consecutive ids in file order) or a negative error; *n_contigs (may be
+ * NULL) receives the record count.  gamx_contig_name returns the first word of a record's header (a per-thread
+ * copy, valid until the thread's next call; "" for contigs that were not loaded from FASTA). */
+GAMX_API int64_t gamx_add_fasta(gamx_ctx* ctx, const char* path, uint64_t* n_contigs);
+GAMX_API const char* gamx_contig_name(const gamx_ctx* ctx, uint32_t id);
 /* Bulk form: n contigs whose codes are concatenated in `codes` (lengths[n] bases each).  The raw
  * bytes are copied to every device (directly when `codes` is pinned host memory, through pinned
  * staging otherwise) and packed there by a kernel; the call returns when `codes` may be reused.
@@ -170,6 +177,15 @@ GAMX_API uint64_t gamx_ops_capacity(const gamx_ctx* ctx, const gamx_job* jobs, u
  * [2*((ops_offset+k)%4), +2) of byte (ops_offset+k)/4; ops_cap is its capacity in ops. */
 GAMX_API int gamx_align_batch(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_result* results,
                      uint8_t* ops_buf, uint64_t ops_cap);
+
+/* The same batch with the edit strings returned as run-length CIGARs that are built ON THE DEVICE (the packed
+ * ops never cross PCIe): job i's runs are runs[run_offsets[i] .. run_offsets[i+1]) (run_offsets has n + 1
+ * entries), each run = length << 2 | op (GAMX_OP_*), in edit-string order - what gamx_cigar_rle produces from the
+ * packed ops of gamx_align_batch.  Jobs that are not in FULL mode, or return no alignment, have no runs.
+ * *runs_needed (may be NULL) receives the total; GAMX_ERR_OPS_CAPACITY when runs_cap is too small (results and
+ * runs are then undefined; call again with a buffer of *runs_needed entries). */
+GAMX_API int gamx_align_batch_cigar(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_result* results,
+                                    uint64_t* run_offsets, uint32_t* runs, uint64_t runs_cap, uint64_t* runs_needed);
 
 /* Expands n_ops packed ops starting at ops_offset to one byte per op (GAMX_OP_*), the layout
  * of the reference's std::vector<AlignmentAlphabet>. */

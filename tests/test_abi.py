@@ -69,7 +69,7 @@ def _build_dropin(tmp_path):
     exe = str(tmp_path / "test_dropin")
     libdir = os.path.join(ROOT, "gam_ngs_b200")
     subprocess.run(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_dropin.cc"),
-                    "-L" + libdir, "-lgamx", "-Wl,-rpath," + libdir], check=True)
+                    "-L" + libdir, "-lgamx", "-pthread", "-Wl,-rpath," + libdir], check=True)
     return exe
 
 

@@ -571,3 +571,84 @@ def test_gpu_matches_compiled_reference_directly(ctx):
         got = run_batch(ctx, cases, mode)
         for k in range(len(cases)):
             assert got[k] == project(exps[k], mode), (k, mode, {a: b for a, b in cases[k].items() if a not in "ab"})
+
+
+def test_device_cigar_matches_host_rle(ctx):
+    """gamx_align_batch_cigar: the run-length CIGARs built on the device (cigar_count_kernel / scan /
+    cigar_emit_kernel) equal gamx_cigar_rle of the packed edit strings of gamx_align_batch and the runs of the
+    oracle's edit strings; jobs of other modes and empty alignments have no runs."""
+    rng = np.random.default_rng(515)
+    cases = []
+    for length, band in ((60, 7), (333, 16), (1000, 64), (1500, 150), (2500, 256), (5000, 512)):
+        for _ in range(6):
+            a, b = gen.make_pair(rng, length + int(rng.integers(0, 50)), div=float(rng.choice([0.0, 0.02, 0.1])), p_n=0.002)
+            cases.append(dict(a=a, b=b, begin_a=0, end_a=len(a) - 1, begin_b=0, end_b=len(b) - 1, band=band, gap=-8,
+                              force_start=False, force_end=False))
+    for _ in range(40):
+        cases.append(gen.fuzz_case(rng))
+    ctx.clear_contigs()
+    jobs = g.make_jobs(len(cases))
+    for k, c in enumerate(cases):
+        jobs[k]["a_id"] = ctx.add_contig(c["a"]); jobs[k]["b_id"] = ctx.add_contig(c["b"])
+        for f in ("begin_a", "end_a", "begin_b", "end_b", "band", "gap"):
+            jobs[k][f] = c[f]
+        jobs[k]["force_start"], jobs[k]["force_end"] = int(c["force_start"]), int(c["force_end"])
+        jobs[k]["mode"] = capi.MODE_FULL if k % 7 != 3 else capi.MODE_ENDPOINTS
+    res, ops = ctx.align_batch(jobs)
+    res2, offs, runs = ctx.align_batch_cigar(jobs)
+    n_runs = 0
+    for k, c in enumerate(cases):
+        assert res2[k]["status"] == res[k]["status"] and res2[k]["score"] == res[k]["score"] and res2[k]["n_ops"] == res[k]["n_ops"]
+        mine = [(int(r & 3), int(r >> 2)) for r in runs[int(offs[k]):int(offs[k + 1])]]
+        if res[k]["status"] != 0 or jobs[k]["mode"] != capi.MODE_FULL:
+            assert mine == []
+            continue
+        assert mine == ctx.cigar_rle(ops, int(res[k]["ops_offset"]), int(res[k]["n_ops"])), k
+        exp = oracle_expect(c) if x_size_of(c) != 0 else {"status": 3}
+        if exp["status"] == 0:
+            want, prev = [], None
+            for op in exp["ops"]:
+                if prev == op:
+                    want[-1][1] += 1
+                else:
+                    want.append([op, 1]); prev = op
+            assert mine == [tuple(w) for w in want], k
+        assert sum(l for _, l in mine) == int(res[k]["n_ops"])
+        n_runs += len(mine)
+    assert n_runs > 500
+
+
+def test_fasta_loader(ctx, tmp_path):
+    """gamx_add_fasta reads records like the reference's reader (io_contig.code.hpp:540-565: everything but
+    newline, blank and '>' is a base; nucleotide.code.hpp:47-75: unknown characters are N)."""
+    rng = np.random.default_rng(99)
+    seqs = [gen.random_seq(rng, n, p_n=0.01) for n in (1, 70, 1000, 4097)]
+    txt = ""
+    for k, s_ in enumerate(seqs):
+        letters = "".join("ATCGN"[c] for c in s_)
+        if k == 1:
+            letters = letters.lower()
+        if k == 2:
+            letters = letters[:500] + "RYK" + letters[500:]     # IUPAC codes -> N
+        txt += f">ctg{k} some description\n"
+        txt += "\n".join(letters[i:i + 60] for i in range(0, len(letters), 60)) + "\n"
+    path = tmp_path / "t.fa"
+    path.write_text(txt)
+    ctx.clear_contigs()
+    first, n = ctx.add_fasta(str(path))
+    assert n == 4 and [ctx.contig_name(first + k) for k in range(4)] == ["ctg0", "ctg1", "ctg2", "ctg3"]
+    want = [s_.copy() for s_ in seqs]
+    want[2] = np.concatenate([seqs[2][:500], np.array([4, 4, 4], dtype=np.uint8), seqs[2][500:]])
+    assert [ctx.contig_length(first + k) for k in range(4)] == [len(w) for w in want]
+    # the stored bases: align every contig against an uploaded copy of what it should be
+    jobs = g.make_jobs(4)
+    for k in range(4):
+        jobs[k]["a_id"] = first + k
+        jobs[k]["b_id"] = ctx.add_contig(want[k])
+        jobs[k]["end_a"] = jobs[k]["end_b"] = len(want[k]) - 1
+        jobs[k]["band"] = 8; jobs[k]["mode"] = capi.MODE_ENDPOINTS
+    res, _ = ctx.align_batch(jobs)
+    for k in range(4):
+        nn = int((want[k] == 4).sum())
+        assert res[k]["status"] == 0 and res[k]["n_ops"] == len(want[k]) and res[k]["n_match"] == len(want[k]), k
+        assert res[k]["score"] == 5 * len(want[k])  # (N against N scores 5 like a match, .cc:86)
