@@ -185,6 +185,19 @@ def band_geometry(band: int):
     return c.value, lg.value
 
 
+def shard_by_cost(cost, n_shards: int) -> np.ndarray:
+    """The cost-balanced split the library applies over a context's devices (longest processing time first),
+    for callers that run one process per GPU: shard index per item.  Pure host code."""
+    cost = np.ascontiguousarray(cost, dtype=np.uint64)
+    out = np.zeros(len(cost), dtype=np.int32)
+    L = load_library()
+    L.gamx_shard_by_cost.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+    L.gamx_shard_by_cost.restype = C.c_int
+    if L.gamx_shard_by_cost(cost.ctypes.data, len(cost), int(n_shards), out.ctypes.data) != 0:
+        raise GamxError("gamx_shard_by_cost failed")
+    return out
+
+
 def make_hits_jobs(n: int) -> np.ndarray:
     jobs = np.zeros(n, dtype=HITS_JOB_DTYPE)
     jobs["a_len"] = U64_MAX

@@ -29,15 +29,38 @@ def main():
     M, S, MB = gen.make_assembly(rng, genome_len=genome, master_mean=60_000, slave_mean=40_000, div=0.01,
                                  trim_prob=0.5, wrong_strand_prob=0.1)
     t_gen = time.perf_counter() - t0
-    ctx = g.Context(devices=[0])
+    # one process per GPU (torchrun): the merge blocks shard independently - rank r takes the blocks the
+    # cost-balanced split (gamx_shard_by_cost, cost = bases of the two contigs) assigns to shard r; no collective
+    # on the data path, the timing is the slowest rank's (barrier + max over ranks)
+    from gam_ngs_b200.dist import Ranks
+    from gam_ngs_b200 import capi
+    ranks = Ranks()
+    all_mb = MB
+    if ranks.world > 1:
+        cost = np.array([sum(b["m_end"] - b["m_begin"] + 1 for b in m["blocks"]) for m in all_mb], dtype=np.uint64)
+        shard = capi.shard_by_cost(cost, ranks.world)
+        MB = [m for m, s_ in zip(all_mb, shard) if s_ == ranks.rank]
+    ctx = g.Context(devices=[ranks.local_rank])
     mbs, blk = to_arrays(g, M, S, MB, ctx)
     ctx.merge_align(mbs[:4], blk)  # warm-up (contig upload, kernel load)
     times = []
     for _ in range(3):
+        ranks.barrier()
         t0 = time.perf_counter()
         res, stats = ctx.merge_align(mbs, blk)
-        times.append(time.perf_counter() - t0)
+        times.append(ranks.max(time.perf_counter() - t0))
     gpu_s = min(times)
+    if ranks.world > 1:
+        tot = {k: int(ranks.sum(float(v))) for k, v in stats.items() if k != "rounds"}
+        tot["rounds"] = int(ranks.max(float(stats["rounds"])))
+        ok_all, exc_all = int(ranks.sum(float(res["align_ok"].sum()))), int(ranks.sum(float((res["status"] != 0).sum())))
+        if ranks.rank == 0:
+            print(json.dumps({"config": "cfg4_merge_alignment_stage_sharded", "genome_bp": genome, "n_gpus": ranks.world,
+                              "merge_blocks": len(all_mb), "merge_blocks_rank0": len(MB), "scaling": "strong",
+                              "gpu": {"seconds": gpu_s, "gcups": tot["cells"] / gpu_s / 1e9, **tot},
+                              "align_ok": ok_all, "exceptions": exc_all, "gen_seconds": t_gen}), flush=True)
+        ranks.close()
+        return
     # CPU arms on a bounded sample of merge blocks (same call pattern, reference aligner)
     class RefChecker:
         def __init__(self):
