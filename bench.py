@@ -225,7 +225,7 @@ def run_reference(args, spec, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def timed_plan(ctx, jobs, steps=3, warmup=1):
+def timed_plan(ctx, jobs, steps=3, warmup=2):
     """Kernel-only rate of a job batch whose contigs are resident: (GCUPS, ms per step, cells, launches per step)."""
     plan = ctx.plan(jobs)
     for _ in range(warmup):
@@ -487,14 +487,15 @@ def main():
                             "the traceback kernel; traffic = ncu dram bytes per cell (profiles/, 100k-pair capture) x cells; "
                             "not the binding resource"}
 
-    cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(spec, a, al, b, bl)
-
     # ---- the other BASELINE.json configs, briefly (single-GPU runs only; the headline above is unaffected) -----
+    # (before the CPU baseline: ten seconds of host-only work let the GPU drop its clocks)
     others = None
     if world == 1 and not args.no_other_configs and args.workload == DEFAULT_WORKLOAD:
         others = other_configs(ctx, g, capi, jobs, int_peak, int_peak_used)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(spec, a, al, b, bl)
 
     if rank == 0:
         line = {"metric": "alignment_gcups", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,

@@ -217,7 +217,9 @@ def make_jobs(n: int) -> np.ndarray:
 
 
 class Plan:
-    """A validated, sharded batch whose descriptors are resident on the devices."""
+    """A validated, sharded batch whose descriptors are resident on the devices.  The plan lives in the context's
+    buffers: any later batch, merge round or plan on the same context takes them over, after which run() / fetch()
+    raise (GAMX_ERR_INVALID) instead of touching another batch's data.  Keep one live plan per context."""
 
     def __init__(self, ctx: "Context", jobs: np.ndarray):
         self.ctx = ctx

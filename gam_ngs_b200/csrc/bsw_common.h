@@ -2,7 +2,7 @@
 //
 // Everything here is host+device: the kernel bodies are written against a small "warp
 // policy" so the very same code can be executed by the CPU lane simulator in tests/sim
-// (test infrastructure) and by the sm_100a kernels in bsw_kernels.cu (the product).
+// (test infrastructure) and by the sm_100a kernels in gamx.cu (the product).
 //
 // Semantics follow the reference's BandedSmithWaterman::find_alignment
 // (/root/reference/lib/src/alignment/banded_smith_waterman.cc:69-323); the exact
@@ -136,7 +136,7 @@ GAMX_HD int is_match_op(uint32_t a, uint32_t b) {
   return (a == b) || a == (uint32_t)kCodeN || b == (uint32_t)kCodeN;
 }
 
-// ---- job as the kernels see it (prepared by the host in gamx_capi.cu) --------------------
+// ---- job as the kernels see it (prepared by the host in gamx.cu) --------------------
 struct DevJob {
   SeqView a;        // view position 0 of a
   SeqView b;        // b.origin already points at view position begin_b (DP row 0)

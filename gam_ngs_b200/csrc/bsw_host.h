@@ -1,4 +1,4 @@
-// Host-side job preparation shared by the C-ABI implementation (gamx_capi.cu) and the CPU
+// Host-side job preparation shared by the C-ABI implementation (gamx.cu) and the CPU
 // lane simulator (tests/sim/warp_sim.cc): 2-bit packing, the guards and sizes of
 // banded_smith_waterman.cc:90-97, classification fast/generic, and the conversion of a
 // device result into the fields of MyAlignment + its reductions (my_alignment.cc:167-296).

@@ -627,6 +627,10 @@ struct Slot {
   // previous wave drain (no idle tail at a wave boundary); ev_ready = inputs of the run are on the device
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_ready = nullptr;
+  // the generic kernel (one thread per job: tens of milliseconds for a kilobase job) runs on a stream of its own
+  // beside the other groups of the run; ev_gen = its jobs are done
+  cudaStream_t gen_stream = nullptr;
+  cudaEvent_t ev_gen = nullptr;
   DevBuf jobs, gjobs, results, dirs, ops, grows, gdirs, counters, retry;  // retry: the k1s launches' retry lists
   PinBuf h_jobs, h_gjobs, h_results, h_ops;
   uint64_t generation = 0;  // bumped by every plan_upload into this slot: a plan whose stamp is older has lost its buffers
@@ -1249,6 +1253,8 @@ int gamx_create(gamx_ctx** out, const int* device_ids, int n_devices) {
       ok = cudaStreamCreateWithFlags(&d.s[k].stream, cudaStreamNonBlocking) == cudaSuccess &&
            cudaStreamCreateWithFlags(&d.s[k].tb_stream, cudaStreamNonBlocking) == cudaSuccess &&
            cudaStreamCreateWithFlags(&d.s[k].stream2, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaStreamCreateWithFlags(&d.s[k].gen_stream, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&d.s[k].ev_gen, cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreateWithFlags(&d.s[k].ev_ready, cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreateWithFlags(&d.s[k].ev_fill[0], cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreateWithFlags(&d.s[k].ev_fill[1], cudaEventDisableTiming) == cudaSuccess &&
@@ -1295,6 +1301,8 @@ void gamx_destroy(gamx_ctx* ctx) {
       cudaEventDestroy(sl.ev1);
       for (int h = 0; h < 2; h++) { cudaEventDestroy(sl.ev_fill[h]); cudaEventDestroy(sl.ev_tb[h]); }
       cudaEventDestroy(sl.ev_ready);
+      cudaEventDestroy(sl.ev_gen);
+      cudaStreamDestroy(sl.gen_stream);
       cudaStreamDestroy(sl.tb_stream);
       cudaStreamDestroy(sl.stream2);
       cudaStreamDestroy(sl.stream);
@@ -1954,14 +1962,19 @@ static int plan_run_locked(gamx_plan* pl) {
     uint32_t launch = 0, wave = 0;
     uint64_t retry_off = 0;  // next free entry of sl.retry
     bool half_used[2] = {false, false};
+    bool gen_used = false;
     for (size_t gi = 0; gi < dp.groups.size(); gi++) {
       const Group& g = dp.groups[gi];
       DevResult* res = (DevResult*)sl.results.p + g.res_off;
       if (!g.c) {
         SeqStore st{(const uint32_t*)d.packed.p, (const uint32_t*)d.nmask.p};
-        generic_kernel<<<g.grid, 64, 0, sl.stream>>>((const GenJob*)sl.gjobs.p + g.job_off, (int)g.job_idx.size(), st,
-                                                     (int64_t*)sl.grows.p, (uint32_t*)sl.gdirs.p, (uint32_t*)sl.ops.p, res);
+        // (on its own stream, beside the other groups: a stray job of this class must not hold up the batch)
+        CU(cudaStreamWaitEvent(sl.gen_stream, sl.ev_ready, 0));
+        generic_kernel<<<g.grid, 64, 0, sl.gen_stream>>>((const GenJob*)sl.gjobs.p + g.job_off, (int)g.job_idx.size(), st,
+                                                         (int64_t*)sl.grows.p, (uint32_t*)sl.gdirs.p, (uint32_t*)sl.ops.p, res);
         CU(cudaGetLastError());
+        CU(cudaEventRecord(sl.ev_gen, sl.gen_stream));
+        gen_used = true;
         pl->launches++; launch++;
         continue;
       }
@@ -2010,6 +2023,7 @@ static int plan_run_locked(gamx_plan* pl) {
     }
     for (int h = 0; h < 2; h++)
       if (half_used[h]) CU(cudaStreamWaitEvent(sl.stream, sl.ev_tb[h], 0));
+    if (gen_used) CU(cudaStreamWaitEvent(sl.stream, sl.ev_gen, 0));
     CU(cudaEventRecord(sl.ev1, sl.stream));
   }
   pl->ran = true;

@@ -12,7 +12,7 @@
  *       lib/src/pctg/PctgBuilder.cc:1544-1607, 1669, 1698.
  *
  * Plain pointers and sizes only; no C++ or torch types cross this boundary.  The C++
- * drop-in classes (gam_ngs_b200/cpp/banded_smith_waterman.hpp) and the Python binding
+ * drop-in classes (gam_ngs_b200/cpp/gamx_dropin.hpp) and the Python binding
  * (gam_ngs_b200/capi.py) are thin layers over these entry points.  INTEGRATION.md shows
  * the reference-side change a maintainer would make.
  *
@@ -159,10 +159,12 @@ GAMX_API const char* gamx_contig_name(const gamx_ctx* ctx, uint32_t id);
 GAMX_API int64_t gamx_add_contigs(gamx_ctx* ctx, const uint8_t* codes, const uint64_t* lengths, uint64_t n);
 /* Same, but only enqueues the copies and the pack kernel on the devices' streams and returns: the
  * upload then overlaps the host-side planning of the next gamx_align_batch, which is stream-ordered
- * behind it.  The copy proceeds in pieces of ~64 MB that are enqueued as the batches need them, so a
+ * behind it.  The copy proceeds in pieces of ~128 MB that are enqueued as the batches need them, so a
  * pipelined gamx_align_batch starts computing on the first contigs while later ones still cross PCIe.
- * `codes` must be PINNED host memory and must stay valid and unchanged until that batch (or any
- * other synchronising call of this context) has returned. */
+ * `codes` must be PINNED host memory and must stay valid and unchanged until the next gamx_align_batch,
+ * gamx_align_batch_cigar or gamx_plan_create call on this context has returned: those calls finish the upload
+ * before they return on every path - errors, empty batches and batches that never refer to the last contigs
+ * included (gamx_add_contigs*, gamx_clear_contigs and gamx_destroy do so too). */
 GAMX_API int64_t gamx_add_contigs_async(gamx_ctx* ctx, const uint8_t* codes, const uint64_t* lengths, uint64_t n);
 GAMX_API uint64_t gamx_contig_length(const gamx_ctx* ctx, uint32_t id);
 GAMX_API int gamx_clear_contigs(gamx_ctx* ctx);
@@ -172,7 +174,8 @@ GAMX_API int gamx_clear_contigs(gamx_ctx* ctx);
 /* Upper bound on the number of ops the batch can emit in FULL mode (0 for other modes). */
 GAMX_API uint64_t gamx_ops_capacity(const gamx_ctx* ctx, const gamx_job* jobs, uint64_t n);
 
-/* Aligns a batch.  results[n] is always filled.  ops_buf (may be NULL when no job is in FULL
+/* Aligns a batch.  On GAMX_OK every results[i] is filled; on a negative return the records are undefined
+ * (on GAMX_ERR_INVALID and on errors of the pipelined path they are left untouched).  ops_buf (may be NULL when no job is in FULL
  * mode) receives the edit strings packed 2 bits per op, op k of a job at bits
  * [2*((ops_offset+k)%4), +2) of byte (ops_offset+k)/4; ops_cap is its capacity in ops. */
 GAMX_API int gamx_align_batch(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_result* results,
@@ -208,7 +211,11 @@ GAMX_API int gamx_set_pipeline_chunk(gamx_ctx* ctx, uint64_t jobs_per_chunk);
 
 typedef struct gamx_plan gamx_plan;
 /* Validates, sorts, shards and uploads a batch once; gamx_plan_run() then only launches the
- * kernels (inputs already resident in HBM) and gamx_plan_fetch() copies the results back. */
+ * kernels (inputs already resident in HBM) and gamx_plan_fetch() copies the results back.
+ * A plan owns no device memory of its own: its descriptors, results and scratch live in the context's
+ * buffers, and the next gamx_align_batch*, gamx_merge_align or gamx_plan_create on the context takes them
+ * over.  gamx_plan_run / gamx_plan_fetch on a plan that has lost its buffers return GAMX_ERR_INVALID (they
+ * never run on, or return, another batch's data): keep one live plan per context. */
 GAMX_API int gamx_plan_create(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan** out);
 GAMX_API int gamx_plan_run(gamx_plan* plan);    /* asynchronous; enqueues on each device's stream */
 GAMX_API int gamx_plan_sync(gamx_plan* plan);   /* waits for all devices */

@@ -12,7 +12,7 @@
  * (SURVEY.md section 4), so this restatement is pinned by executing the
  * unmodified reference itself (oracle/_ref/libgamref.so, built by
  * oracle/Makefile from /root/reference) on seeded randomized and edge-case
- * inputs (tests/test_oracle_vs_reference.py) and by the committed fixtures in
+ * inputs (tests/test_oracle.py) and by the committed fixtures in
  * tests/golden/ that were generated from that reference build
  * (tests/golden/make_golden.py).
  *

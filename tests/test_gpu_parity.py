@@ -652,3 +652,58 @@ def test_fasta_loader(ctx, tmp_path):
         nn = int((want[k] == 4).sum())
         assert res[k]["status"] == 0 and res[k]["n_ops"] == len(want[k]) and res[k]["n_match"] == len(want[k]), k
         assert res[k]["score"] == 5 * len(want[k])  # (N against N scores 5 like a match, .cc:86)
+
+
+def test_plan_invalidated_by_a_later_batch_and_async_upload_contract(ctx):
+    """(1) A plan whose slot buffers were taken over by a later plan or batch refuses to run / fetch instead of
+    returning another batch's results.  (2) gamx_add_contigs_async: the caller's buffer may be reused as soon as
+    the next batch call returns - also when that batch is small, single-plan and touches only the first contigs."""
+    import torch
+    rng = np.random.default_rng(31)
+    cases = []
+    for _ in range(6):
+        a, b = gen.make_pair(rng, 400, div=0.02)
+        cases.append(dict(a=a, b=b, begin_a=0, end_a=len(a) - 1, begin_b=0, end_b=len(b) - 1, band=32, gap=-8,
+                          force_start=False, force_end=False))
+    ctx.clear_contigs()
+    jobs = g.make_jobs(len(cases))
+    for k, c in enumerate(cases):
+        jobs[k]["a_id"] = ctx.add_contig(c["a"]); jobs[k]["b_id"] = ctx.add_contig(c["b"])
+        jobs[k]["end_a"], jobs[k]["end_b"], jobs[k]["band"], jobs[k]["mode"] = len(c["a"]) - 1, len(c["b"]) - 1, 32, capi.MODE_ENDPOINTS
+    p1 = ctx.plan(jobs[:3])
+    p2 = ctx.plan(jobs[3:])          # takes the slot over
+    with pytest.raises(g.GamxError):
+        p1.run()
+    with pytest.raises(g.GamxError):
+        p1.fetch()
+    p2.run(); p2.sync()
+    r2, _ = p2.fetch()
+    want = [project(oracle_expect(c), capi.MODE_ENDPOINTS) for c in cases[3:]]
+    assert [result_to_expect(ctx, r2[k], None, capi.MODE_ENDPOINTS) for k in range(3)] == want
+    ctx.align_batch(jobs)            # a batch invalidates the plan as well
+    with pytest.raises(g.GamxError):
+        p2.run()
+    p1.close(); p2.close()
+
+    # (2) many contigs (several upload pieces with a small piece size are not needed: the contract is about
+    # pieces that no job of the batch refers to), a batch that touches only the first pair, then the buffer dies
+    n = 3000
+    a, al, b, bl = gen.bulk_pairs(rng, n, 700)
+    host = torch.empty(len(a) + len(b), dtype=torch.uint8, pin_memory=True)
+    host.numpy()[:len(a)] = a; host.numpy()[len(a):] = b
+    lengths = np.concatenate([al, bl])
+    ctx.clear_contigs()
+    first = ctx.add_contigs(host.data_ptr(), lengths, async_upload=True)
+    j = g.make_jobs(1)
+    j["a_id"], j["b_id"], j["end_a"], j["end_b"], j["band"], j["mode"] = first, first + n, al[0] - 1, bl[0] - 1, 64, capi.MODE_SCORE
+    ctx.align_batch(j)
+    host.numpy()[:] = 4              # the caller reuses its buffer: everything must have been copied by now
+    jj = g.make_jobs(n)
+    jj["a_id"] = first + np.arange(n); jj["b_id"] = first + n + np.arange(n)
+    jj["end_a"] = al - 1; jj["end_b"] = bl - 1; jj["band"] = 64; jj["mode"] = capi.MODE_SCORE
+    res, _ = ctx.align_batch(jj)
+    ao = np.concatenate([[0], np.cumsum(al)]).astype(np.int64); bo = np.concatenate([[0], np.cumsum(bl)]).astype(np.int64)
+    for k in (0, 1, n // 2, n - 2, n - 1):
+        c = dict(a=a[ao[k]:ao[k + 1]], b=b[bo[k]:bo[k + 1]], begin_a=0, end_a=int(al[k]) - 1, begin_b=0, end_b=int(bl[k]) - 1,
+                 band=64, gap=-8, force_start=False, force_end=False)
+        assert int(res[k]["score"]) == oracle_expect(c)["score"], k
