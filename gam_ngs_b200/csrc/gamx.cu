@@ -128,8 +128,24 @@ __device__ uint32_t g_dir_sink[kMaxC * 32];
 // kernel (k1_kernel<.., RETRY>, launched right behind this one) computes them - same results, same direction
 // regions.  (The 32-bit body used to be called from here; as a second kernel it costs this one neither
 // registers nor instruction cache.)
+// Resident blocks per SM asked of the compiler for the pair kernels: one fewer than the 32-bit kernels' table
+// (three for the direction-storing kernels of wide stripes, i.e. up to 168 registers) - the half-word step loop has
+// no issue slots to spare, so what counts is that a warp never waits for its selector loads, which takes
+// registers; two such warps per scheduler already saturate the ALU pipe (profiles/r2j_probe_occ_scale.txt).
+// Measured on one box, full builds, this table against the 32-bit one (profiles/r2u_blocks_sweep.txt): band 64
+// endpoints +4 %, band 150 +10 %, band 100 +7 %, bands 16 / 32 +3..6 %, band 256 unchanged; score-only kernels of
+// wide stripes were 3 % slower with three blocks and keep four.
+#ifndef GAMX_K1S_BLOCKS_WIDE_DIRS
+#define GAMX_K1S_BLOCKS_WIDE_DIRS 3
+#endif
+#ifndef GAMX_K1S_BLOCKS_DELTA
+#define GAMX_K1S_BLOCKS_DELTA 1
+#endif
+__host__ __device__ constexpr int k1s_min_blocks(int c, bool dirs) {
+  return c >= 14 ? (dirs ? GAMX_K1S_BLOCKS_WIDE_DIRS : GAMX_K1_MIN_BLOCKS(c)) : GAMX_K1_MIN_BLOCKS(c) - GAMX_K1S_BLOCKS_DELTA;
+}
 template <int C, int LG, bool DIRS>
-__global__ void __launch_bounds__(warps_per_block(LG) * 32, GAMX_K1_MIN_BLOCKS(C) * 4 / warps_per_block(LG))
+__global__ void __launch_bounds__(warps_per_block(LG) * 32, k1s_min_blocks(C, DIRS) * 4 / warps_per_block(LG))
 k1s_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counters, int* __restrict__ retry_list, SeqStore store,
            uint32_t* __restrict__ dirs, uint64_t stride, DevResult* __restrict__ results) {
   constexpr int G = 32 / LG;  // pairs per warp
@@ -2550,6 +2566,8 @@ int gamx_merge_align(gamx_ctx* ctx, const gamx_merge_block* mbs, uint64_t n, con
   std::vector<MergeState> st(n);
   std::vector<uint32_t> n_aln(n, 0), n_hits(n, 0);
   const uint32_t band = GAMX_DEFAULT_BAND;
+  static const bool speculate = getenv("GAMX_NO_SPECULATION") == nullptr;  // (experiments: the strictly sequential retry)
+  constexpr uint64_t kSpeculateMaxChains = 1024;
   // ---- INIT (alignMergeBlock .cc:741-744, findBestAlignment .cc:1380-1408) ----
   for (uint64_t i = 0; i < n; i++) {
     MergeState& m = st[i];
@@ -2579,6 +2597,7 @@ int gamx_merge_align(gamx_ctx* ctx, const gamx_merge_block* mbs, uint64_t n, con
     if (m.con_prob >= 0.5) start_chain(m, false, s_start, s_end);
     else if (m.con_prob < 0.5) start_chain(m, true, s_start, s_end);
     else m.phase = MergeState::kDone;  // NaN: neither branch runs -> bad alignment
+    if (speculate && m.phase == MergeState::kChain) start_shadow(m);
   }
   std::vector<gamx_job> jobs;
   std::vector<gamx_hits_job> hjobs;
@@ -2604,22 +2623,34 @@ int gamx_merge_align(gamx_ctx* ctx, const gamx_merge_block* mbs, uint64_t n, con
   // ---- rounds ----
   for (;;) {
     jobs.clear(); hjobs.clear();
+    // speculative jobs ride along only in rounds that leave the device mostly idle anyway (the rounds of a big
+    // graph start with thousands of chains: there the extra work would cost time, and the long chains that
+    // decide the number of rounds are still running when the crowd has finished)
+    uint64_t n_chain = 0;
+    for (uint64_t i = 0; i < n; i++) n_chain += st[i].phase == MergeState::kChain;
+    const bool spec_round = speculate && n_chain <= kSpeculateMaxChains;
     for (uint64_t i = 0; i < n; i++) {
       MergeState& m = st[i];
       const uint32_t mid = m.mb->m_id, sid = m.mb->s_id;
       if (m.phase == MergeState::kChain) {
-        // alignBlocks: the k-th chained window (.cc:1657-1669)
-        const gamx_block& b = block_at(m, m.k);
-        const int32_t mlen = frame_len(b.m_begin, b.m_end), slen = frame_len(b.s_begin, b.s_end);
-        if (m.k > 0) {
-          const gamx_block& p = block_at(m, m.k - 1);
-          const int32_t mgap = p.m_begin <= b.m_begin ? (b.m_begin - p.m_end - 1) : (p.m_begin - b.m_end - 1);
-          const int32_t sgap = p.s_begin <= b.s_begin ? (b.s_begin - p.s_end - 1) : (p.s_begin - b.s_end - 1);
-          m.m_at = std::max<int64_t>((int64_t)m.lm_a + mgap, 0);
-          m.s_at = std::max<int64_t>((int64_t)m.lm_b + sgap, 0);
-        }
-        m.job_main = mk_job(mid, false, 0, sid, m.rev, (uint64_t)m.m_at, (uint64_t)(m.m_at + mlen - 1), (uint64_t)m.s_at,
-                            (uint64_t)(m.s_at + slen - 1), false, false);
+        // alignBlocks: the k-th chained window (.cc:1657-1669) of a chain in orientation `rev`
+        auto chain_job = [&](uint32_t k, bool rev, int64_t& m_at, int64_t& s_at, uint64_t lm_a, uint64_t lm_b) {
+          const gamx_block& b = block_at(m, k);
+          const int32_t mlen = frame_len(b.m_begin, b.m_end), slen = frame_len(b.s_begin, b.s_end);
+          if (k > 0) {
+            const gamx_block& p = block_at(m, k - 1);
+            const int32_t mgap = p.m_begin <= b.m_begin ? (b.m_begin - p.m_end - 1) : (p.m_begin - b.m_end - 1);
+            const int32_t sgap = p.s_begin <= b.s_begin ? (b.s_begin - p.s_end - 1) : (p.s_begin - b.s_end - 1);
+            m_at = std::max<int64_t>((int64_t)lm_a + mgap, 0);
+            s_at = std::max<int64_t>((int64_t)lm_b + sgap, 0);
+          }
+          return mk_job(mid, false, 0, sid, rev, (uint64_t)m_at, (uint64_t)(m_at + mlen - 1), (uint64_t)s_at,
+                        (uint64_t)(s_at + slen - 1), false, false);
+        };
+        m.job_main = chain_job(m.k, m.rev, m.m_at, m.s_at, m.lm_a, m.lm_b);
+        MergeState::Shadow& h = m.sh;
+        h.issued = spec_round && h.active && !h.threw && h.k < m.mb->n_blocks;
+        if (h.issued) h.job = chain_job(h.k, h.rev, h.m_at, h.s_at, h.lm_a, h.lm_b);
       } else if (m.phase == MergeState::kTailHits) {
         // findHits seeds, .cc:1539,1555,1579,1597
         if (m.want_left) {
@@ -2668,15 +2699,29 @@ int gamx_merge_align(gamx_ctx* ctx, const gamx_merge_block* mbs, uint64_t n, con
     if (!jobs.empty()) {
       jres.assign(jobs.size(), gamx_result());
       if (int rc = gamx_align_batch(ctx, jobs.data(), jobs.size(), jres.data(), nullptr, 0)) return rc;
-      S.alignments += jobs.size();
-      for (const gamx_result& r : jres) S.cells += r.x_size * (2ull * band + 1);
     }
+    // (statistics count the alignments the reference would have run: speculative ones only once adopted)
+    auto count = [&](const gamx_result& r) { S.alignments++; S.cells += r.x_size * (2ull * band + 1); };
     // ---- advance every live merge block ----
     for (uint64_t i = 0; i < n; i++) {
       MergeState& m = st[i];
       if (m.phase == MergeState::kChain) {
+        MergeState::Shadow& h = m.sh;
+        if (h.issued) {  // the speculative chain of the other orientation moves one block as well
+          const gamx_result& r = jres[h.job];
+          h.issued = false;
+          h.cells += r.x_size * (2ull * band + 1);
+          if (r.status == GAMX_JOB_OUT_OF_RANGE || r.status == GAMX_JOB_UNDEFINED) {
+            h.threw = true; h.k++;  // (the retry would throw at this alignment, if it comes to the retry)
+          } else {
+            const AlnLite al = lite_from(r);
+            h.aligns.push_back(al);
+            h.lm_a = al.last_a; h.lm_b = al.last_b;
+            h.k++;
+          }
+        }
         const gamx_result& r = jres[m.job_main];
-        n_aln[i]++;
+        n_aln[i]++; count(r);
         if (r.status == GAMX_JOB_OUT_OF_RANGE || r.status == GAMX_JOB_UNDEFINED) { m.status = 2; m.phase = MergeState::kDone; continue; }
         const AlnLite al = lite_from(r);
         m.aligns.push_back(al);
@@ -2685,13 +2730,26 @@ int gamx_merge_align(gamx_ctx* ctx, const gamx_merge_block* mbs, uint64_t n, con
         // chain finished in this orientation: is_good? (.cc:1435,1454,1485,1503)
         if (!is_good_list(m.aligns, (uint64_t)m.align_threshold)) {
           if (m.attempts < 2) {
-            start_chain(m, !m.rev, m.s_start_fwd, m.s_end_fwd);
+            if (h.active) {
+              // the other orientation has been running all along: its alignments so far are the retry's
+              n_aln[i] += h.k; S.alignments += h.k; S.cells += h.cells;
+              const bool threw = h.threw;
+              adopt_shadow(m);
+              if (threw) { m.status = 2; m.phase = MergeState::kDone; continue; }
+              if (m.k < m.mb->n_blocks) continue;
+              // (it has finished too: judged right here, like the first one)
+              if (!is_good_list(m.aligns, (uint64_t)m.align_threshold)) { m.aligns.clear(); m.phase = MergeState::kDone; continue; }
+            } else {
+              start_chain(m, !m.rev, m.s_start_fwd, m.s_end_fwd);
+              continue;
+            }
           } else {
             m.aligns.clear();  // bad alignment: interrupts the merge (.cc:1512)
             m.phase = MergeState::kDone;
+            continue;
           }
-          continue;
         }
+        h.active = false;  // the running chain is good: the speculative one is dropped
         // ENDS (.cc:1515-1526)
         m.as_a = m.aligns.front().first_a; m.as_b = m.aligns.front().first_b;
         m.ae_a = m.aligns.back().last_a; m.ae_b = m.aligns.back().last_b;
@@ -2716,13 +2774,13 @@ int gamx_merge_align(gamx_ctx* ctx, const gamx_merge_block* mbs, uint64_t n, con
         bool threw = false;
         if (m.want_left) {
           const gamx_result& r = jres[m.job_left];
-          n_aln[i]++;
+          n_aln[i]++; count(r);
           if (r.status == GAMX_JOB_OUT_OF_RANGE || r.status == GAMX_JOB_UNDEFINED) threw = true;
           m.left = lite_from(r); m.have_left = true;
         }
         if (m.want_right) {
           const gamx_result& r = jres[m.job_right];
-          n_aln[i]++;
+          n_aln[i]++; count(r);
           if (r.status == GAMX_JOB_OUT_OF_RANGE || r.status == GAMX_JOB_UNDEFINED) threw = true;
           m.right = lite_from(r); m.have_right = true;
         }

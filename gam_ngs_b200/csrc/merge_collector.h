@@ -61,6 +61,22 @@ struct MergeState {
   gamx_hits_result left_hits = {}, right_hits = {};
   AlnLite left, right;
   size_t job_main = 0, job_left = 0, job_right = 0;  // indices into the round's batches
+  // Orientation speculation: while the first orientation's chain runs, the chain of the OTHER
+  // orientation - what findBestAlignment would start only after the first one has failed (.cc:1435-1459,
+  // 1485-1509) - advances in the same rounds.  It is consulted only if the first chain turns out bad; a merge
+  // block that needs the retry then finishes in max(k) instead of 2k rounds.  Its results are exactly the
+  // retry's (the chain depends on the orientation only), so nothing observable changes.
+  struct Shadow {
+    bool active = false, threw = false;
+    bool rev = false;
+    uint32_t k = 0;
+    int64_t slave_start = 0, slave_end = 0, m_at = 0, s_at = 0;
+    uint64_t lm_a = 0, lm_b = 0;
+    std::vector<AlnLite> aligns;
+    uint64_t cells = 0;      // DP cells of its alignments so far (committed to the statistics only on a switch)
+    size_t job = 0;
+    bool issued = false;     // a job of this chain is in the current round
+  } sh;
 };
 
 inline const gamx_block& block_at(const MergeState& st, uint32_t k) {
@@ -94,6 +110,28 @@ inline void start_chain(MergeState& st, bool rev, int64_t s_start_fwd, int64_t s
   st.aligns.clear();
   st.phase = MergeState::kChain;
   st.attempts++;
+}
+
+// starts the speculative chain of the orientation opposite to the running first attempt
+inline void start_shadow(MergeState& st) {
+  MergeState::Shadow& h = st.sh;
+  h = MergeState::Shadow();
+  h.active = true;
+  h.rev = !st.rev;
+  if (h.rev) { h.slave_start = (int64_t)st.ssz - st.s_end_fwd - 1; h.slave_end = (int64_t)st.ssz - st.s_start_fwd - 1; }
+  else { h.slave_start = st.s_start_fwd; h.slave_end = st.s_end_fwd; }
+  h.m_at = st.master_start; h.s_at = h.slave_start;
+}
+
+// the first orientation failed: the speculative chain becomes the running (second) attempt
+inline void adopt_shadow(MergeState& st) {
+  MergeState::Shadow& h = st.sh;
+  st.rev = h.rev; st.slave_start = h.slave_start; st.slave_end = h.slave_end;
+  st.k = h.k; st.m_at = h.m_at; st.s_at = h.s_at; st.lm_a = h.lm_a; st.lm_b = h.lm_b;
+  st.aligns.swap(h.aligns);
+  st.phase = MergeState::kChain;
+  st.attempts++;
+  h.active = false;
 }
 
 }  // namespace gamx
