@@ -35,6 +35,8 @@ import time
 
 import numpy as np
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before the first CUDA call: see gamx_create (stream count vs hardware queues)
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -265,7 +267,7 @@ def other_configs(ctx, g, capi, jobs_cfg2, int_peak32, int_peak16):
     entry("cfg2_1M_1kb_band64_score", j, 64, 0, "same contigs and jobs as the headline, score only")
     # config 3 sample
     rng = np.random.default_rng(3)
-    n3 = 1500
+    n3 = 6000
     a, al, b, bl = gen.bulk_pairs(rng, n3, 0, div=0.02, len_lo=10000, len_hi=50000)
     ctx.clear_contigs()
     ctx.add_contigs(np.concatenate([a, b]), np.concatenate([al, bl]))
@@ -275,7 +277,7 @@ def other_configs(ctx, g, capi, jobs_cfg2, int_peak32, int_peak16):
     entry("cfg3_long_band256_full", j, 256, 2, f"{n3}-pair sample of the 100000 pairs of config 3 (10-50 kb, full traceback + edit strings)", steps=2)
     # config 5 sweep points: mixed lengths (log-uniform 256..16384), band sweep at 2 %, divergence sweep at band 64
     rng = np.random.default_rng(5)
-    n5 = 40000
+    n5 = 100000
     lengths = np.exp(rng.uniform(np.log(256), np.log(16384), n5)).astype(np.int64)
     for div in (0.02, 0.0, 0.10):
         a, al, b, bl = gen.bulk_pairs(rng, n5, 0, div=div, lengths=lengths)

@@ -26,6 +26,7 @@
 #include <cub/device/device_scan.cuh>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -34,6 +35,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -416,6 +418,16 @@ generic_kernel(const GenJob* __restrict__ jobs, int n_jobs, SeqStore store, int6
 // 64-thread blocks with at most 32 registers per thread: small enough to become resident next to the
 // persistent alignment blocks (which leave ~4 K registers per SM free), so the pack of upload piece
 // p+1 proceeds while the alignment kernel of an earlier chunk still owns every SM.
+// Descriptor fetch of a pipelined chunk: the SMs read the chunk's job records straight out of the pinned host
+// buffer (unified addressing).  A cudaMemcpyAsync would queue on the copy engine behind the 128 MB sequence
+// pieces that are in flight at the same time and hold the chunk back by milliseconds.
+constexpr int kFetchThreads = 128;
+__global__ void __launch_bounds__(kFetchThreads, 16)
+fetch_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src_host, uint64_t n16) {
+  for (uint64_t i = (uint64_t)blockIdx.x * kFetchThreads + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * kFetchThreads)
+    dst[i] = src_host[i];
+}
+
 constexpr int kPackThreads = 64;
 constexpr int kPackPerThread = 4;                           // 32-base groups per thread (more loads in flight)
 constexpr int kPackGroups = kPackThreads * kPackPerThread;  // groups per block
@@ -672,6 +684,10 @@ struct Device {
   // the last piece it needs (pieces complete in order)
   cudaStream_t up_stream = nullptr;
   std::vector<cudaEvent_t> up_events;  // event pool, one per piece of the upload in flight (+ [0] = "all earlier uploads")
+  // K0 runs on a stream of its own behind the copy of its piece, so the copies follow each other without a
+  // gap (a pack launch has to find room beside the resident alignment blocks and may take a while)
+  cudaStream_t pack_stream = nullptr;
+  std::vector<cudaEvent_t> copy_events;  // piece p has crossed PCIe
 };
 
 // Index of the contig store.  Sequence data itself lives only on the devices; contigs added one
@@ -719,6 +735,7 @@ struct Upload {
   const uint64_t* roff = nullptr;     // per contig: raw byte offset (n+1 entries), in the context's pinned meta buffer
   const uint64_t* sgroup = nullptr;   // per contig: first store group relative to group0 (n+1 entries)
   size_t enqueued = 0;                // pieces already enqueued on every device
+  bool events_valid = false;          // the per-piece events belong to this upload (also after the last piece was enqueued)
 };
 
 struct gamx_ctx {
@@ -773,6 +790,85 @@ int ensure_pin(gamx_ctx* ctx, PinBuf& b, size_t bytes) {
   return GAMX_OK;
 }
 
+// Host worker pool.  Batch preparation runs many short parallel passes (an index pass over two million
+// contigs takes 0.2 ms of work); starting a thread per slice and pass cost more than the passes themselves
+// (0.4 ms per call with 16 threads: 3 ms of gamx_add_contigs_async's 3.4 ms).  The workers are created once per
+// process and never destroyed (they sleep on a condition variable); several callers - the producer and the
+// consumer of a pipelined batch, concurrent contexts - may submit passes at the same time.
+class HostPool {
+ public:
+  static HostPool& get() {
+    static HostPool* pool = new HostPool();  // (leaked on purpose: workers may outlive static destruction)
+    return *pool;
+  }
+  // runs task(k) for k in [0, n): k = 0 on the calling thread, the others on the workers; returns when all are done
+  template <class Task>
+  void run(unsigned n, const Task& task) {
+    if (n <= 1) { if (n) task(0u); return; }
+    Call call;
+    call.pending = n - 1;
+    call.fn = [&task](unsigned k) { task(k); };
+    ensure_workers(n - 1);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      for (unsigned k = 1; k < n; k++) queue_.push_back({&call, k});
+    }
+    cv_.notify_all();
+    task(0u);
+    // help with the own call's slices that no worker has picked up yet, then wait for the rest
+    for (;;) {
+      Item it{nullptr, 0};
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        for (auto q = queue_.begin(); q != queue_.end(); ++q)
+          if (q->call == &call) { it = *q; queue_.erase(q); break; }
+      }
+      if (!it.call) break;
+      call.fn(it.k);
+      finish_one(call);
+    }
+    std::unique_lock<std::mutex> lk(call.mu);
+    call.cv.wait(lk, [&] { return call.pending == 0; });
+  }
+
+ private:
+  struct Call {
+    std::function<void(unsigned)> fn;
+    std::mutex mu;
+    std::condition_variable cv;
+    unsigned pending = 0;
+  };
+  struct Item { Call* call; unsigned k; };
+  static void finish_one(Call& c) {
+    std::lock_guard<std::mutex> lk(c.mu);  // (notify under the lock: the waiter destroys the Call right after)
+    if (--c.pending == 0) c.cv.notify_one();
+  }
+  void ensure_workers(unsigned want) {
+    std::lock_guard<std::mutex> lk(mu_);
+    while (n_workers_ < want) {
+      std::thread([this] { worker(); }).detach();
+      n_workers_++;
+    }
+  }
+  void worker() {
+    for (;;) {
+      Item it;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return !queue_.empty(); });
+        it = queue_.front();
+        queue_.pop_front();
+      }
+      it.call->fn(it.k);
+      finish_one(*it.call);
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<Item> queue_;
+  unsigned n_workers_ = 0;
+};
+
 // splits [0, n) over the host's cores; fn(slice, begin, end) must be thread-safe, slice < kMaxHostThreads
 constexpr unsigned kMaxHostThreads = 32;
 template <class F>
@@ -786,17 +882,15 @@ void parallel_slices(uint64_t n, F fn) {
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) { const int v = atoi(e); if (v > 1) n = std::max(1u, n / (unsigned)v); }
     return std::min(n, kMaxHostThreads);
   }();
-  unsigned nt = nt_cfg;
-  if (n < 20000 || nt == 1) { fn(0u, (uint64_t)0, n); return; }
-  std::vector<std::thread> th;
+  // (slices of at least 1024 items: handing a slice to a pooled worker costs a few microseconds)
+  const unsigned nt = (unsigned)std::min<uint64_t>(nt_cfg, n / 1024);
+  if (nt <= 1) { fn(0u, (uint64_t)0, n); return; }
   const uint64_t chunk = (n + nt - 1) / nt;
-  for (unsigned t = 1; t < nt; t++) {
+  const unsigned slices = (unsigned)((n + chunk - 1) / chunk);
+  HostPool::get().run(slices, [&](unsigned t) {
     const uint64_t b = t * chunk, e = std::min(n, b + chunk);
-    if (b >= e) break;
-    th.emplace_back([=] { fn(t, b, e); });
-  }
-  fn(0u, (uint64_t)0, std::min(n, chunk));  // the calling thread takes the first slice
-  for (auto& t : th) t.join();
+    fn(t, b, e);
+  });
 }
 template <class F>
 void parallel_for(uint64_t n, F fn) {
@@ -869,23 +963,26 @@ int upload_advance(gamx_ctx* ctx, size_t upto) {
     for (Device& d : ctx->devs) {
       CU(cudaSetDevice(d.id));
       if (int rc = h2d_raw(ctx, d, (uint8_t*)d.raw.p + u.roff[c0], u.raw + u.roff[c0], u.roff[c1] - u.roff[c0], pinned)) return rc;
-      // (K0 runs on the copy stream itself: letting the copies run ahead on their own stream was
-      //  measured slower end to end - the job-descriptor copies of the chunks then queue behind them)
+      // K0 follows on the pack stream; the next piece's copy does not wait for it.  (In round 1 copies that
+      // ran ahead measured slower: the job-descriptor copies of the chunks queued behind them on the copy
+      // engine.  Chunks now fetch their descriptors with a kernel, see plan_upload.)
+      CU(cudaEventRecord(d.copy_events[p], d.up_stream));
+      CU(cudaStreamWaitEvent(d.pack_stream, d.copy_events[p], 0));
       if (g1 > g0) {
         const uint64_t* dm = (const uint64_t*)d.meta.p;  // roff[n+1], sgroup[n+1]
         const unsigned blocks = (unsigned)((g1 - g0 + kPackGroups - 1) / kPackGroups);
-        pack_kernel<<<blocks, kPackThreads, 0, d.up_stream>>>((const uint8_t*)d.raw.p, dm + c0, dm + (u.n + 1) + c0, (int)(c1 - c0),
-                                                    u.group0, g0, g1 - g0, (uint32_t*)d.packed.p, (uint32_t*)d.nmask.p);
+        pack_kernel<<<blocks, kPackThreads, 0, d.pack_stream>>>((const uint8_t*)d.raw.p, dm + c0, dm + (u.n + 1) + c0, (int)(c1 - c0),
+                                                      u.group0, g0, g1 - g0, (uint32_t*)d.packed.p, (uint32_t*)d.nmask.p);
         CU(cudaGetLastError());
       }
-      CU(cudaEventRecord(d.up_events[p + 1], d.up_stream));
+      CU(cudaEventRecord(d.up_events[p + 1], d.pack_stream));
     }
   }
   u.enqueued = want;
   if (want == np) {  // everything is enqueued: later consumers wait for event 0 ("all uploads so far")
     for (Device& d : ctx->devs) {
       CU(cudaSetDevice(d.id));
-      CU(cudaEventRecord(d.up_events[0], d.up_stream));
+      CU(cudaEventRecord(d.up_events[0], d.pack_stream));
     }
     u.active = false;
   }
@@ -898,7 +995,7 @@ int store_ready(gamx_ctx* ctx, Device& d, cudaStream_t stream, size_t upto) {
   const Upload& u = ctx->up;
   if (d.up_events.empty()) return GAMX_OK;  // nothing was ever uploaded
   CU(cudaSetDevice(d.id));
-  if (u.active && upto != SIZE_MAX && upto >= u.first) {
+  if (u.events_valid && upto != SIZE_MAX && upto >= u.first) {
     const size_t rel = std::min(upto - u.first, u.n - 1);
     const size_t p = (size_t)(std::upper_bound(u.piece_end.begin(), u.piece_end.end(), rel) - u.piece_end.begin());
     CU(cudaStreamWaitEvent(stream, d.up_events[std::min(p, u.piece_end.size() - 1) + 1], 0));
@@ -912,6 +1009,10 @@ int store_ready(gamx_ctx* ctx, Device& d, cudaStream_t stream, size_t upto) {
 // index - to every device.  wait: enqueue all pieces and return when `raw` may be reused.
 int store_upload(gamx_ctx* ctx, const uint8_t* raw, size_t first, size_t n, bool wait = true) {
   if (n == 0) return GAMX_OK;
+  static const bool timing = getenv("GAMX_TIMING") != nullptr;
+  auto tp = std::chrono::steady_clock::now();
+  double tm[4] = {0, 0, 0, 0};
+  auto lap = [&](int k) { const auto t = std::chrono::steady_clock::now(); tm[k] += std::chrono::duration<double, std::milli>(t - tp).count(); tp = t; };
   if (int rc = upload_advance(ctx, SIZE_MAX)) return rc;  // finish enqueuing an earlier deferred upload
   const StoreIndex& si = ctx->store;
   Upload& u = ctx->up;
@@ -919,10 +1020,13 @@ int store_upload(gamx_ctx* ctx, const uint8_t* raw, size_t first, size_t n, bool
   u.group0 = si.start[first] / 32;
   const uint64_t groups_end = si.n_bases / 32;
   const size_t meta_bytes = 2 * (n + 1) * sizeof(uint64_t);
-  for (Device& d : ctx->devs) {  // an earlier upload may still read the pinned meta buffer / raw
+  u.events_valid = false;
+  for (Device& d : ctx->devs) {  // an earlier upload may still read the pinned meta buffer / raw (host and device side)
     CU(cudaSetDevice(d.id));
     CU(cudaStreamSynchronize(d.up_stream));
+    CU(cudaStreamSynchronize(d.pack_stream));
   }
+  lap(0);
   if (int rc = ensure_pin(ctx, ctx->h_meta, meta_bytes)) return rc;
   uint64_t* roff = (uint64_t*)ctx->h_meta.p;
   uint64_t* sgroup = roff + (n + 1);
@@ -940,20 +1044,36 @@ int store_upload(gamx_ctx* ctx, const uint8_t* raw, size_t first, size_t n, bool
     slice_raw[t + 1] = sum;
   });
   for (unsigned t = 0; t < kMaxHostThreads; t++) slice_raw[t + 1] += slice_raw[t];
+  // Piece boundaries: multiples of piece_bytes, except that a large upload starts and ends with short
+  // pieces (1/8, 1/4, 1/2 of a piece): the first chunk of a pipelined batch then starts after the first
+  // 16 MB instead of the first 128 MB, and what is left to compute once the last byte has crossed PCIe
+  // is a short chunk instead of a whole one.  piece_of() numbers the pieces (monotone in the offset).
+  const uint64_t total_raw = slice_raw[kMaxHostThreads];
+  static const bool no_ramp = getenv("GAMX_NO_PIECE_RAMP") != nullptr;  // experiments only
+  const bool ramp = !no_ramp && total_raw >= 6 * piece_bytes && piece_bytes >= 4096;
+  const uint64_t head = ramp ? piece_bytes / 8 * 7 : 0;  // the three short pieces at either end
+  auto piece_of = [=](uint64_t x) -> uint64_t {
+    if (!ramp) return x / piece_bytes;
+    uint64_t k = x < piece_bytes / 8 ? 0 : x < piece_bytes / 8 * 3 ? 1 : x < head ? 2 : 3 + (x - head) / piece_bytes;
+    const uint64_t left = total_raw - x;  // (x <= total_raw)
+    k += (left <= head) + (left <= piece_bytes / 8 * 3) + (left <= piece_bytes / 8);
+    return k;
+  };
   parallel_slices(n, [&](unsigned t, uint64_t b, uint64_t e) {
     uint64_t off = slice_raw[t];
     for (uint64_t c = b; c < e; c++) {
       roff[c] = off; sgroup[c] = st[c] / 32 - g0;
       const uint64_t end = off + ln[c];
-      if (end / piece_bytes != off / piece_bytes) slice_pieces[t].push_back(c + 1);
+      if (piece_of(end) != piece_of(off)) slice_pieces[t].push_back(c + 1);
       off = end;
     }
   });
-  const uint64_t off = slice_raw[kMaxHostThreads];
+  const uint64_t off = total_raw;
   u.piece_end.clear();
   for (unsigned t = 0; t < kMaxHostThreads; t++) u.piece_end.insert(u.piece_end.end(), slice_pieces[t].begin(), slice_pieces[t].end());
   roff[n] = off; sgroup[n] = groups_end - u.group0;
   if (u.piece_end.empty() || u.piece_end.back() != n) u.piece_end.push_back(n);
+  lap(1);
   for (Device& d : ctx->devs) {
     CU(cudaSetDevice(d.id));
     if (int rc = grow_keep(ctx, d, d.packed, groups_end * 8 + 64, d.store_groups * 8)) return rc;
@@ -965,10 +1085,17 @@ int store_upload(gamx_ctx* ctx, const uint8_t* raw, size_t first, size_t n, bool
       CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
       d.up_events.push_back(e);
     }
+    while (d.copy_events.size() < u.piece_end.size()) {
+      cudaEvent_t e;
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      d.copy_events.push_back(e);
+    }
     CU(cudaMemcpyAsync(d.meta.p, ctx->h_meta.p, meta_bytes, cudaMemcpyHostToDevice, d.up_stream));
     d.store_groups = groups_end;
   }
+  lap(2);
   u.active = true;
+  u.events_valid = true;
   ctx->up_unsettled = !wait;
   if (wait) {
     if (int rc = upload_advance(ctx, SIZE_MAX)) return rc;
@@ -976,7 +1103,18 @@ int store_upload(gamx_ctx* ctx, const uint8_t* raw, size_t first, size_t n, bool
       CU(cudaSetDevice(d.id));
       CU(cudaStreamSynchronize(d.up_stream));
     }
+  } else {
+    // A pinned source needs no host work per piece: every copy is enqueued right away and the copy engine
+    // runs through the upload at PCIe speed, whatever the consumer is doing.  (A pageable source goes through
+    // staging buffers piece by piece as the batches ask for it; GAMX_UPLOAD_LAZY=1 does that for both.)
+    static const bool lazy = getenv("GAMX_UPLOAD_LAZY") != nullptr;
+    if (!lazy && is_pinned(raw))
+      if (int rc = upload_advance(ctx, SIZE_MAX)) return rc;
   }
+  lap(3);
+  if (timing)
+    fprintf(stderr, "[gamx] store_upload: wait for earlier upload %.2f, offsets+pieces %.2f, buffers+meta %.2f, enqueue %.2f ms (%zu pieces)\n",
+            tm[0], tm[1], tm[2], tm[3], u.piece_end.size());
   return GAMX_OK;
 }
 
@@ -1250,6 +1388,12 @@ int gamx_abi_version(void) { return GAMX_ABI_VERSION; }
 int gamx_create(gamx_ctx** out, const int* device_ids, int n_devices) {
   if (!out) return GAMX_ERR_INVALID;
   *out = nullptr;
+  // A context runs ~20 streams per device (four slots of four streams, upload, pack).  With the default of 8
+  // hardware queues several of them share a queue, and a chunk whose stream shares one with the upload stream
+  // waits for the whole upload (measured: one chunk in four held back by 30 ms).  The variable is read when
+  // the device's primary context is created, so it only takes effect if that has not happened yet - a host
+  // program that touches CUDA before gamx_create sets it itself (the Python package does so on import).
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int visible = 0;
   if (cudaGetDeviceCount(&visible) != cudaSuccess || visible <= 0) {
     cudaGetLastError();
@@ -1280,6 +1424,7 @@ int gamx_create(gamx_ctx** out, const int* device_ids, int n_devices) {
     int prio_lo = 0, prio_hi = 0;  // the upload stream's small pack blocks go first when an SM has room
     ok = ok && cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) == cudaSuccess;
     ok = ok && cudaStreamCreateWithPriority(&d.up_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+         cudaStreamCreateWithPriority(&d.pack_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
          cudaEventCreate(&d.ev0) == cudaSuccess && cudaEventCreate(&d.ev1) == cudaSuccess &&
          cudaEventCreateWithFlags(&d.ev_stage[0], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&d.ev_stage[1], cudaEventDisableTiming) == cudaSuccess;
@@ -1324,6 +1469,8 @@ void gamx_destroy(gamx_ctx* ctx) {
       cudaStreamDestroy(sl.stream);
     }
     for (cudaEvent_t e : d.up_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : d.copy_events) cudaEventDestroy(e);
+    cudaStreamDestroy(d.pack_stream);
     cudaEventDestroy(d.ev0);
     cudaEventDestroy(d.ev1);
     cudaEventDestroy(d.ev_stage[0]);
@@ -1537,6 +1684,7 @@ int gamx_clear_contigs(gamx_ctx* ctx) {
   ctx->pending.clear();
   ctx->pending_first = 0;
   ctx->names.clear();
+  ctx->up.events_valid = false;
   return GAMX_OK;
 }
 
@@ -1926,7 +2074,14 @@ static int plan_upload(gamx_plan* pl) {
       });
     }
     lap(3);
-    if (dp.n_dev_jobs)
+    static const bool dma_jobs = getenv("GAMX_JOBS_BY_DMA") != nullptr;  // experiments only
+    if (dp.n_dev_jobs && pl->chunked && !dma_jobs) {
+      static_assert(sizeof(DevJob) % 16 == 0, "descriptor records are copied in 16-byte units");
+      const uint64_t n16 = (uint64_t)dp.n_dev_jobs * sizeof(DevJob) / 16;
+      fetch_kernel<<<(unsigned)std::min<uint64_t>((n16 + kFetchThreads - 1) / kFetchThreads, 2 * (uint64_t)d.sm_count), kFetchThreads, 0,
+                     sl.stream>>>((uint4*)sl.jobs.p, (const uint4*)hj, n16);
+      CU(cudaGetLastError());
+    } else if (dp.n_dev_jobs)
       CU(cudaMemcpyAsync(sl.jobs.p, hj, (size_t)dp.n_dev_jobs * sizeof(DevJob), cudaMemcpyHostToDevice, sl.stream));
     if (dp.n_gen_jobs)
       CU(cudaMemcpyAsync(sl.gjobs.p, hg, (size_t)dp.n_gen_jobs * sizeof(GenJob), cudaMemcpyHostToDevice, sl.stream));
@@ -2169,11 +2324,21 @@ void gamx_plan_destroy(gamx_plan* pl) { delete pl; }
 // copies and the host work all overlap.
 constexpr int kNeedsSinglePlan = 1000;  // internal: a chunk holds a FULL-mode job
 static int align_batch_pipelined(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_result* results, uint64_t chunk) {
-  // chunk boundaries: two short chunks first, so that the device starts early
+  // chunk boundaries: two short chunks first, so that the device starts early, and three short ones last
+  // (1/2, 1/4, 1/8 of a chunk), so that little is left to do when the last upload piece has arrived and
+  // the last traceback launch is a short one
   std::vector<uint64_t> lo_of;
-  for (uint64_t at = 0, k = 0; at < n; k++) {
-    lo_of.push_back(at);
-    at += k == 0 ? std::max<uint64_t>(chunk / 4, 1) : k == 1 ? std::max<uint64_t>(chunk / 2, 1) : chunk;
+  {
+    static const bool no_ramp = getenv("GAMX_NO_CHUNK_RAMP") != nullptr;  // experiments only
+    const uint64_t tail = chunk / 2 + chunk / 4 + chunk / 8;
+    const uint64_t tail_at = (!no_ramp && chunk >= 8 && n >= 4 * chunk) ? n - tail : n;
+    uint64_t at = 0;
+    for (uint64_t k = 0; at < tail_at; k++) {
+      lo_of.push_back(at);
+      at += k == 0 ? std::max<uint64_t>(chunk / 4, 1) : k == 1 ? std::max<uint64_t>(chunk / 2, 1) : chunk;
+    }
+    // (the last full-size step may overshoot tail_at: the body's last chunk is just shorter)
+    if (tail_at < n) { lo_of.push_back(tail_at); lo_of.push_back(tail_at + chunk / 2); lo_of.push_back(tail_at + chunk / 2 + chunk / 4); }
   }
   const uint64_t nchunks = lo_of.size();
   lo_of.push_back(n);
