@@ -451,11 +451,22 @@ def main():
                              f"in {len(bad)} jobs, first {bad[:6]}: {r2[bad[0]]} vs {res[bad[0]]}")
         h2d = total_bases + lengths.nbytes * 3 + n * 96  # raw codes + pack metadata + DevJob descriptors (96 B each)
         d2h = n * 104                                     # DevResult records
+        # what the PCIe link of this box does with nothing else going on: one 1 GiB copy out of the same pinned
+        # buffer, best of 3 (the end-to-end step cannot be shorter than its H2D bytes at this rate)
+        probe = torch.empty(min(1 << 30, host.numel()), dtype=torch.uint8, device=f"cuda:{local_rank}")
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h2d_gbs = 0.0
+        for _ in range(3):
+            ev_a.record(); probe.copy_(host[:probe.numel()], non_blocking=True); ev_b.record(); ev_b.synchronize()
+            h2d_gbs = max(h2d_gbs, probe.numel() / (ev_a.elapsed_time(ev_b) * 1e-3) / 1e9)
+        del probe
         e2e = {"value": total_cells * args.steps / e2e_s / 1e9, "unit": "GCUPS",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": e2e_s / args.steps * 1e3,
                "includes": "raw sequence H2D from pinned memory + device 2-bit pack, job descriptor H2D, kernels, result D2H",
-               "pipeline": "chunks of 65536 jobs over 4 buffer slots/streams; upload pieces of 128 MB on their own stream"}
+               "pcie_h2d_gbs_measured": h2d_gbs, "pcie_floor_ms": h2d / (h2d_gbs * 1e9) * 1e3 if h2d_gbs else None,
+               "pipeline": "chunks of 65536 jobs over 4 buffer slots/streams; every upload piece (128 MB, short ones first and last) "
+                           "enqueued at once on a copy stream, pack kernel per piece on its own stream, descriptors fetched by a kernel"}
     # ---- roofline --------------------------------------------------------------------------------
     geo = capi.band_geometry(spec["band"]) or (0, 0)
     s16 = geo[1] <= 32 and os.environ.get("GAMX_NO_S16") is None   # warp-level launches run the 16x2 pair kernel

@@ -92,6 +92,7 @@ EXPORTS = [
     "gamx_plan_create", "gamx_plan_run", "gamx_plan_sync", "gamx_plan_fetch", "gamx_plan_last_ms",
     "gamx_plan_cells", "gamx_plan_kernel_launches", "gamx_plan_destroy", "gamx_measure_int_peak",
     "gamx_shard_by_cost", "gamx_find_hits_batch", "gamx_merge_align", "gamx_band_geometry",
+    "gamx_host_selftest",
 ]
 
 _lib = None
@@ -171,6 +172,8 @@ def load_library(build_if_missing: bool = True):
     L.gamx_merge_align.restype = C.c_int
     L.gamx_band_geometry.argtypes = [u64, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.gamx_band_geometry.restype = C.c_int
+    L.gamx_host_selftest.argtypes = [C.c_int, u64]
+    L.gamx_host_selftest.restype = C.c_int
     L.gamx_measure_int_peak.argtypes = [vp, C.c_int, C.c_int]
     L.gamx_measure_int_peak.restype = C.c_double
     _lib = L

@@ -228,14 +228,18 @@ k2_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counter
 // loads, so it wants many independent walks in flight, not a lane of a busy fill warp; its small
 // blocks (64 threads, <= 48 registers) fit beside the resident fill blocks of the next wave.
 constexpr int kTbThreads = 64;
-constexpr int kTbWarpRows = 4096;  // jobs with at least this many rows are walked by a whole warp (tbw_kernel)
+constexpr int kTbWarpRows = 4096;  // jobs with at least this many rows are walked by a whole warp (tbw_kernel) ...
+// ... and in a launch of at most this many jobs every job is: such a launch cannot fill the device with one walk per
+// thread anyway, and what its caller waits for is the longest walk (a merge round: a 2.6 k-row walk takes 0.6 ms
+// on a thread - as long as the fill - and a fraction of that on a warp that fetches 32 step blocks per round trip)
+constexpr uint64_t kTbAllWarpJobs = 8192;
 __global__ void __launch_bounds__(kTbThreads, 20)
 tb_kernel(const DevJob* __restrict__ jobs, int n_jobs, const uint32_t* __restrict__ dirs, uint64_t stride, int c, int lg,
-          uint32_t* __restrict__ ops, DevResult* __restrict__ results) {
+          uint32_t* __restrict__ ops, DevResult* __restrict__ results, int warp_rows) {
   const int j = (int)(blockIdx.x * blockDim.x + threadIdx.x);
   if (j >= n_jobs) return;
   const DevJob* Jp = jobs + j;
-  if (Jp->x >= kTbWarpRows) return;  // tbw_kernel's
+  if (Jp->x >= warp_rows) return;  // tbw_kernel's
   DevResult R = results[j];
   if (R.status != kStatusOk || (Jp->mode & 0x100)) return;  // empty / out of range: nothing to walk
   const int lay = R.has_match;  // left by the fill kernel: 0 = 32-bit layout, 1 + h = half h of a 16x2 pair region
@@ -293,11 +297,11 @@ struct WarpFetch16 {
 constexpr int kTbwThreads = 128;
 __global__ void __launch_bounds__(kTbwThreads, 8)
 tbw_kernel(const DevJob* __restrict__ jobs, int n_jobs, const uint32_t* __restrict__ dirs, uint64_t stride, int c, int lg,
-           uint32_t* __restrict__ ops, DevResult* __restrict__ results) {
+           uint32_t* __restrict__ ops, DevResult* __restrict__ results, int warp_rows) {
   const int j = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (j >= n_jobs) return;
   const DevJob* Jp = jobs + j;
-  if (Jp->x < kTbWarpRows) return;  // tb_kernel's
+  if (Jp->x < warp_rows) return;  // tb_kernel's
   DevResult R = results[j];
   if (R.status != kStatusOk || (Jp->mode & 0x100)) return;
   const bool leader = (threadIdx.x & 31) == 0;
@@ -1873,15 +1877,17 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
         groups[find_group(0, 32, true, -1, 0)].job_idx.push_back(i);
       }
     }
-    // Latency mode: a launch of few long pairs cannot fill the device with one warp per pair, so
-    // those pairs go to the CTA-per-pair kernel (64 lanes per pair) instead.
+    // Latency mode: a launch of few pairs cannot fill the device with one warp per pair, and what its caller
+    // waits for is its longest pair (a round of the merge stage): when that one has at least 1024 rows the
+    // group goes to the CTA-per-pair kernel (64 lanes per pair: 115 instead of 330 ns per row).
     static const bool no_latency_mode = getenv("GAMX_NO_LATENCY_MODE") != nullptr;  // experiments only
     for (Group& g : groups) {
       if (no_latency_mode) break;
       if (g.c == 0 || g.lg != 32 || g.job_idx.size() >= (size_t)2 * ctx->devs[d].sm_count) continue;
-      uint64_t min_x = ~0ull;
-      for (uint32_t i : g.job_idx) min_x = std::min(min_x, preps[i].x_size);
-      if (min_x < 2048) continue;
+      uint64_t max_x = 0;
+      for (uint32_t i : g.job_idx) max_x = std::max(max_x, preps[i].x_size);
+      static const uint64_t latency_rows = [] { const char* e = getenv("GAMX_LATENCY_ROWS"); return e ? (uint64_t)strtoull(e, nullptr, 10) : (uint64_t)1024; }();
+      if (max_x < latency_rows) continue;
       int c2 = 0, lg2 = 0;
       cta_geometry_for_latency((uint64_t)preps[g.job_idx[0]].dj.band, &c2, &lg2);
       bool same_band = true;
@@ -2173,16 +2179,18 @@ static int plan_run_locked(gamx_plan* pl) {
         if (walk) {
           CU(cudaEventRecord(sl.ev_fill[h], fs));
           CU(cudaStreamWaitEvent(sl.tb_stream, sl.ev_fill[h], 0));
-          if (g.min_x < (uint64_t)kTbWarpRows) {  // short jobs: one per thread
+          static const bool tb_all_warp = getenv("GAMX_NO_TB_ALL_WARP") == nullptr;  // (experiments)
+          const int warp_rows = (tb_all_warp && nw <= kTbAllWarpJobs) ? 0 : kTbWarpRows;  // small launch: every walk on a warp
+          if (g.min_x < (uint64_t)warp_rows) {  // short jobs: one per thread
             tb_kernel<<<(unsigned)((nw + kTbThreads - 1) / kTbThreads), kTbThreads, 0, sl.tb_stream>>>(
-                dj + w0, (int)nw, half, g.max_dir_words, g.c, g.lg, (uint32_t*)sl.ops.p, res + w0);
+                dj + w0, (int)nw, half, g.max_dir_words, g.c, g.lg, (uint32_t*)sl.ops.p, res + w0, warp_rows);
             CU(cudaGetLastError());
             pl->launches++;
           }
-          if (g.max_x >= (uint64_t)kTbWarpRows) {  // long jobs: one per warp
+          if (g.max_x >= (uint64_t)warp_rows) {  // long jobs: one per warp
             const uint64_t warps_per_block = kTbwThreads / 32;
             tbw_kernel<<<(unsigned)((nw + warps_per_block - 1) / warps_per_block), kTbwThreads, 0, sl.tb_stream>>>(
-                dj + w0, (int)nw, half, g.max_dir_words, g.c, g.lg, (uint32_t*)sl.ops.p, res + w0);
+                dj + w0, (int)nw, half, g.max_dir_words, g.c, g.lg, (uint32_t*)sl.ops.p, res + w0, warp_rows);
             CU(cudaGetLastError());
             pl->launches++;
           }
@@ -3012,6 +3020,36 @@ int gamx_band_geometry(uint64_t band, int* stripe_width, int* lanes_per_pair) {
   if (y <= 32ull * kMaxC) geometry_for_band(band, true, stripe_width, lanes_per_pair);
   else if (!geometry_cta(band, stripe_width, lanes_per_pair)) return GAMX_ERR_INVALID;
   return GAMX_OK;
+}
+
+int gamx_host_selftest(int callers, uint64_t items) {
+  if (callers < 1) callers = 1;
+  std::atomic<int> wrong(0);
+  auto one_caller = [&](int who) {
+    std::vector<uint64_t> v(items);
+    for (int pass = 0; pass < 20; pass++) {
+      // pass A: fill in parallel; pass B: per-slice sums (slice ids must be distinct and < kMaxHostThreads)
+      parallel_for(items, [&](uint64_t b, uint64_t e) { for (uint64_t i = b; i < e; i++) v[i] = i * 3 + (uint64_t)who + (uint64_t)pass; });
+      uint64_t part[kMaxHostThreads] = {0};
+      std::atomic<uint32_t> seen(0);
+      bool dup = false;
+      parallel_slices(items, [&](unsigned t, uint64_t b, uint64_t e) {
+        if (t >= kMaxHostThreads || (seen.fetch_or(1u << t) & (1u << t))) { dup = true; return; }
+        uint64_t s = 0;
+        for (uint64_t i = b; i < e; i++) s += v[i];
+        part[t] = s;
+      });
+      uint64_t sum = 0;
+      for (unsigned t = 0; t < kMaxHostThreads; t++) sum += part[t];
+      const uint64_t want = items ? 3 * (items * (items - 1) / 2) + items * ((uint64_t)who + (uint64_t)pass) : 0;
+      if (dup || sum != want) wrong++;
+    }
+  };
+  std::vector<std::thread> th;
+  for (int c = 1; c < callers; c++) th.emplace_back(one_caller, c);
+  one_caller(0);
+  for (auto& t : th) t.join();
+  return wrong.load();
 }
 
 double gamx_measure_int_peak(gamx_ctx* ctx, int dev_index, int which) {

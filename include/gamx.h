@@ -305,6 +305,14 @@ GAMX_API int gamx_shard_by_cost(const uint64_t* cost, uint64_t n, int n_shards, 
  * kernel K2).  Returns 0, or GAMX_ERR_INVALID when the band needs the generic kernel.  Pure host code. */
 GAMX_API int gamx_band_geometry(uint64_t band, int* stripe_width, int* lanes_per_pair);
 
+/* ---- diagnostics ------------------------------------------------------------------------- */
+
+/* Exercises the host worker pool the batch preparation runs on (pure host code, no device): `callers`
+ * threads submit parallel passes over `items` elements at the same time - the way the producer and the
+ * consumer of a pipelined batch, or several contexts, do - and check every pass's result.  Returns 0, or
+ * the number of passes that came out wrong. */
+GAMX_API int gamx_host_selftest(int callers, uint64_t items);
+
 /* ---- microbenchmarks used for the roofline denominators (bench.py) ------------------ */
 
 /* Measures the integer/DPX issue peak of device `dev_index` of the context with a

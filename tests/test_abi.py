@@ -100,3 +100,12 @@ def test_band_geometry_is_pure_host_code():
     for band in range(0, 2304, 7):
         c, lg = capi.band_geometry(band)
         assert 2 <= c <= 18 and lg in (4, 8, 16, 32, 64, 128, 256) and c * lg >= 2 * band + 1 and c not in (13, 17)
+
+
+def test_host_worker_pool_under_concurrent_callers():
+    """The pool behind batch preparation (parallel index / descriptor / result passes): several threads submit
+    passes at once - producer and consumer of a pipelined batch, concurrent contexts - sizes below and above the
+    one-slice threshold, results checked inside the library.  Pure host code."""
+    lib = capi.load_library()
+    for callers, items in ((1, 0), (1, 1000), (1, 200_000), (2, 65_536), (6, 50_000), (8, 3_000)):
+        assert lib.gamx_host_selftest(callers, items) == 0, (callers, items)

@@ -2,6 +2,8 @@
 (include/gamx.h via gam_ngs_b200.capi), against the oracle on the same seeded inputs -
 bit-exact scores, coordinates, statuses and every edit op.  Nothing here reads /root/reference:
 the checker is the C restatement (oracle/bsw_oracle.c) plus the committed golden vectors."""
+import os
+
 import numpy as np
 import pytest
 
@@ -707,3 +709,23 @@ def test_plan_invalidated_by_a_later_batch_and_async_upload_contract(ctx):
         c = dict(a=a[ao[k]:ao[k + 1]], b=b[bo[k]:bo[k + 1]], begin_a=0, end_a=int(al[k]) - 1, begin_b=0, end_b=int(bl[k]) - 1,
                  band=64, gap=-8, force_start=False, force_end=False)
         assert int(res[k]["score"]) == oracle_expect(c)["score"], k
+
+
+def test_throughput_paths_on_small_batches():
+    """Small launches are routed for latency: a group of fewer than 2 x SM-count pairs whose longest pair has
+    1024+ rows runs on the CTA-per-pair kernel, and a launch of at most 8192 jobs walks every traceback on a warp.
+    The tests above therefore see the warp-level pair kernels of 32-lane stripes and the thread-per-job traceback
+    mostly through their big batches.  Here the golden vectors, every stripe width and one fuzz seed run again in a
+    process that has both routings switched off (the switches are read once per process), so the throughput
+    kernels face the same small adversarial cases."""
+    import subprocess
+    import sys
+    if os.environ.get("GAMX_TEST_INNER"):
+        pytest.skip("inner run")
+    env = dict(os.environ, GAMX_NO_LATENCY_MODE="1", GAMX_NO_TB_ALL_WARP="1", GAMX_TEST_INNER="1")
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-m", "gpu", "-x", "-q", "-p", "no:cacheprovider", "-k",
+                        "golden_vectors or all_stripe_widths or fuzz_every_clamp and 21 or reference_directly"],
+                       env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(here)))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-1000:]
