@@ -128,12 +128,67 @@ GAMX_HD uint32_t opaque(uint32_t v) {
 GAMX_HD uint32_t bitsel(uint32_t m, uint32_t a, uint32_t b) { return (a & m) | (b & ~m); }
 
 template <int C, int LG>
-struct alignas(16) GroupSmem16 {
+struct alignas(16) GroupSmem16Raw {
   uint64_t btab[(kTileSteps + LG + 15) / 16 * 16];  // rows of the tile: low word = job A's 4-byte Cd table, high word = job B's (staged in runs of 16)
   uint16_t asel[(kTileSteps + LG * C + 15) / 16 * 16 + 16];  // one PRMT selector per a-position of the tile (both jobs; runs of 16)
   uint16_t cap[2][C * LG];                       // latched "last column" cells (half-words of the lane's frame), [job][slot][lane]
   uint32_t dump[C * LG];                         // a lane's stripe, to read one slot back by index, [slot][lane]
 };
+
+// Bank conflicts between the lane groups of a warp.  Every step a lane loads its selectors (16 bits, half-word index
+// gl * (C - 1) + s with s common to the warp) and its row table (64 bits, index LG - 1 - gl + s) from ITS GROUP's
+// arrays, so which banks a warp instruction touches depends on the distance between two groups' arrays.  With the
+// natural struct size that distance is a multiple of 32 words for C = 18 / LG = 4 (band 29..35) and for a few other
+// geometries: eight groups on the same banks, 8-way conflicts of every selector load (ncu: 4.6 short-scoreboard
+// stall cycles per issue, band 32 at half the rate of band 64).  group_pad_bytes() picks, at compile time, the
+// padding (a multiple of 16 bytes) after each group's arrays that minimises the modelled conflict degree.
+constexpr int smem_conflict_degree(const int* words, int n) {
+  int worst = 0;
+  for (int i = 0; i < n; i++) {
+    int distinct = 0;  // distinct words on lane i's bank, counted at the first lane that holds each word
+    for (int j = 0; j < n; j++) {
+      if (((words[j] ^ words[i]) & 31) != 0) continue;
+      bool first = true;
+      for (int k = 0; k < j; k++) first = first && words[k] != words[j];
+      distinct += first ? 1 : 0;
+    }
+    worst = distinct > worst ? distinct : worst;
+  }
+  return worst;
+}
+constexpr int smem_group_cost(int c, int lg, int stride_words) {
+  int cost = 0;
+  for (int par = 0; par < 2; par++) {  // selector loads: both alignments of the half-word index
+    int words[32] = {};
+    for (int lane = 0; lane < 32; lane++) words[lane] = (lane / lg) * stride_words + (((lane % lg) * (c - 1) + par) >> 1);
+    cost += 8 * smem_conflict_degree(words, 32);  // (about C / 2 of them per step against one table load)
+  }
+  for (int half = 0; half < 2; half++) {  // the 64-bit table load: two half-warp transactions
+    int words[32] = {};
+    for (int q = 0; q < 16; q++) {
+      const int lane = half * 16 + q, e = lg - 1 - lane % lg;
+      words[2 * q] = (lane / lg) * stride_words + 2 * e;
+      words[2 * q + 1] = words[2 * q] + 1;
+    }
+    cost += smem_conflict_degree(words, 32);
+  }
+  return cost;
+}
+template <int C, int LG>
+constexpr int group_pad_bytes() {
+  if (LG >= 32) return 0;  // one group per warp
+  const int base = (int)sizeof(GroupSmem16Raw<C, LG>);
+  int best = 0, best_cost = smem_group_cost(C, LG, base / 4);
+  for (int pad = 16; pad < 128; pad += 16) {
+    const int cost = smem_group_cost(C, LG, (base + pad) / 4);
+    if (cost < best_cost) { best_cost = cost; best = pad; }
+  }
+  return best;
+}
+template <int N> struct SmemPad { uint8_t pad_[N]; };
+template <> struct SmemPad<0> {};
+template <int C, int LG>
+struct alignas(16) GroupSmem16 : GroupSmem16Raw<C, LG>, SmemPad<group_pad_bytes<C, LG>()> {};
 template <int C, int LG>
 struct WarpSmem16 {
   GroupSmem16<C, LG> g[LG >= 32 ? 1 : 32 / LG];
