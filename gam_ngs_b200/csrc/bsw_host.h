@@ -102,6 +102,9 @@ inline void geometry_for_band(uint64_t band, bool dirs, int* c_out, int* lg_out)
     // GCUPS with C = 17, 4735 with C = 18) - take one slot more
     static const bool no_even = getenv("GAMX_NO_EVEN_C") != nullptr;  // experiments only
     if (!no_even && (c == 13 || c == 17) && c + 1 <= kMaxC) c++;
+    // (9-slot stripes of several groups per warp keep 4-way conflicts of the selector loads - a lane stride of 4
+    //  words leaves 8 banks whatever the distance between the groups' arrays, bsw_warp16.h group_pad_bytes - but
+    //  10 slots measured no better overall: uniform 1 kb pairs at band 16 +1..2 %, mixed lengths -9 %)
     if (forced_c > c && forced_c <= kMaxC) c = forced_c;
     if (c > kMaxC) continue;
     if (forced && lg != forced && (y + forced - 1) / forced <= (uint64_t)kMaxC) continue;

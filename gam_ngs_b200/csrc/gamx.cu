@@ -254,43 +254,79 @@ tb_kernel(const DevJob* __restrict__ jobs, int n_jobs, const uint32_t* __restric
   results[j] = R;
 }
 
-// Long jobs: one job per WARP.  Every lane runs the same walk (no divergence, no state exchange);
-// what the lanes share is the fetch: when the walk needs a word that is not cached, lane i loads the
-// word of step block blk - i of the current band column, so one round trip covers 32 step blocks
-// (512 rows of a DIAG run) instead of one, and the words then come from a shuffle.
-struct WarpFetch {
+// One job per WARP.  Every lane runs the same walk (no divergence, no state exchange); what the lanes share
+// is the fetch.  A word holds 16 rows of one band column, a DIAG move stays in its column and a gap move
+// changes the column inside the same step block, so two shapes of a 32-word window are useful:
+//   column mode: lane i holds step block cb - i of the current column - one round trip per 512 rows of a
+//                clean alignment;
+//   tile mode:   lane i holds step block cb - i / 8 of column cj - 3 + i % 8 (8 columns x 4 step blocks) - for
+//                gap-heavy paths (the merge stage aligns every block chain in both orientations, and the wrong
+//                one pairs unrelated sequence), where every gap move would miss the column window.
+// (Measured on the merge stage: config 4 0.131 -> 0.123 s, config 1 unchanged - a walk is mostly its ~100
+//  dependent instructions per 16-row word, not its fetches: profiles/r3l_tbw_lines.txt.)
+// A miss by a column change within 64 rows of the last fetch switches to tile mode; two tile windows in a
+// row left through their bottom in the column they were fetched for switch back.  The decisions depend on
+// the path only, so all lanes take them alike.  Load: the word of (step block, slot k, lane l) of the job.
+struct LoadWord32 {
   const uint32_t* dirs;
   int C, LG;
-  int cb, ck, cl;   // cached: step blocks cb .. cb-31 of column (ck, cl); cb < 0: nothing
-  uint32_t mine;    // this lane's word: step block cb - lane
-  __device__ __forceinline__ uint32_t operator()(int blk, int k, int l) {
-    if (k != ck || l != cl || blk > cb || blk < cb - 31) {  // (uniform: all lanes walk the same path)
-      cb = blk; ck = k; cl = l;
-      const int b = blk - (int)(threadIdx.x & 31);
-      mine = b >= 0 ? dirs[((uint32_t)b * (uint32_t)C + (uint32_t)k) * (uint32_t)LG + (uint32_t)l] : 0u;
-    }
-    return __shfl_sync(0xffffffffu, mine, cb - blk);
+  __device__ __forceinline__ uint32_t operator()(int b, int k, int l) const {
+    return dirs[((uint32_t)b * (uint32_t)C + (uint32_t)k) * (uint32_t)LG + (uint32_t)l];
   }
 };
-
 // the same for half `half` of a 16x2 pair region (two 8-step blocks per 16-step word)
-struct WarpFetch16 {
+struct LoadWord16 {
   const uint32_t* dirs;
   int C, LG, half;
-  int cb, ck, cl;
-  uint32_t mine;
+  __device__ __forceinline__ uint32_t operator()(int b, int k, int l) const {
+    const uint32_t w0 = dirs[((uint32_t)(2 * b) * (uint32_t)C + (uint32_t)k) * (uint32_t)LG + (uint32_t)l];
+    const uint32_t w1 = dirs[((uint32_t)(2 * b + 1) * (uint32_t)C + (uint32_t)k) * (uint32_t)LG + (uint32_t)l];
+    return pair_word16(w0, w1, half);
+  }
+};
+template <class Load>
+struct WarpFetch {
+  Load load;
+  int C, LG;
+  int mode = 0;          // 0 column, 1 tile
+  int cb = -1, cj = -1;  // window origin: step block cb (and the ones below it), band column cj; cb < 0: nothing cached
+  int streak = 0;
+  uint32_t mine = 0u;
+  __device__ __forceinline__ WarpFetch(const Load& ld, int c, int lg) : load(ld), C(c), LG(lg) {}
   __device__ __forceinline__ uint32_t operator()(int blk, int k, int l) {
-    if (k != ck || l != cl || blk > cb || blk < cb - 31) {
-      cb = blk; ck = k; cl = l;
-      const int b = blk - (int)(threadIdx.x & 31);
-      mine = 0u;
-      if (b >= 0) {
-        const uint32_t w0 = dirs[((uint32_t)(2 * b) * (uint32_t)C + (uint32_t)k) * (uint32_t)LG + (uint32_t)l];
-        const uint32_t w1 = dirs[((uint32_t)(2 * b + 1) * (uint32_t)C + (uint32_t)k) * (uint32_t)LG + (uint32_t)l];
-        mine = pair_word16(w0, w1, half);
+    const int j = l * C + k;
+    int src;
+    bool hit;
+    if (mode == 0) {
+      src = cb - blk;
+      hit = j == cj && (unsigned)src < 32u;
+    } else {
+      const int dj = j - cj + 3, db = cb - blk;
+      src = db * 8 + dj;
+      hit = (unsigned)dj < 8u && (unsigned)db < 4u;
+    }
+    if (!hit) {  // (uniform: all lanes walk the same path)
+      if (mode == 0) {
+        if (cb >= 0 && j != cj && blk >= cb - 3) { mode = 1; streak = 0; }
+      } else if (j == cj) {
+        if (++streak >= 2) mode = 0;
+      } else {
+        streak = 0;
+      }
+      cb = blk; cj = j;
+      const int lane = (int)(threadIdx.x & 31);
+      if (mode == 0) {
+        const int b = blk - lane;
+        mine = b >= 0 ? load(b, k, l) : 0u;
+        src = 0;
+      } else {
+        const int jj = j + (lane & 7) - 3, b = blk - (lane >> 3);
+        const int l2 = jj / C;
+        mine = (b >= 0 && jj >= 0 && jj < C * LG) ? load(b, jj - l2 * C, l2) : 0u;
+        src = 3;
       }
     }
-    return __shfl_sync(0xffffffffu, mine, cb - blk);
+    return __shfl_sync(0xffffffffu, mine, src);
   }
 };
 
@@ -307,10 +343,10 @@ tbw_kernel(const DevJob* __restrict__ jobs, int n_jobs, const uint32_t* __restri
   const bool leader = (threadIdx.x & 31) == 0;
   const int lay = R.has_match;  // 0 = 32-bit layout, 1 + h = half h of a 16x2 pair region
   if (lay == 0) {
-    WarpFetch f{dirs + (uint64_t)j * stride, c, lg, -1, -1, -1, 0u};
+    WarpFetch<LoadWord32> f(LoadWord32{dirs + (uint64_t)j * stride, c, lg}, c, lg);
     k1_traceback_t(f, c, R.end_i, R.end_j, Jp->p0, leader && (Jp->mode & 0xff) == kModeFull, ops + Jp->ops_word, Jp->ops_cap, R);
   } else {
-    WarpFetch16 f{dirs + (uint64_t)(j & ~1) * stride, c, lg, lay - 1, -1, -1, -1, 0u};
+    WarpFetch<LoadWord16> f(LoadWord16{dirs + (uint64_t)(j & ~1) * stride, c, lg, lay - 1}, c, lg);
     k1_traceback_t(f, c, R.end_i, R.end_j, Jp->p0, leader && (Jp->mode & 0xff) == kModeFull, ops + Jp->ops_word, Jp->ops_cap, R);
   }
   if (leader) {
@@ -1166,7 +1202,10 @@ struct Group {
   uint32_t job_off = 0;  // offset into the device job array (DevJob or GenJob)
   int grid = 0;
   uint64_t min_x = ~0ull, max_x = 0;  // rows of the shortest / longest job (which traceback kernels are needed)
-  uint64_t wave_jobs = 0;  // dirs groups: jobs per launch (their direction words fill one scratch half)
+  // launches ("waves") of the group: jobs [w0, w0 + n) of the group, job j of the wave owns the direction words
+  // [j * stride, + stride) of one scratch half
+  struct Wave { uint64_t w0, n, stride; };
+  std::vector<Wave> waves;
 };
 
 struct DevPlan {
@@ -1186,6 +1225,7 @@ struct DevPlan {
 }  // namespace
 
 struct gamx_plan {
+  bool sorted_by_cost = false;  // the groups' jobs are in descending order of cost (plan_build)
   gamx_ctx* ctx = nullptr;
   uint64_t n = 0;
   std::unique_ptr<Prepared[]> preps;  // uninitialised storage, filled in parallel
@@ -1842,7 +1882,7 @@ static int plan_build(gamx_ctx* ctx, const gamx_job* jobs, uint64_t n, gamx_plan
     // only matters for the tail of a launch, and sequential access to the job records is much faster
     uint64_t cmin = ~0ull, cmax = 0;
     for (uint32_t i : order) { cmin = std::min(cmin, preps[i].cells); cmax = std::max(cmax, preps[i].cells); }
-    if (!order.empty() && cmax > cmin + cmin / 4) sort_by_cost_desc(order, preps);
+    if (!order.empty() && cmax > cmin + cmin / 4) { sort_by_cost_desc(order, preps); pl->sorted_by_cost = true; }
   }
   std::vector<std::vector<uint32_t>> per_dev(nd);
   if (nd == 1) {
@@ -2037,19 +2077,42 @@ static int plan_upload(gamx_plan* pl) {
     for (Group& g : dp.groups) {
       if (!g.c) continue;
       if (g.dirs && g.max_dir_words) {
-        g.wave_jobs = std::min<uint64_t>((half_words / g.max_dir_words) & ~1ull, ((uint64_t)g.job_idx.size() + 1) & ~1ull);  // even: pairs stay together
+        uint64_t wave_jobs = std::min<uint64_t>((half_words / g.max_dir_words) & ~1ull, ((uint64_t)g.job_idx.size() + 1) & ~1ull);  // even: pairs stay together
         // a big group is cut into at least four waves even when one would fit, so that all but the last
         // traceback launch run beside a fill launch (needs the second scratch half; every wave still
         // holds several times the resident jobs)
+        uint64_t cap_jobs = ~0ull;
         if (dp.two_halves_ok) {
           const uint64_t pairs_per_block = g.lg > 32 ? 1 : k1_jobs_per_block(g.lg);
           const uint64_t resident = (uint64_t)g.grid * pairs_per_block;
           const uint64_t quarter = (((uint64_t)g.job_idx.size() + 3) / 4 + 1) & ~1ull;
-          if (quarter >= 4 * resident) g.wave_jobs = std::min(g.wave_jobs, quarter);
+          if (quarter >= 4 * resident) { wave_jobs = std::min(wave_jobs, quarter); cap_jobs = quarter; }
         }
-        dp.n_launches += (uint32_t)((g.job_idx.size() + g.wave_jobs - 1) / g.wave_jobs);
+        g.waves.clear();
+        const uint64_t n = g.job_idx.size();
+        if (pl->sorted_by_cost && wave_jobs < n) {
+          // Jobs in descending order of cost and more than one wave: the region size of a wave is that of ITS
+          // largest job, not of the group's, so the waves of the short jobs hold many more of them (a mixed-length
+          // batch at band 1024 took 36 waves of 2870 jobs, most of them a fraction of a resident set of work)
+          const Prepared* preps = pl->preps.get();
+          for (uint64_t w0 = 0; w0 < n;) {
+            uint64_t smax = 0, k = w0;
+            while (k < n && k - w0 < cap_jobs) {
+              const uint64_t s2 = std::max(smax, std::max<uint64_t>(preps[g.job_idx[k]].dir_words, 1));
+              if (k >= w0 + 2 && s2 * ((k - w0 + 2) & ~(uint64_t)1) > half_words) break;  // (even count: a pair writes both regions)
+              smax = s2; k++;
+            }
+            uint64_t cnt = k - w0;
+            if (k < n && (cnt & 1)) cnt--;  // pairs stay together
+            g.waves.push_back({w0, cnt, smax});
+            w0 += cnt;
+          }
+        } else {
+          for (uint64_t w0 = 0; w0 < n; w0 += wave_jobs) g.waves.push_back({w0, std::min(wave_jobs, n - w0), g.max_dir_words});
+        }
+        dp.n_launches += (uint32_t)g.waves.size();
       } else {
-        g.wave_jobs = g.job_idx.size();
+        g.waves.assign(1, {0, (uint64_t)g.job_idx.size(), 0});
         dp.n_launches++;
       }
     }
@@ -2058,8 +2121,8 @@ static int plan_upload(gamx_plan* pl) {
     uint64_t used_words = 0;  // what a half really has to hold
     for (const Group& g : dp.groups)
       if (g.c && g.dirs && g.max_dir_words) {
-        dp.two_halves = dp.two_halves || g.wave_jobs < g.job_idx.size();
-        used_words = std::max(used_words, g.wave_jobs * g.max_dir_words);
+        dp.two_halves = dp.two_halves || g.waves.size() > 1;
+        for (const Group::Wave& w : g.waves) used_words = std::max<uint64_t>(used_words, ((w.n + 1) & ~(uint64_t)1) * w.stride);
       }
     dp.dirs_words = dp.two_halves ? std::min(half_words, used_words) : (want_words ? half_words : 0);
     if (int rc = ensure_dev(ctx, sl.dirs, dp.dirs_words * (dp.two_halves ? 8 : 4) + 64)) return rc;
@@ -2158,8 +2221,9 @@ static int plan_run_locked(gamx_plan* pl) {
       const DevJob* dj = (const DevJob*)sl.jobs.p + g.job_off;
       const uint64_t n = g.job_idx.size();
       const bool walk = g.dirs && g.max_dir_words;
-      for (uint64_t w0 = 0; w0 < n; w0 += g.wave_jobs) {
-        const uint64_t nw = std::min(g.wave_jobs, n - w0);
+      (void)n;
+      for (const Group::Wave& wv : g.waves) {
+        const uint64_t w0 = wv.w0, nw = wv.n, wstride = wv.stride;
         const int h = (walk && dp.two_halves) ? (int)(wave & 1) : 0;
         cudaStream_t fs = h ? sl.stream2 : sl.stream;  // fill stream of this wave
         uint32_t* half = (uint32_t*)sl.dirs.p + (uint64_t)h * dp.dirs_words;
@@ -2170,9 +2234,9 @@ static int plan_run_locked(gamx_plan* pl) {
         gw.grid = (int)std::min<uint64_t>((uint64_t)g.grid, (nw + pairs_per_block - 1) / pairs_per_block);
         int* const counters = (int*)sl.counters.p + (size_t)kCountersPerLaunch * launch;
         const int rc = g.lg > 32 ? launch_k2(ctx, d, fs, gw, (int)nw, dj + w0, counters, half,
-                                             g.max_dir_words, (uint32_t*)sl.ops.p, res + w0)
+                                             wstride, (uint32_t*)sl.ops.p, res + w0)
                                  : launch_k1(ctx, d, fs, gw, (int)nw, dj + w0, counters, (int*)sl.retry.p + retry_off, half,
-                                             g.max_dir_words, (uint32_t*)sl.ops.p, res + w0);
+                                             wstride, (uint32_t*)sl.ops.p, res + w0);
         if (rc) return rc;
         if (g.lg <= 32) { retry_off += nw / 2 + 1; if (use_s16()) pl->launches++; }
         pl->launches++; launch++;
@@ -2183,14 +2247,14 @@ static int plan_run_locked(gamx_plan* pl) {
           const int warp_rows = (tb_all_warp && nw <= kTbAllWarpJobs) ? 0 : kTbWarpRows;  // small launch: every walk on a warp
           if (g.min_x < (uint64_t)warp_rows) {  // short jobs: one per thread
             tb_kernel<<<(unsigned)((nw + kTbThreads - 1) / kTbThreads), kTbThreads, 0, sl.tb_stream>>>(
-                dj + w0, (int)nw, half, g.max_dir_words, g.c, g.lg, (uint32_t*)sl.ops.p, res + w0, warp_rows);
+                dj + w0, (int)nw, half, wstride, g.c, g.lg, (uint32_t*)sl.ops.p, res + w0, warp_rows);
             CU(cudaGetLastError());
             pl->launches++;
           }
           if (g.max_x >= (uint64_t)warp_rows) {  // long jobs: one per warp
             const uint64_t warps_per_block = kTbwThreads / 32;
             tbw_kernel<<<(unsigned)((nw + warps_per_block - 1) / warps_per_block), kTbwThreads, 0, sl.tb_stream>>>(
-                dj + w0, (int)nw, half, g.max_dir_words, g.c, g.lg, (uint32_t*)sl.ops.p, res + w0, warp_rows);
+                dj + w0, (int)nw, half, wstride, g.c, g.lg, (uint32_t*)sl.ops.p, res + w0, warp_rows);
             CU(cudaGetLastError());
             pl->launches++;
           }

@@ -159,8 +159,11 @@ GAMX_API const char* gamx_contig_name(const gamx_ctx* ctx, uint32_t id);
 GAMX_API int64_t gamx_add_contigs(gamx_ctx* ctx, const uint8_t* codes, const uint64_t* lengths, uint64_t n);
 /* Same, but only enqueues the copies and the pack kernel on the devices' streams and returns: the
  * upload then overlaps the host-side planning of the next gamx_align_batch, which is stream-ordered
- * behind it.  The copy proceeds in pieces of ~128 MB that are enqueued as the batches need them, so a
- * pipelined gamx_align_batch starts computing on the first contigs while later ones still cross PCIe.
+ * behind it.  The copy proceeds in pieces of ~128 MB (shorter ones first and last), all enqueued by this
+ * call, each followed by its pack launch on a second stream; a pipelined gamx_align_batch waits per chunk for
+ * the pieces its jobs refer to, so it computes on the first contigs while later ones still cross PCIe.
+ * (A context drives ~20 streams per device: gamx_create sets CUDA_DEVICE_MAX_CONNECTIONS=32 if it is unset,
+ * which takes effect only if the process has not created its CUDA context yet - see INTEGRATION.md 3a.)
  * `codes` must be PINNED host memory and must stay valid and unchanged until the next gamx_align_batch,
  * gamx_align_batch_cigar or gamx_plan_create call on this context has returned: those calls finish the upload
  * before they return on every path - errors, empty batches and batches that never refer to the last contigs
