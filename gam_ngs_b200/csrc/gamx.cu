@@ -201,8 +201,11 @@ struct CtaPolicy {
   __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
 
+// (512 resident threads per SM asked of the compiler, i.e. at most 128 registers: without the bound ptxas takes up to
+//  253 registers for the wide direction-storing variants in some builds - the optimiser's parallel split makes the
+//  build non-deterministic, DESIGN.md section 8 - and band 1024 then runs at 2230 instead of 2720 GCUPS)
 template <int C, int LG, bool DIRS>
-__global__ void __launch_bounds__(LG)
+__global__ void __launch_bounds__(LG, 512 / LG)
 k2_kernel(const DevJob* __restrict__ jobs, int n_jobs, int* __restrict__ counter, SeqStore store,
           uint32_t* __restrict__ dirs, uint64_t group_stride, uint32_t* __restrict__ ops,
           DevResult* __restrict__ results) {
