@@ -694,6 +694,10 @@ struct Slot {
   // direction scratch: ev_fill[h] = half h is filled, ev_tb[h] = half h has been walked
   cudaStream_t tb_stream = nullptr;
   cudaEvent_t ev_fill[2] = {nullptr, nullptr}, ev_tb[2] = {nullptr, nullptr};
+  // a wave with short and long jobs has two traceback launches (thread per job / warp per job): the second one
+  // runs beside the first on tbw_stream, ev_tbw[h] joins it back into tb_stream
+  cudaStream_t tbw_stream = nullptr;
+  cudaEvent_t ev_tbw[2] = {nullptr, nullptr};
   // odd waves are launched on stream2, so that their blocks move in while the persistent blocks of the
   // previous wave drain (no idle tail at a wave boundary); ev_ready = inputs of the run are on the device
   cudaStream_t stream2 = nullptr;
@@ -1459,6 +1463,9 @@ int gamx_create(gamx_ctx** out, const int* device_ids, int n_devices) {
     for (int k = 0; ok && k < kSlots; k++)
       ok = cudaStreamCreateWithFlags(&d.s[k].stream, cudaStreamNonBlocking) == cudaSuccess &&
            cudaStreamCreateWithFlags(&d.s[k].tb_stream, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaStreamCreateWithFlags(&d.s[k].tbw_stream, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&d.s[k].ev_tbw[0], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&d.s[k].ev_tbw[1], cudaEventDisableTiming) == cudaSuccess &&
            cudaStreamCreateWithFlags(&d.s[k].stream2, cudaStreamNonBlocking) == cudaSuccess &&
            cudaStreamCreateWithFlags(&d.s[k].gen_stream, cudaStreamNonBlocking) == cudaSuccess &&
            cudaEventCreateWithFlags(&d.s[k].ev_gen, cudaEventDisableTiming) == cudaSuccess &&
@@ -1507,7 +1514,8 @@ void gamx_destroy(gamx_ctx* ctx) {
       for (PinBuf* b : sp) if (b->p) cudaFreeHost(b->p);
       cudaEventDestroy(sl.ev0);
       cudaEventDestroy(sl.ev1);
-      for (int h = 0; h < 2; h++) { cudaEventDestroy(sl.ev_fill[h]); cudaEventDestroy(sl.ev_tb[h]); }
+      for (int h = 0; h < 2; h++) { cudaEventDestroy(sl.ev_fill[h]); cudaEventDestroy(sl.ev_tb[h]); cudaEventDestroy(sl.ev_tbw[h]); }
+      cudaStreamDestroy(sl.tbw_stream);
       cudaEventDestroy(sl.ev_ready);
       cudaEventDestroy(sl.ev_gen);
       cudaStreamDestroy(sl.gen_stream);
@@ -2256,9 +2264,16 @@ static int plan_run_locked(gamx_plan* pl) {
           }
           if (g.max_x >= (uint64_t)warp_rows) {  // long jobs: one per warp
             const uint64_t warps_per_block = kTbwThreads / 32;
-            tbw_kernel<<<(unsigned)((nw + warps_per_block - 1) / warps_per_block), kTbwThreads, 0, sl.tb_stream>>>(
+            const bool both = g.min_x < (uint64_t)warp_rows;  // beside the thread-per-job launch, not behind it
+            cudaStream_t ws = both ? sl.tbw_stream : sl.tb_stream;
+            if (both) CU(cudaStreamWaitEvent(ws, sl.ev_fill[h], 0));
+            tbw_kernel<<<(unsigned)((nw + warps_per_block - 1) / warps_per_block), kTbwThreads, 0, ws>>>(
                 dj + w0, (int)nw, half, wstride, g.c, g.lg, (uint32_t*)sl.ops.p, res + w0, warp_rows);
             CU(cudaGetLastError());
+            if (both) {
+              CU(cudaEventRecord(sl.ev_tbw[h], ws));
+              CU(cudaStreamWaitEvent(sl.tb_stream, sl.ev_tbw[h], 0));
+            }
             pl->launches++;
           }
           CU(cudaEventRecord(sl.ev_tb[h], sl.tb_stream));
